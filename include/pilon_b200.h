@@ -1,0 +1,251 @@
+/*
+ * pilon_b200.h -- C ABI of the B200-native pileup + BaseCall engine (libpilonb200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of broadinstitute/pilon: everything the Scala
+ * class `PileUpRegion` and its per-locus `PileUp` / `PileUp.BaseCall` view compute
+ * (reference: src/main/scala/org/broadinstitute/pilon/PileUpRegion.scala, PileUp.scala,
+ * BaseSum.scala, Utils.scala) plus pass 1 of `GenomeRegion.postProcess`
+ * (GenomeRegion.scala:214-272) and the fragCoverage bookkeeping of `GenomeRegion.processBam`
+ * (GenomeRegion.scala:287-300).  The reference has no FFI of its own (pure JVM); the entry
+ * points below are what a re-plumbed `BamFile.process` (BamFile.scala:108-148) and a
+ * `PileUpRegion` facade would bind through Panama / JNA -- see INTEGRATION.md.
+ *
+ * Conventions: plain C, no exceptions, no torch types.  Every function returns PB_OK (0) or a
+ * negative PB_ERR_* code; pb_last_error() returns a thread-local message for the last failure.
+ * An engine handle is NOT thread-safe; use one handle per (GPU, stream).  All citations
+ * "File.scala:a-b" refer to the reference tree above.
+ */
+#ifndef PILON_B200_H
+#define PILON_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_ABI_VERSION 1
+
+/* ---- status codes ---------------------------------------------------------------------- */
+#define PB_OK                 0
+#define PB_ERR_INVALID       -1   /* bad argument / call order                                */
+#define PB_ERR_CUDA          -2   /* CUDA runtime failure (message has the cudaError string)  */
+#define PB_ERR_UNSORTED      -3   /* reads of a batch are not sorted by pos                   */
+#define PB_ERR_UNSUPPORTED   -4   /* feature gated off (long-read branches)    */
+#define PB_ERR_OOM           -5
+#define PB_ERR_HASH          -6   /* 32-bit insertion-hash collision detected (never seen)    */
+
+/* ---- configuration: the `object Pilon` vars the path reads (Pilon.scala:28-73) ---------- */
+typedef struct pb_config {
+    int32_t min_qual;        /* Pilon.minQual      used PileUp.scala:77            default 0   */
+    int32_t min_mq;          /* Pilon.minMq        used PileUpRegion.scala:107     default 0   */
+    int32_t flank;           /* Pilon.flank        used PileUpRegion.scala:34,118  default 10  */
+    int32_t default_qual;    /* Pilon.defaultQual  used PileUpRegion.scala:115     default 10  */
+    int32_t min_min_depth;   /* Pilon.minMinDepth  PileUp.scala:213, GenomeRegion.scala:223  5 */
+    int32_t old_indel;       /* Pilon.oldIndel     used PileUp.scala:223           default 0   */
+    int32_t fix_amb;         /* Pilon.iupac || Pilon.fixAmb  GenomeRegion.scala:235 default 0  */
+    int32_t reserved;
+    double  min_depth;       /* Pilon.minDepth     used GenomeRegion.scala:221-224 default 0.1 */
+} pb_config;
+
+/* ---- one batch of reads, struct-of-arrays ------------------------------------------------
+ * What `BamFile.process` (BamFile.scala:126-139) would have fed to `PileUpRegion.addRead` one
+ * SAMRecord at a time, for reads that passed `validateRead` (BamFile.scala:101-105).
+ * Reads MUST be sorted by `pos` ascending (a coordinate-sorted BAM query is).
+ *
+ * Per-read flag bits (from SAMRecord accessors used at PileUpRegion.scala:103-111): */
+#define PB_F_PAIRED         0x01  /* getReadPairedFlag                                        */
+#define PB_F_PROPER         0x02  /* getProperPairFlag                                        */
+#define PB_F_MATE_SAME_REF  0x04  /* getReferenceIndex == getMateReferenceIndex               */
+#define PB_F_HAS_QUALS      0x08  /* getBaseQualities.size > 0 (BAM: first qual byte != 0xFF) */
+#define PB_F_UNMAPPED       0x10  /* getReadUnmappedFlag (getAlignmentEnd == 0)               */
+#define PB_F_REVERSE        0x20  /* getReadNegativeStrandFlag (BamFile.scala:137 only)       */
+
+/* CIGAR ops are BAM-encoded: len << 4 | op, op = 0..8 for "MIDNSHP=X". */
+
+/* Base / quality packing.  Each read owns a run of `read_len` bases starting at base index
+ * seq_off[r] (a multiple of 4) inside the batch:
+ *   bases2[i >> 2] >> (2 * (i & 3)) & 3   = 0,1,2,3 for A,C,G,T
+ *   quals[i]                               = phred quality, 0..127; bit 7 set marks a base the
+ *                                            per-locus counters can never count: a read byte that
+ *                                            is not exactly 'A','C','G','T' (PileUp.scala:46-52) or
+ *                                            a quality byte >= 128 (a negative JVM Byte).
+ * Every base with bit 7 set has one entry in the sparse exception table (sorted by base index)
+ * holding its original ASCII letter and raw quality byte, so the rare paths that need them
+ * (indel strings, indel anchor qualities, left-shift comparisons) stay bit-exact.
+ * For reads without PB_F_HAS_QUALS the quality bytes carry only bit 7. */
+#define PB_MEM_HOST    0   /* pointers are host memory (pinned preferred); engine copies H2D   */
+#define PB_MEM_DEVICE  1   /* pointers are device memory on the engine's GPU; used in place    */
+
+typedef struct pb_batch {
+    int64_t n_reads;
+    int64_t n_cigar;            /* total CIGAR ops                                            */
+    int64_t n_seq;              /* total base slots incl. padding; multiple of 4; < 2^32      */
+    int64_t n_exc;              /* exception table entries                                    */
+    const int32_t*  pos;        /* [n_reads]   getAlignmentStart (1-based)                    */
+    const int32_t*  tlen;       /* [n_reads]   getInferredInsertSize                          */
+    const int32_t*  read_len;   /* [n_reads]   getReadLength (SEQ length)                     */
+    const uint8_t*  mapq;       /* [n_reads]   getMappingQuality                              */
+    const uint8_t*  flags;      /* [n_reads]   PB_F_*                                         */
+    const uint32_t* cigar_off;  /* [n_reads+1] CSR offsets into cigar                         */
+    const uint32_t* cigar;      /* [n_cigar]                                                  */
+    const uint32_t* seq_off;    /* [n_reads]   first base index of the read (multiple of 4)   */
+    const uint8_t*  quals;      /* [n_seq]                                                    */
+    const uint8_t*  bases2;     /* [n_seq / 4]                                                */
+    const uint32_t* exc_idx;    /* [n_exc] sorted base indices                                */
+    const uint8_t*  exc_base;   /* [n_exc] original ASCII read byte                           */
+    const uint8_t*  exc_qual;   /* [n_exc] original quality byte                              */
+    int32_t mem;                /* PB_MEM_HOST | PB_MEM_DEVICE                                */
+    int32_t reserved;
+} pb_batch;
+
+/* ---- per-locus call record (PileUp.BaseCall, PileUp.scala:132-167) -----------------------
+ * Computed on the FINAL per-locus state, i.e. after pass 1 spilled homozygous-deletion counts
+ * into the deleted loci (GenomeRegion.scala:259-264) -- what Vcf.writeRecord would see.
+ *   bits  0..2  base      0..3 = A,C,G,T ; 4 = 'N' (n == 0)          (:138)
+ *   bits  3..4  altBase   0..3                                        (:140)
+ *   bit   5     homo                                                  (:147)
+ *   bits  6..7  indel     0 none, 1 insertion, 2 deletion             (:151-162)
+ *   bit   8     homoIndel                                             (:151-162)
+ *   bit   9     called                                                (:165)
+ *   bit   10    highConfidence (q >= 10)                              (:167)
+ *   bits 16..63 score (48 bit, non-negative)                          (:148)            */
+#define PB_CALL_BASE(c)      ((int)((c) & 7))
+#define PB_CALL_ALT(c)       ((int)(((c) >> 3) & 3))
+#define PB_CALL_HOMO(c)      ((int)(((c) >> 5) & 1))
+#define PB_CALL_INDEL(c)     ((int)(((c) >> 6) & 3))
+#define PB_CALL_HOMOINDEL(c) ((int)(((c) >> 8) & 1))
+#define PB_CALL_CALLED(c)    ((int)(((c) >> 9) & 1))
+#define PB_CALL_HICONF(c)    ((int)(((c) >> 10) & 1))
+#define PB_CALL_SCORE(c)     ((int64_t)((c) >> 16))
+
+/* Pass-1 disposition flags (GenomeRegion.scala:45-49, 84-88, 255-271) */
+#define PB_FL_CONFIRMED  0x01
+#define PB_FL_CHANGED    0x02   /* SNP, INS or DEL                                            */
+#define PB_FL_AMBIGUOUS  0x04   /* AMB                                                        */
+#define PB_FL_DELETED    0x08
+#define PB_FL_KIND_SHIFT 4      /* bits 4..5: 0 SNP, 1 INS, 2 DEL, 3 AMB (valid if CHANGED|AMBIGUOUS) */
+#define PB_KIND_SNP 0
+#define PB_KIND_INS 1
+#define PB_KIND_DEL 2
+#define PB_KIND_AMB 3
+
+/* One entry per (locus, kind) that received at least one insertion / deletion. */
+typedef struct pb_indel {
+    int32_t  locus_index;   /* 0-based index into the region                                  */
+    int32_t  kind;          /* 1 insertion, 2 deletion                                        */
+    int32_t  list_len;      /* insertionList / deletionList length (PileUp.scala:40-41)       */
+    int32_t  win_count;     /* occurrences of the most frequent string                        */
+    int32_t  win_len;       /* its length                                                     */
+    int32_t  win_has_n;     /* contains 'N' (PileUp.scala:222)                                */
+    int64_t  str_off;       /* offset of its bytes in pb_region_result.indel_bytes            */
+} pb_indel;
+
+/* ---- region results ------------------------------------------------------------------------
+ * All array pointers are HOST memory owned by the caller, each `size` elements long unless noted;
+ * a NULL pointer means "not wanted" (no device->host copy is made for it). */
+typedef struct pb_region_result {
+    /* scalars, always filled */
+    int64_t size;            /* stop + 1 - start                               Region.scala:27 */
+    int64_t base_count;      /* PileUpRegion.baseCount                   PileUpRegion.scala:32 */
+    int64_t coverage;        /* roundDiv(baseCount, size)                PileUpRegion.scala:36 */
+    int64_t aligned_bases;   /* sum of M/=/X lengths of the submitted reads (bench metric)     */
+    int32_t read_count;      /* PileUpRegion.readCount                   PileUpRegion.scala:33 */
+    int32_t min_depth;       /* GenomeRegion.minDepth                GenomeRegion.scala:221-224 */
+    int32_t unknown_ops;     /* CIGAR ops that hit the println at    PileUpRegion.scala:211-212 */
+    int32_t dropped_oob;     /* indels whose left shift left the region (JVM: AIOOBE crash)    */
+    int64_t n_indels;        /* entries written to `indels`                                    */
+    int64_t n_indel_bytes;   /* bytes written to `indel_bytes`                                 */
+
+    /* PileUp counters (PileUp.scala:26-39), final state */
+    int32_t* base_count4;    /* [size*4] baseCount.sums, locus-major (values fit 31 bits)      */
+    int64_t* qual_sum4;      /* [size*4] qualSum.sums, locus-major                             */
+    int32_t* mq_sum;
+    int32_t* q_sum;
+    int32_t* phys_cov;       /* after computePhysCov                 PileUpRegion.scala:90-100 */
+    int32_t* insert_size;    /* after computePhysCov                                           */
+    int32_t* bad_pair;
+    int32_t* deletions;      /* including the pass-1 spill          GenomeRegion.scala:263     */
+    int32_t* del_qual;
+    int32_t* insertions;
+    int32_t* ins_qual;
+    int32_t* clips;
+
+    /* GenomeRegion pass-1 arrays that are not plain copies of the above */
+    int32_t* coverage_arr;   /* coverage(i) = depth.toInt           GenomeRegion.scala:247     */
+    int32_t* frag_coverage;  /* fragCoverage(i)                     GenomeRegion.scala:296-298 */
+    int8_t*  weighted_qual;  /* weightedQual.toByte                 GenomeRegion.scala:251     */
+    int8_t*  weighted_mq;    /* weightedMq.toByte                   GenomeRegion.scala:252     */
+    uint8_t* flags;          /* PB_FL_*                                                        */
+    uint64_t* call;          /* packed BaseCall record                                         */
+
+    /* sparse indel evidence; capacities are inputs, counts come back in n_indels/n_indel_bytes */
+    pb_indel* indels;        int64_t indels_cap;
+    uint8_t*  indel_bytes;   int64_t indel_bytes_cap;
+} pb_region_result;
+
+typedef struct pb_engine pb_engine;
+
+/* library-level */
+int         pb_abi_version(void);
+const char* pb_last_error(void);
+int         pb_device_count(int* n_out);
+
+/* Engine lifetime = what GenomeRegion.initializePileUps / finalizePileUps bracket
+ * (GenomeRegion.scala:149-155), but reusable across regions to keep device buffers warm. */
+int pb_create(int device, const pb_config* cfg, pb_engine** out);
+int pb_destroy(pb_engine* e);
+
+/* new PileUpRegion(name, start, stop)  (GenomeRegion.scala:150; PileUpRegion.scala:26-36).
+ * contig_bases = GenomeRegion.contigBases (raw FASTA bytes, case preserved), host memory. */
+int pb_region_begin(pb_engine* e, const uint8_t* contig_bases, int64_t contig_len,
+                    int32_t start, int32_t stop);
+
+/* The batched equivalent of the `for (read <- reads) ... addRead` loop (BamFile.scala:126-139).
+ * counts_toward_frag_coverage = (bamType != "jumps")      (GenomeRegion.scala:291,296)
+ * long_read_type              = BamFile.longReadType       (BamFile.scala:43-47); only 0 is
+ *                               implemented in this round (PB_ERR_UNSUPPORTED otherwise).
+ * The call is asynchronous on the engine's stream; host buffers must stay valid until
+ * pb_region_finish returns. */
+int pb_region_add_batch(pb_engine* e, const pb_batch* batch,
+                        int counts_toward_frag_coverage, int long_read_type);
+
+/* PileUpRegion.postProcess + GenomeRegion.postProcess pass 1 (PileUpRegion.scala:226-229;
+ * GenomeRegion.scala:214-272) and the copy of everything the driver / writers read back.
+ * insert_sizes_out[b] (may be NULL) receives, for batch b in add order, the per-read return value
+ * of addRead (PileUpRegion.scala:219) as int32[n_reads] -- what BamFile.addInsert consumes. */
+int pb_region_finish(pb_engine* e, pb_region_result* res, int32_t* const* insert_sizes_out);
+
+/* Device-resident timing hook for bench.py: (re)runs the compute part of pb_region_finish on the
+ * batches already added, without any host<->device copy, `iters` times, and reports the elapsed
+ * device milliseconds measured with CUDA events on the engine's stream (total and for the pileup
+ * kernel alone), plus the number of kernel launches. */
+int pb_region_compute_timed(pb_engine* e, int iters, float* total_ms, float* pileup_ms,
+                            int64_t* launches);
+
+/* Raw CUDA stream handle (cudaStream_t) so callers can order their own copies against the engine. */
+int pb_stream(pb_engine* e, void** stream_out);
+
+/* ---- host-side packer (the `BamFile.process` side of the seam) ---------------------------
+ * Packs one read given the way BAM stores it / htsjdk exposes it into the arrays of a pb_batch
+ * under construction.  `seq` is ASCII (getReadBases), `qual` raw phred bytes or NULL. */
+typedef struct pb_packer pb_packer;
+int pb_packer_create(pb_packer** out);
+int pb_packer_destroy(pb_packer* p);
+int pb_packer_reset(pb_packer* p);
+int pb_packer_add(pb_packer* p, int32_t pos, int32_t tlen, int32_t mapq, uint32_t flags,
+                  const uint32_t* cigar, int32_t n_cigar,
+                  const uint8_t* seq, const uint8_t* qual, int32_t read_len);
+/* Bulk form: reads already in struct-of-arrays with ASCII bases (one byte per base, unpadded). */
+int pb_packer_add_many(pb_packer* p, int64_t n_reads, const int32_t* pos, const int32_t* tlen,
+                       const uint8_t* mapq, const uint8_t* flags, const int32_t* read_len,
+                       const uint32_t* cigar_off, const uint32_t* cigar,
+                       const uint64_t* ascii_off, const uint8_t* seq, const uint8_t* qual);
+/* The returned view points into the packer's (pinned when possible) buffers, valid until the next
+ * reset / add / destroy. */
+int pb_packer_view(pb_packer* p, pb_batch* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PILON_B200_H */

@@ -1,0 +1,216 @@
+"""Host-side read batching: SAMRecord-like objects -> the struct-of-arrays `pb_batch`
+(include/pilon_b200.h).  This is the re-plumbed half of `BamFile.process`
+(reference BamFile.scala:108-148): instead of calling `PileUpRegion.addRead` once per record,
+the records of a region query are packed once and handed to the engine.
+
+htsjdk semantics restated here (htsjdk 2.23.0, SAM spec): bases are the upper-case ASCII letters
+"=ACMGRSVTWYHKDBN"; an all-0xFF quality array means "no qualities" (PB_F_HAS_QUALS clear);
+getAlignmentStart is 1-based.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi as capi
+
+_OPCODE = {op: i for i, op in enumerate(capi.CIGAR_OPS)}
+_BASE_CODE = np.full(256, 255, np.uint8)
+for _i, _c in enumerate(b"ACGT"):
+    _BASE_CODE[_c] = _i
+
+
+@dataclass
+class ReadBatch:
+    """Numpy struct-of-arrays with the exact layout of `pb_batch`."""
+    pos: np.ndarray
+    tlen: np.ndarray
+    read_len: np.ndarray
+    mapq: np.ndarray
+    flags: np.ndarray
+    cigar_off: np.ndarray
+    cigar: np.ndarray
+    seq_off: np.ndarray
+    quals: np.ndarray
+    bases2: np.ndarray
+    exc_idx: np.ndarray
+    exc_base: np.ndarray
+    exc_qual: np.ndarray
+
+    @property
+    def n_reads(self) -> int:
+        return int(self.pos.shape[0])
+
+    @property
+    def aligned_bases(self) -> int:
+        ops = self.cigar & 15
+        return int((self.cigar >> 4)[(ops == 0) | (ops == 7) | (ops == 8)].sum())
+
+    def to_c(self) -> capi.pb_batch:
+        b = capi.pb_batch()
+        b.n_reads, b.n_cigar = self.n_reads, int(self.cigar.shape[0])
+        b.n_seq, b.n_exc = int(self.quals.shape[0]), int(self.exc_idx.shape[0])
+        for name in ("pos", "tlen", "read_len", "mapq", "flags", "cigar_off", "cigar", "seq_off",
+                     "quals", "bases2", "exc_idx", "exc_base", "exc_qual"):
+            arr = getattr(self, name)
+            assert arr.flags["C_CONTIGUOUS"]
+            setattr(b, name, arr.ctypes.data)
+        b.mem = capi.PB_MEM_HOST
+        b._keepalive = self
+        return b
+
+    def slice_reads(self, lo: int, hi: int) -> "ReadBatch":
+        """Sub-batch of reads [lo, hi) (re-based offsets); used to split a region's reads."""
+        co = self.cigar_off[lo:hi + 1].astype(np.int64)
+        if hi > lo:
+            s0 = int(self.seq_off[lo])
+            s1 = int(self.seq_off[hi - 1]) + ((int(self.read_len[hi - 1]) + 3) & ~3)
+        else:
+            s0 = s1 = 0
+        e0, e1 = np.searchsorted(self.exc_idx, [s0, s1])
+        return ReadBatch(self.pos[lo:hi].copy(), self.tlen[lo:hi].copy(), self.read_len[lo:hi].copy(),
+                         self.mapq[lo:hi].copy(), self.flags[lo:hi].copy(),
+                         (co - co[0]).astype(np.uint32), self.cigar[co[0]:co[-1]].copy(),
+                         (self.seq_off[lo:hi] - np.uint32(s0)).astype(np.uint32),
+                         self.quals[s0:s1].copy(), self.bases2[s0 // 4:s1 // 4].copy(),
+                         (self.exc_idx[e0:e1] - np.uint32(s0)).astype(np.uint32),
+                         self.exc_base[e0:e1].copy(), self.exc_qual[e0:e1].copy())
+
+
+def encode_cigar(cigar: Sequence) -> List[int]:
+    return [(int(ln) << 4) | _OPCODE[op] for op, ln in cigar]
+
+
+def record_flags(r) -> int:
+    f = 0
+    if r.paired:
+        f |= capi.PB_F_PAIRED
+    if r.proper:
+        f |= capi.PB_F_PROPER
+    if r.mate_same_ref:
+        f |= capi.PB_F_MATE_SAME_REF
+    if len(r.quals) > 0:
+        f |= capi.PB_F_HAS_QUALS
+    if getattr(r, "unmapped", False):
+        f |= capi.PB_F_UNMAPPED
+    if getattr(r, "reverse", False):
+        f |= capi.PB_F_REVERSE
+    return f
+
+
+def pack_soa(pos, tlen, mapq, flags, read_len, cigar_off, cigar, ascii_off, seq, qual) -> ReadBatch:
+    """Vectorised packer: reads given as struct-of-arrays with one ASCII byte per base (unpadded,
+    read r occupying seq[ascii_off[r] : ascii_off[r]+read_len[r]]) and raw quality bytes (ignored
+    for reads without PB_F_HAS_QUALS)."""
+    pos = np.ascontiguousarray(pos, np.int32)
+    n = pos.shape[0]
+    read_len = np.ascontiguousarray(read_len, np.int32)
+    flags = np.ascontiguousarray(flags, np.uint8)
+    padded = (read_len.astype(np.int64) + 3) & ~3
+    seq_off64 = np.zeros(n + 1, np.int64)
+    np.cumsum(padded, out=seq_off64[1:])
+    n_seq = int(seq_off64[-1])
+    if n_seq >= 2 ** 32:
+        raise ValueError("batch too large: split it (n_seq must be < 2^32)")
+    seq = np.ascontiguousarray(seq, np.uint8)
+    qual = np.ascontiguousarray(qual, np.uint8)
+    ascii_off = np.ascontiguousarray(ascii_off, np.int64)
+    # destination index of every source base
+    total = int(read_len.sum())
+    rid = np.repeat(np.arange(n, dtype=np.int64), read_len)
+    within = np.arange(total, dtype=np.int64) - np.repeat(np.cumsum(read_len.astype(np.int64)) - read_len, read_len)
+    src = ascii_off[rid] + within
+    dst = seq_off64[rid] + within
+    letters = seq[src]
+    hasq = (flags[rid] & capi.PB_F_HAS_QUALS) != 0
+    q = np.where(hasq, qual[src] if qual.shape[0] else np.zeros(total, np.uint8), 0).astype(np.uint8)
+    code = _BASE_CODE[letters]
+    exc = (code == 255) | (q >= 128)
+    quals = np.zeros(n_seq, np.uint8)
+    quals[dst] = np.where(exc, (q & 0x7F) | 0x80, q)
+    code2 = np.where(code == 255, 0, code).astype(np.uint8)
+    codes_full = np.zeros(n_seq, np.uint8)
+    codes_full[dst] = code2
+    c4 = codes_full.reshape(-1, 4)
+    bases2 = (c4[:, 0] | (c4[:, 1] << 2) | (c4[:, 2] << 4) | (c4[:, 3] << 6)).astype(np.uint8)
+    return ReadBatch(pos, np.ascontiguousarray(tlen, np.int32), read_len,
+                     np.ascontiguousarray(mapq, np.uint8), flags,
+                     np.ascontiguousarray(cigar_off, np.uint32), np.ascontiguousarray(cigar, np.uint32),
+                     seq_off64[:-1].astype(np.uint32), quals, bases2,
+                     dst[exc].astype(np.uint32), letters[exc].copy(), q[exc].copy())
+
+
+def pack_records(records: Iterable) -> ReadBatch:
+    """Pack SAMRecord-like objects (attributes: pos, cigar [(op, len)], bases, quals, mapq, paired,
+    proper, mate_same_ref, tlen, unmapped, reverse).  Records must already be sorted by pos."""
+    recs = list(records)
+    n = len(recs)
+    pos = np.array([r.pos for r in recs], np.int32).reshape(n)
+    tlen = np.array([r.tlen for r in recs], np.int32).reshape(n)
+    mapq = np.array([r.mapq for r in recs], np.uint8).reshape(n)
+    flags = np.array([record_flags(r) for r in recs], np.uint8).reshape(n)
+    read_len = np.array([len(r.bases) for r in recs], np.int32).reshape(n)
+    cig: List[int] = []
+    cigar_off = np.zeros(n + 1, np.uint32)
+    for i, r in enumerate(recs):
+        cig.extend(encode_cigar(r.cigar))
+        cigar_off[i + 1] = len(cig)
+    ascii_off = np.zeros(n, np.int64)
+    if n:
+        ascii_off[1:] = np.cumsum(read_len[:-1].astype(np.int64))
+    seq = np.frombuffer(b"".join(bytes(r.bases) for r in recs), np.uint8)
+    qual = np.frombuffer(b"".join(bytes(r.quals) if len(r.quals) else bytes(len(r.bases)) for r in recs), np.uint8)
+    return pack_soa(pos, tlen, mapq, flags, read_len, cigar_off, np.array(cig, np.uint32), ascii_off, seq, qual)
+
+
+class ResultBuffers:
+    """Caller-owned host arrays behind a `pb_region_result`."""
+
+    def __init__(self, size: int, planes: Optional[Sequence[str]] = None, indels_cap: int = 0,
+                 indel_bytes_cap: int = 0, pinned: bool = False):
+        self.size = size
+        self.arrays = {}
+        self.c = capi.pb_region_result()
+        want = set(planes) if planes is not None else {p[0] for p in capi.RESULT_PLANES}
+        for name, dt, per in capi.RESULT_PLANES:
+            if name in want:
+                arr = _alloc(size * per, np.dtype(dt), pinned)
+                self.arrays[name] = arr
+                setattr(self.c, name, arr.ctypes.data)
+        self.indels_cap, self.indel_bytes_cap = indels_cap, indel_bytes_cap
+        if indels_cap:
+            self._indels = (capi.pb_indel * indels_cap)()
+            self.c.indels = C.addressof(self._indels)
+            self.c.indels_cap = indels_cap
+        if indel_bytes_cap:
+            self.indel_bytes = np.zeros(indel_bytes_cap, np.uint8)
+            self.c.indel_bytes = self.indel_bytes.ctypes.data
+            self.c.indel_bytes_cap = indel_bytes_cap
+
+    def __getitem__(self, name: str) -> np.ndarray:
+        a = self.arrays[name]
+        per = {p[0]: p[2] for p in capi.RESULT_PLANES}[name]
+        return a.reshape(self.size, per) if per > 1 else a
+
+    def indels(self):
+        out = []
+        n = min(int(self.c.n_indels), self.indels_cap)
+        for k in range(n):
+            e = self._indels[k]
+            s = bytes(self.indel_bytes[e.str_off:e.str_off + e.win_len]) if self.indel_bytes_cap else b""
+            out.append(dict(locus_index=e.locus_index, kind=e.kind, list_len=e.list_len, win_count=e.win_count,
+                            win_len=e.win_len, win_has_n=e.win_has_n, string=s))
+        return out
+
+
+def _alloc(n: int, dt: np.dtype, pinned: bool) -> np.ndarray:
+    if pinned:
+        import torch
+        t = torch.empty(max(n, 1) * dt.itemsize, dtype=torch.uint8, pin_memory=True)
+        arr = t.numpy().view(dt)[:n]   # the ndarray keeps the pinned tensor alive through .base
+        arr.fill(0)
+        return arr
+    return np.zeros(n, dt)

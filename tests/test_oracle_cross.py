@@ -1,0 +1,46 @@
+"""Two independent restatements of the reference path must agree bit for bit:
+the literal Python transliteration (oracle/pilon_oracle.py) and the C restatement
+(oracle/pilon_oracle.c) that consumes the engine's packed batches."""
+import random
+
+import pytest
+
+from oracle import pilon_oracle as po
+from pilon_b200.packing import pack_records
+from tests import helpers as H
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_c_oracle_matches_python_oracle(seed):
+    contig, start, stop, reads = H.random_case(seed)
+    rng = random.Random(seed * 7 + 1)
+    groups = H.split_batches(reads, rng)
+    cfg = po.Config()
+    if seed % 5 == 1:
+        cfg = po.Config(minQual=7, minMq=2, flank=rng.choice([0, 3, 10]), defaultQual=rng.choice([3, 10, 15]))
+    if seed % 7 == 3:
+        cfg.oldIndel = True
+    if seed % 11 == 4:
+        cfg.minDepth = 3.0
+    py = H.run_py_oracle(contig, start, stop, groups, cfg)
+    res, ins = H.run_c_oracle(contig, start, stop, [(pack_records(g), f) for g, f in groups], cfg)
+    H.assert_matches_py(res, ins, py, "seed %d" % seed)
+
+
+def test_cases_exercise_the_interesting_paths():
+    """The generator must actually reach indel calls, the deletion spill, drops, clips..."""
+    seen = dict(ins_call=0, del_call=0, deleted=0, dropped=0, snp=0, amb=0, confirmed=0, unknown=0)
+    for seed in range(40):
+        contig, start, stop, reads = H.random_case(seed)
+        res, _ = H.run_c_oracle(contig, start, stop, [(pack_records(reads), True)])
+        fl = res["flags"]
+        kind = (fl >> 4) & 3
+        seen["ins_call"] += int(((fl & 2) != 0)[kind == 1].sum())
+        seen["del_call"] += int(((fl & 2) != 0)[kind == 2].sum())
+        seen["snp"] += int((((fl & 2) != 0) & (kind == 0)).sum())
+        seen["amb"] += int(((fl & 4) != 0).sum())
+        seen["deleted"] += int(((fl & 8) != 0).sum())
+        seen["confirmed"] += int((fl & 1).sum())
+        seen["dropped"] += res.c.dropped_oob
+        seen["unknown"] += res.c.unknown_ops
+    assert all(v > 0 for v in seen.values()), seen
