@@ -1,0 +1,470 @@
+// pb_engine.cu -- host orchestration + C ABI of libpilonb200.so (see include/pilon_b200.h).
+//
+// One engine = one CUDA stream on one GPU.  Region lifetime mirrors
+// GenomeRegion.initializePileUps / finalizePileUps (GenomeRegion.scala:149-155): begin, add the
+// region's read batches (BamFile.process, BamFile.scala:108-148), finish (PileUpRegion.postProcess
+// + GenomeRegion.postProcess pass 1, GenomeRegion.scala:214-272) and read everything back.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_merge_sort.cuh>
+
+#include "pb_kernels.cuh"
+
+using namespace pb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(PB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+namespace {
+
+// grow-only device buffer, zero-filled on growth when asked (the "rare" planes rely on it)
+struct DBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes, bool zero, cudaStream_t s) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); if (e != cudaSuccess) return e; p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return e;
+        cap = want;
+        if (zero) return cudaMemsetAsync(p, 0, cap, s);
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostBatch {
+    DevBatch d;                      // device view
+    std::vector<void*> owned;        // device allocations owned by this batch (cudaMallocAsync)
+};
+
+}  // namespace
+
+struct pb_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr, ev_sc = nullptr;
+    Cfg cfg{};
+    bool in_region = false;
+    RegionDev R{};
+    std::vector<HostBatch> batches;
+    DBuf d_batches;                  // DevBatch[] image
+    // per-locus buffers
+    DBuf ref, rare[10], rare_bits, cand_len, pc_diff, block_sums, scalars;
+    DBuf o_cnt, o_qs, o_i32[12], o_wq, o_wmq, o_flags, o_call;
+    // event buffers
+    DBuf ev_key, ev, perm, groups, cand, spill_scratch, str_pool, cub_tmp;
+    Scalars* h_sc = nullptr;         // pinned
+    int64_t launches = 0;
+    float last_pileup_ms = 0.f;
+    bool dirty = false;              // rare planes may be non-zero after a failed run
+};
+
+static int free_batches(pb_engine* e) {
+    for (auto& hb : e->batches)
+        for (void* p : hb.owned) CK(cudaFreeAsync(p, e->stream));
+    e->batches.clear();
+    return PB_OK;
+}
+
+extern "C" int pb_abi_version(void) { return PB_ABI_VERSION; }
+extern "C" const char* pb_last_error(void) { return g_err.c_str(); }
+extern "C" int pb_device_count(int* n_out) { CK(cudaGetDeviceCount(n_out)); return PB_OK; }
+
+extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
+    if (!c || !out) return fail(PB_ERR_INVALID, "null argument");
+    // the packed format folds "negative quality byte" into the uncountable flag, which is only
+    // equivalent to PileUp.scala:77 when minQual >= 0; defaultQual is a phred value
+    if (c->min_qual < 0) return fail(PB_ERR_UNSUPPORTED, "min_qual < 0 is not supported");
+    if (c->default_qual < 0 || c->default_qual > 127) return fail(PB_ERR_UNSUPPORTED, "default_qual must be in 0..127");
+    if (c->flank < 0) return fail(PB_ERR_INVALID, "flank < 0");
+    CK(cudaSetDevice(device));
+    pb_engine* e = new pb_engine();
+    e->device = device;
+    e->cfg.min_qual = c->min_qual; e->cfg.min_mq = c->min_mq; e->cfg.flank = c->flank;
+    e->cfg.default_qual = c->default_qual; e->cfg.min_min_depth = c->min_min_depth;
+    e->cfg.old_indel = c->old_indel; e->cfg.fix_amb = c->fix_amb; e->cfg.min_depth = c->min_depth;
+    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
+    CK(cudaEventCreate(&e->evp0)); CK(cudaEventCreate(&e->evp1));
+    CK(cudaEventCreateWithFlags(&e->ev_sc, cudaEventDisableTiming));
+    CK(cudaMallocHost(&e->h_sc, sizeof(Scalars)));
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    *out = e;
+    return PB_OK;
+}
+
+extern "C" int pb_destroy(pb_engine* e) {
+    if (!e) return PB_OK;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    free_batches(e);
+    cudaStreamSynchronize(e->stream);
+    DBuf* all[] = {&e->d_batches, &e->ref, &e->rare_bits, &e->cand_len, &e->pc_diff, &e->block_sums, &e->scalars,
+                   &e->o_cnt, &e->o_qs, &e->o_wq, &e->o_wmq, &e->o_flags, &e->o_call, &e->ev_key, &e->ev, &e->perm,
+                   &e->groups, &e->cand, &e->spill_scratch, &e->str_pool, &e->cub_tmp};
+    for (DBuf* b : all) b->release();
+    for (auto& b : e->rare) b.release();
+    for (auto& b : e->o_i32) b.release();
+    if (e->h_sc) cudaFreeHost(e->h_sc);
+    cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->evp0); cudaEventDestroy(e->evp1);
+    cudaEventDestroy(e->ev_sc);
+    cudaStreamDestroy(e->stream);
+    delete e;
+    return PB_OK;
+}
+
+extern "C" int pb_stream(pb_engine* e, void** s) { if (!e || !s) return fail(PB_ERR_INVALID, "null"); *s = e->stream; return PB_OK; }
+
+extern "C" int pb_region_begin(pb_engine* e, const uint8_t* contig, int64_t contig_len, int32_t start, int32_t stop) {
+    if (!e || !contig) return fail(PB_ERR_INVALID, "null argument");
+    if (start < 1 || stop < start || stop > contig_len) return fail(PB_ERR_INVALID, "region must satisfy 1 <= start <= stop <= contig_len");
+    const int64_t S = (int64_t)stop + 1 - start;
+    if (S >= (1ll << 30)) return fail(PB_ERR_INVALID, "region too large (size must be < 2^30)");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    if (free_batches(e) != PB_OK) return PB_ERR_CUDA;
+    RegionDev& R = e->R;
+    R = RegionDev{};
+    R.start = start; R.stop = stop; R.size = S; R.n_win = (int32_t)((S + 31) >> 5);
+    R.ref_locus0 = start - 1 > 1 ? start - 1 : 1;
+    R.cfg = e->cfg;
+    const size_t ref_bytes = (size_t)(stop - R.ref_locus0 + 1);
+    CK(e->ref.ensure(ref_bytes, false, s));
+    CK(cudaMemcpyAsync(e->ref.p, contig + (R.ref_locus0 - 1), ref_bytes, cudaMemcpyHostToDevice, s));
+    R.ref = e->ref.as<uint8_t>();
+    if (e->dirty) {   // a failed run may have left sparse planes populated
+        for (auto& b : e->rare) if (b.p) CK(cudaMemsetAsync(b.p, 0, b.cap, s));
+        if (e->rare_bits.p) CK(cudaMemsetAsync(e->rare_bits.p, 0, e->rare_bits.cap, s));
+        if (e->pc_diff.p) CK(cudaMemsetAsync(e->pc_diff.p, 0, e->pc_diff.cap, s));
+        e->dirty = false;
+    }
+    const size_t n4 = (size_t)S * 4;
+    for (auto& b : e->rare) CK(b.ensure(n4, true, s));
+    CK(e->rare_bits.ensure((size_t)R.n_win * 4, true, s));
+    CK(e->pc_diff.ensure((size_t)S * 8, true, s));
+    CK(e->cand_len.ensure(n4, false, s));
+    CK(e->scalars.ensure(sizeof(Scalars), false, s));
+    CK(cudaMemsetAsync(e->scalars.p, 0, sizeof(Scalars), s));
+    CK(e->o_cnt.ensure((size_t)S * 16, false, s)); CK(e->o_qs.ensure((size_t)S * 32, false, s));
+    for (auto& b : e->o_i32) CK(b.ensure(n4, false, s));
+    CK(e->o_wq.ensure((size_t)S, false, s)); CK(e->o_wmq.ensure((size_t)S, false, s));
+    CK(e->o_flags.ensure((size_t)S, false, s)); CK(e->o_call.ensure((size_t)S * 8, false, s));
+    const int nblocks = (int)((S + SCAN_TILE - 1) / SCAN_TILE);
+    CK(e->block_sums.ensure((size_t)nblocks * 8, false, s));
+    R.sc = e->scalars.as<Scalars>();
+    R.r_ins = e->rare[0].as<int32_t>(); R.r_insq = e->rare[1].as<int32_t>(); R.r_del = e->rare[2].as<int32_t>();
+    R.r_delq = e->rare[3].as<int32_t>(); R.r_q = e->rare[4].as<int32_t>(); R.r_mq = e->rare[5].as<int32_t>();
+    R.r_clips = e->rare[6].as<int32_t>(); R.r_delfrag = e->rare[7].as<int32_t>();
+    R.r_gins = e->rare[8].as<uint32_t>(); R.r_gdel = e->rare[9].as<uint32_t>();
+    R.rare_bits = e->rare_bits.as<uint32_t>(); R.cand_len = e->cand_len.as<int32_t>();
+    R.pc_diff = e->pc_diff.as<int2>();
+    R.o_cnt = e->o_cnt.as<int32_t>(); R.o_qs = e->o_qs.as<int64_t>();
+    int32_t** o32[] = {&R.o_mq, &R.o_q, &R.o_pc, &R.o_is, &R.o_bp, &R.o_del, &R.o_delq, &R.o_ins, &R.o_insq,
+                       &R.o_clips, &R.o_cov, &R.o_frag};
+    for (int i = 0; i < 12; i++) *o32[i] = e->o_i32[i].as<int32_t>();
+    R.o_wq = e->o_wq.as<int8_t>(); R.o_wmq = e->o_wmq.as<int8_t>();
+    R.o_flags = e->o_flags.as<uint8_t>(); R.o_call = e->o_call.as<uint64_t>();
+    e->in_region = true;
+    return PB_OK;
+}
+
+// Make one batch array visible to the device: device pointers are used in place, host arrays are
+// copied asynchronously into stream-ordered allocations owned by the batch.
+template <class T>
+static int stage(pb_engine* e, HostBatch& hb, const T* src, size_t n, int mem, const T** dst) {
+    if (mem == PB_MEM_DEVICE) { *dst = src; return PB_OK; }
+    void* p = nullptr;
+    CK(cudaMallocAsync(&p, n * sizeof(T) + 16, e->stream));
+    hb.owned.push_back(p);
+    if (n) CK(cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    *dst = (const T*)p;
+    return PB_OK;
+}
+
+extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, int long_read_type) {
+    if (!e || !b) return fail(PB_ERR_INVALID, "null argument");
+    if (!e->in_region) return fail(PB_ERR_INVALID, "pb_region_begin has not been called");
+    if (long_read_type != 0) return fail(PB_ERR_UNSUPPORTED, "long-read branches (PileUpRegion.scala:120-134,160,180,190) are gated off");
+    if (b->n_seq >= (1ll << 32) || (b->n_seq & 3)) return fail(PB_ERR_INVALID, "n_seq must be a multiple of 4 and < 2^32");
+    if (b->n_cigar >= (1ll << 32) || b->n_reads >= (1ll << 31)) return fail(PB_ERR_INVALID, "batch too large");
+    CK(cudaSetDevice(e->device));
+    e->batches.emplace_back();
+    HostBatch& hb = e->batches.back();
+    DevBatch& d = hb.d;
+    memset(&d, 0, sizeof(d));
+    d.n_reads = b->n_reads; d.n_cigar = b->n_cigar; d.n_seq = b->n_seq; d.n_exc = b->n_exc; d.frag = frag ? 1 : 0;
+    const size_t n = (size_t)b->n_reads;
+    int rc;
+#define ST(field, count) if ((rc = stage(e, hb, b->field, (size_t)(count), b->mem, &d.field)) != PB_OK) return rc
+    ST(pos, n); ST(tlen, n); ST(read_len, n); ST(mapq, n); ST(flags, n); ST(cigar_off, n + 1);
+    ST(cigar, b->n_cigar); ST(seq_off, n); ST(quals, b->n_seq); ST(bases2, b->n_seq / 4);
+    ST(exc_idx, b->n_exc); ST(exc_base, b->n_exc); ST(exc_qual, b->n_exc);
+#undef ST
+    void* p = nullptr;
+    CK(cudaMallocAsync(&p, ((size_t)b->n_cigar + 1) * sizeof(Seg), e->stream)); hb.owned.push_back(p); d.seg = (Seg*)p;
+    CK(cudaMallocAsync(&p, ((size_t)e->R.n_win + 2) * 4, e->stream)); hb.owned.push_back(p); d.win_first = (uint32_t*)p;
+    CK(cudaMallocAsync(&p, (n + 1) * 4, e->stream)); hb.owned.push_back(p); d.insert_out = (int32_t*)p;
+    CK(cudaMallocAsync(&p, 16, e->stream)); hb.owned.push_back(p); d.reach = (int32_t*)p;
+    return PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the compute pipeline (no host<->device data copies except one 80-byte scalar read-back)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_iota(uint32_t* p, uint32_t n) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; }
+
+static int compute(pb_engine* e, bool time_pileup) {
+    cudaStream_t s = e->stream;
+    RegionDev& R = e->R;
+    const int nb = (int)e->batches.size();
+    size_t total_cigar = 0;
+    for (auto& hb : e->batches) total_cigar += (size_t)hb.d.n_cigar;
+    const uint32_t cap = (uint32_t)std::min<size_t>(total_cigar, 0xFFFFFFF0u);
+    CK(e->ev_key.ensure((size_t)cap * sizeof(EventKey) + 16, false, s));
+    CK(e->ev.ensure((size_t)cap * sizeof(Event) + 16, false, s));
+    CK(e->perm.ensure((size_t)cap * 4 + 16, false, s));
+    CK(e->groups.ensure((size_t)cap * sizeof(Group) + 16, false, s));
+    CK(e->cand.ensure((size_t)cap * sizeof(int2) + 16, false, s));
+    R.ev_key = e->ev_key.as<EventKey>(); R.ev = e->ev.as<Event>(); R.ev_cap = cap;
+    R.groups = e->groups.as<Group>(); R.groups_cap = cap;
+    R.cand = e->cand.as<int2>(); R.cand_cap = cap;
+    R.str_pool = e->str_pool.as<uint8_t>(); R.str_cap = e->str_pool.cap;
+    std::vector<DevBatch> img(nb);
+    for (int i = 0; i < nb; i++) img[i] = e->batches[i].d;
+    CK(e->d_batches.ensure(sizeof(DevBatch) * (size_t)std::max(nb, 1), false, s));
+    if (nb) CK(cudaMemcpyAsync(e->d_batches.p, img.data(), sizeof(DevBatch) * nb, cudaMemcpyHostToDevice, s));
+    const DevBatch* dB = e->d_batches.as<DevBatch>();
+    e->dirty = true;
+    CK(cudaMemsetAsync(e->scalars.p, 0, sizeof(Scalars), s));
+
+    for (int i = 0; i < nb; i++) {
+        const DevBatch& d = e->batches[i].d;
+        CK(cudaMemsetAsync(d.reach, 0, 8, s));
+        CK(cudaMemsetAsync(d.win_first, 0, ((size_t)R.n_win + 2) * 4, s));
+        if (d.n_reads == 0) continue;
+        k_prep<<<(unsigned)((d.n_reads + 127) / 128), 128, 0, s>>>(R, d, (uint32_t)i);
+        k_index<<<(unsigned)((d.n_reads + 255) / 256), 256, 0, s>>>(R, d);
+        e->launches += 2;
+    }
+    k_scalars<<<1, 1, 0, s>>>(R); e->launches++;
+    CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(e->ev_sc, s));
+    // physCov scan does not depend on the events: keeps the GPU busy while the host waits for n_events
+    const int nblocks = (int)((R.size + SCAN_TILE - 1) / SCAN_TILE);
+    k_scan1<<<nblocks, SCAN_THREADS, 0, s>>>(R, e->block_sums.as<uint2>());
+    k_scan2<<<1, 1024, 0, s>>>(R, e->block_sums.as<uint2>(), nblocks);
+    k_scan3<<<nblocks, SCAN_THREADS, 0, s>>>(R, e->block_sums.as<uint2>());
+    e->launches += 3;
+    CK(cudaEventSynchronize(e->ev_sc));
+    if (e->h_sc->error & 1) return fail(PB_ERR_UNSORTED, "a batch is not sorted by pos");
+    if (e->h_sc->error) return fail(PB_ERR_CUDA, "internal capacity error in k_prep");
+    const uint32_t n_ev = e->h_sc->n_events;
+    if (n_ev) {
+        k_iota<<<(n_ev + 255) / 256, 256, 0, s>>>(e->perm.as<uint32_t>(), n_ev); e->launches++;
+        size_t tmp = 0;
+        CK(cub::DeviceMergeSort::SortPairs(nullptr, tmp, R.ev_key, e->perm.as<uint32_t>(), (int64_t)n_ev, EventKeyLess(), s));
+        CK(e->cub_tmp.ensure(tmp + 16, false, s));
+        CK(cub::DeviceMergeSort::SortPairs(e->cub_tmp.p, tmp, R.ev_key, e->perm.as<uint32_t>(), (int64_t)n_ev, EventKeyLess(), s));
+        k_groups<<<(n_ev + 255) / 256, 256, 0, s>>>(R, dB, R.ev_key, e->perm.as<uint32_t>(), n_ev); e->launches++;
+    }
+    if (time_pileup) CK(cudaEventRecord(e->evp0, s));
+    const unsigned grid = (unsigned)((R.n_win + PILEUP_WARPS - 1) / PILEUP_WARPS);
+    if (e->cfg.min_qual > 0) k_pileup<true><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
+    else k_pileup<false><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
+    e->launches++;
+    if (time_pileup) CK(cudaEventRecord(e->evp1, s));
+    // deletion spill: candidates are bounded by the number of deletion groups
+    uint32_t p2 = 1; while (p2 < n_ev) p2 <<= 1;
+    CK(e->spill_scratch.ensure((size_t)p2 * sizeof(int2) + 16, false, s));
+    if (n_ev) { k_spill<<<1, 1024, 4096 * sizeof(int2), s>>>(R, e->spill_scratch.as<int2>(), p2); e->launches++; }
+    CK(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_region_compute_timed(pb_engine* e, int iters, float* total_ms, float* pileup_ms, int64_t* launches) {
+    if (!e || !e->in_region) return fail(PB_ERR_INVALID, "no region");
+    CK(cudaSetDevice(e->device));
+    const int64_t l0 = e->launches;
+    float tot = 0.f, pil = 0.f;
+    for (int it = 0; it < iters; it++) {
+        CK(cudaEventRecord(e->ev0, e->stream));
+        int rc = compute(e, true);
+        if (rc != PB_OK) return rc;
+        // leave the sparse group planes clean for the next iteration
+        CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        if (e->h_sc->n_groups) { k_groups_clear<<<(e->h_sc->n_groups + 127) / 128, 128, 0, e->stream>>>(e->R, e->h_sc->n_groups); e->launches++; }
+        CK(cudaEventRecord(e->ev1, e->stream));
+        CK(cudaEventSynchronize(e->ev1));
+        float a = 0, b = 0;
+        CK(cudaEventElapsedTime(&a, e->ev0, e->ev1));
+        CK(cudaEventElapsedTime(&b, e->evp0, e->evp1));
+        tot += a; pil += b;
+        e->dirty = false;
+    }
+    if (total_ms) *total_ms = tot;
+    if (pileup_ms) *pileup_ms = pil;
+    if (launches) *launches = e->launches - l0;
+    return PB_OK;
+}
+
+extern "C" int pb_region_finish(pb_engine* e, pb_region_result* res, int32_t* const* insert_sizes_out) {
+    if (!e || !res) return fail(PB_ERR_INVALID, "null argument");
+    if (!e->in_region) return fail(PB_ERR_INVALID, "pb_region_begin has not been called");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    RegionDev& R = e->R;
+    int rc = compute(e, false);
+    if (rc != PB_OK) { cudaStreamSynchronize(s); return rc; }
+    CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (e->h_sc->error) return fail(e->h_sc->error & 4 ? PB_ERR_HASH : PB_ERR_CUDA, "internal error flag set by a kernel");
+    const uint32_t ng = e->h_sc->n_groups;
+    // winning strings: sized exactly, then gathered
+    std::vector<Group> groups(ng);
+    if (ng) {
+        CK(cudaMemcpyAsync(groups.data(), R.groups, sizeof(Group) * ng, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        size_t need = 0;
+        for (auto& g : groups) need += (size_t)g.win_len;
+        CK(e->str_pool.ensure(need + 16, false, s));
+        R.str_pool = e->str_pool.as<uint8_t>(); R.str_cap = e->str_pool.cap;
+        k_indel_strings<<<(ng + 127) / 128, 128, 0, s>>>(R, e->d_batches.as<DevBatch>(), ng); e->launches++;
+        k_groups_clear<<<(ng + 127) / 128, 128, 0, s>>>(R, ng); e->launches++;
+        CK(cudaMemcpyAsync(groups.data(), R.groups, sizeof(Group) * ng, cudaMemcpyDeviceToHost, s));
+    }
+    const size_t S = (size_t)R.size;
+#define D2H(dst, src, bytes) if (res->dst) CK(cudaMemcpyAsync(res->dst, src, (bytes), cudaMemcpyDeviceToHost, s))
+    D2H(base_count4, R.o_cnt, S * 16); D2H(qual_sum4, R.o_qs, S * 32);
+    D2H(mq_sum, R.o_mq, S * 4); D2H(q_sum, R.o_q, S * 4); D2H(phys_cov, R.o_pc, S * 4); D2H(insert_size, R.o_is, S * 4);
+    D2H(bad_pair, R.o_bp, S * 4); D2H(deletions, R.o_del, S * 4); D2H(del_qual, R.o_delq, S * 4);
+    D2H(insertions, R.o_ins, S * 4); D2H(ins_qual, R.o_insq, S * 4); D2H(clips, R.o_clips, S * 4);
+    D2H(coverage_arr, R.o_cov, S * 4); D2H(frag_coverage, R.o_frag, S * 4);
+    D2H(weighted_qual, R.o_wq, S); D2H(weighted_mq, R.o_wmq, S); D2H(flags, R.o_flags, S); D2H(call, R.o_call, S * 8);
+#undef D2H
+    if (insert_sizes_out)
+        for (size_t i = 0; i < e->batches.size(); i++)
+            if (insert_sizes_out[i] && e->batches[i].d.n_reads)
+                CK(cudaMemcpyAsync(insert_sizes_out[i], e->batches[i].d.insert_out, (size_t)e->batches[i].d.n_reads * 4, cudaMemcpyDeviceToHost, s));
+    std::vector<uint8_t> pool;
+    CK(cudaStreamSynchronize(s));
+    CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (e->h_sc->error) return fail(PB_ERR_CUDA, "internal error flag set by a kernel");
+    const size_t nbytes = (size_t)e->h_sc->str_bytes;
+    if (nbytes) { pool.resize(nbytes); CK(cudaMemcpy(pool.data(), R.str_pool, nbytes, cudaMemcpyDeviceToHost)); }
+    e->dirty = false;
+    // scalars
+    const Scalars& sc = *e->h_sc;
+    res->size = R.size; res->base_count = (int64_t)sc.base_count; res->coverage = sc.coverage;
+    res->aligned_bases = (int64_t)sc.aligned_bases; res->read_count = sc.read_count; res->min_depth = sc.min_depth;
+    res->unknown_ops = sc.unknown_ops; res->dropped_oob = sc.dropped_oob;
+    // indel evidence, ordered by (locus, kind)
+    std::sort(groups.begin(), groups.end(), [](const Group& a, const Group& b) { return a.loc < b.loc || (a.loc == b.loc && a.kind < b.kind); });
+    int64_t ni = 0, nbo = 0;
+    for (auto& g : groups) {
+        if (res->indels && ni < res->indels_cap) {
+            pb_indel& o = res->indels[ni];
+            o.locus_index = g.loc; o.kind = g.kind; o.list_len = g.list_len; o.win_count = g.win_count;
+            o.win_len = g.win_len; o.win_has_n = g.win_has_n; o.str_off = nbo;
+            if (res->indel_bytes && nbo + g.win_len <= res->indel_bytes_cap && g.win_len)
+                memcpy(res->indel_bytes + nbo, pool.data() + g.str_off, (size_t)g.win_len);
+        }
+        ni++; nbo += g.win_len;
+    }
+    res->n_indels = ni; res->n_indel_bytes = nbo;
+    if (free_batches(e) != PB_OK) return PB_ERR_CUDA;
+    e->in_region = false;
+    return PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host packer: what a re-plumbed BamFile.process (BamFile.scala:126-139) calls per record
+// ---------------------------------------------------------------------------------------------
+struct pb_packer {
+    std::vector<int32_t> pos, tlen, read_len;
+    std::vector<uint8_t> mapq, flags, quals, bases2, exc_base, exc_qual;
+    std::vector<uint32_t> cigar_off{0}, cigar, seq_off, exc_idx;
+};
+
+extern "C" int pb_packer_create(pb_packer** out) { if (!out) return fail(PB_ERR_INVALID, "null"); *out = new pb_packer(); return PB_OK; }
+extern "C" int pb_packer_destroy(pb_packer* p) { delete p; return PB_OK; }
+extern "C" int pb_packer_reset(pb_packer* p) {
+    if (!p) return fail(PB_ERR_INVALID, "null");
+    p->pos.clear(); p->tlen.clear(); p->read_len.clear(); p->mapq.clear(); p->flags.clear(); p->quals.clear();
+    p->bases2.clear(); p->exc_base.clear(); p->exc_qual.clear(); p->cigar_off.assign(1, 0); p->cigar.clear();
+    p->seq_off.clear(); p->exc_idx.clear();
+    return PB_OK;
+}
+
+extern "C" int pb_packer_add(pb_packer* p, int32_t pos, int32_t tlen, int32_t mapq, uint32_t flags,
+                             const uint32_t* cigar, int32_t n_cigar, const uint8_t* seq, const uint8_t* qual, int32_t read_len) {
+    if (!p || read_len < 0 || n_cigar < 0) return fail(PB_ERR_INVALID, "bad argument");
+    const size_t off = p->quals.size();
+    const size_t padded = ((size_t)read_len + 3) & ~(size_t)3;
+    if (off + padded >= (1ull << 32)) return fail(PB_ERR_INVALID, "batch full (n_seq must stay < 2^32): start a new batch");
+    if (!p->pos.empty() && pos < p->pos.back()) return fail(PB_ERR_UNSORTED, "records must be added in coordinate order");
+    const bool hasq = qual != nullptr && read_len > 0 && qual[0] != 0xFF;   // htsjdk: 0xFF.. == no qualities
+    p->pos.push_back(pos); p->tlen.push_back(tlen); p->read_len.push_back(read_len);
+    p->mapq.push_back((uint8_t)mapq);
+    p->flags.push_back((uint8_t)((flags & ~(uint32_t)PB_F_HAS_QUALS) | (hasq ? PB_F_HAS_QUALS : 0)));
+    p->cigar.insert(p->cigar.end(), cigar, cigar + n_cigar);
+    p->cigar_off.push_back((uint32_t)p->cigar.size());
+    p->seq_off.push_back((uint32_t)off);
+    p->quals.resize(off + padded, 0);
+    p->bases2.resize((off + padded) / 4, 0);
+    for (int32_t j = 0; j < read_len; j++) {
+        const uint8_t c = seq[j];
+        const int code = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
+        const uint8_t q = hasq ? qual[j] : 0;
+        const size_t i = off + (size_t)j;
+        if (code < 0 || q >= 128) {
+            p->quals[i] = (uint8_t)((q & 0x7F) | 0x80);
+            p->exc_idx.push_back((uint32_t)i); p->exc_base.push_back(c); p->exc_qual.push_back(q);
+        } else p->quals[i] = q;
+        if (code > 0) p->bases2[i >> 2] |= (uint8_t)(code << (2 * (i & 3)));
+    }
+    return PB_OK;
+}
+
+extern "C" int pb_packer_add_many(pb_packer* p, int64_t n, const int32_t* pos, const int32_t* tlen, const uint8_t* mapq,
+                                  const uint8_t* flags, const int32_t* read_len, const uint32_t* cigar_off,
+                                  const uint32_t* cigar, const uint64_t* ascii_off, const uint8_t* seq, const uint8_t* qual) {
+    for (int64_t r = 0; r < n; r++) {
+        const bool hasq = (flags[r] & PB_F_HAS_QUALS) && qual;
+        int rc = pb_packer_add(p, pos[r], tlen[r], mapq[r], flags[r], cigar + cigar_off[r],
+                               (int32_t)(cigar_off[r + 1] - cigar_off[r]), seq + ascii_off[r],
+                               hasq ? qual + ascii_off[r] : nullptr, read_len[r]);
+        if (rc != PB_OK) return rc;
+    }
+    return PB_OK;
+}
+
+extern "C" int pb_packer_view(pb_packer* p, pb_batch* b) {
+    if (!p || !b) return fail(PB_ERR_INVALID, "null");
+    memset(b, 0, sizeof(*b));
+    b->n_reads = (int64_t)p->pos.size(); b->n_cigar = (int64_t)p->cigar.size();
+    b->n_seq = (int64_t)p->quals.size(); b->n_exc = (int64_t)p->exc_idx.size();
+    b->pos = p->pos.data(); b->tlen = p->tlen.data(); b->read_len = p->read_len.data();
+    b->mapq = p->mapq.data(); b->flags = p->flags.data(); b->cigar_off = p->cigar_off.data();
+    b->cigar = p->cigar.data(); b->seq_off = p->seq_off.data(); b->quals = p->quals.data();
+    b->bases2 = p->bases2.data(); b->exc_idx = p->exc_idx.data(); b->exc_base = p->exc_base.data();
+    b->exc_qual = p->exc_qual.data(); b->mem = PB_MEM_HOST;
+    return PB_OK;
+}

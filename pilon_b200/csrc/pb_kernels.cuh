@@ -1,0 +1,641 @@
+// pb_kernels.cuh -- sm_100a kernels of the pileup + BaseCall engine.
+//
+// Pipeline per region:
+//   k_prep      thread per read: CIGAR walk -> segments, sparse updates, indel events, physCov diffs
+//   k_index     per batch: window -> first candidate read table
+//   k_scalars   region coverage / minDepth
+//   (cub merge sort of the indel events) -> k_groups -> k_indel_strings
+//   k_scan1/2/3 physCov prefix sums (PileUpRegion.computePhysCov)
+//   k_pileup    THE hot kernel: warp per 32-locus window gathers every overlapping segment,
+//               accumulates in registers, then runs BaseCall + pass-1 classification and flushes
+//   k_spill     sequential deletion-spill resolution (GenomeRegion.scala:259-264) + fix-up
+//
+// Reference citations are relative to /root/reference/src/main/scala/org/broadinstitute/pilon/.
+#pragma once
+#include "pb_device.cuh"
+
+namespace pb {
+
+static constexpr unsigned FULL = 0xFFFFFFFFu;
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t ref_at(const RegionDev& R, int64_t locus) { return R.ref[locus - R.ref_locus0]; }
+
+__device__ __forceinline__ int64_t exc_find(const DevBatch& B, uint32_t idx) {
+    int64_t lo = 0, hi = B.n_exc;
+    while (lo < hi) { int64_t m = (lo + hi) >> 1; if (B.exc_idx[m] < idx) lo = m + 1; else hi = m; }
+    return lo;   // contract: exc_idx[lo] == idx
+}
+
+// ASCII read byte + raw quality byte of batch base `idx` (what htsjdk's getReadBases / getBaseQualities hold)
+__device__ __forceinline__ void read_base(const DevBatch& B, uint32_t idx, uint8_t* base, uint8_t* qraw) {
+    const uint8_t q = B.quals[idx];
+    if (q & 0x80) {
+        const int64_t p = exc_find(B, idx);
+        *base = B.exc_base[p]; *qraw = B.exc_qual[p];
+    } else {
+        const uint32_t code = (B.bases2[idx >> 2] >> (2 * (idx & 3))) & 3;
+        *base = (uint8_t)("ACGT"[code]); *qraw = q;
+    }
+}
+
+__device__ __forceinline__ void mark_rare(const RegionDev& R, int64_t i) {
+    atomicOr(&R.rare_bits[i >> 5], 1u << (i & 31));
+}
+
+__device__ __forceinline__ uint64_t fnv64(uint64_t h, uint8_t b) { return (h ^ b) * 1099511628211ull; }
+
+// ---------------------------------------------------------------------------------------------
+// k_prep: one thread per read.  PileUpRegion.addRead (PileUpRegion.scala:102-220) minus the
+// per-base adds, which become segments for k_pileup.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t batch_id) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long bc = 0, aligned = 0;
+    int rc = 0, unk = 0, drop = 0, fwd = 0, back = 0;
+    if (r < B.n_reads) {
+        const Cfg& cfg = R.cfg;
+        const int32_t length = B.read_len[r];
+        const int mq = B.mapq[r];
+        const uint8_t fl = B.flags[r];
+        const bool paired = fl & PB_F_PAIRED;
+        const bool valid = (mq >= cfg.min_mq) && (!paired || ((fl & PB_F_PROPER) && (fl & PB_F_MATE_SAME_REF)));  // :107
+        const bool hasq = fl & PB_F_HAS_QUALS;
+        const int32_t aStart = B.pos[r];
+        if (r > 0 && B.pos[r - 1] > aStart) atomicOr(&R.sc->error, 1);     // batch not sorted by pos
+        const uint32_t c0 = B.cigar_off[r], c1 = B.cigar_off[r + 1];
+        const uint32_t seq0 = B.seq_off[r];
+        const int32_t flank = cfg.flank;
+        int64_t clipped = 0, reflen = 0;
+        for (uint32_t k = c0; k < c1; k++) {
+            const uint32_t e = B.cigar[k]; const int op = e & 15; const int64_t len = e >> 4;
+            if (op == 4) clipped += len;                                                        // :139
+            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) reflen += len;
+            if (op == 0 || op == 7 || op == 8) aligned += len;
+        }
+        const int32_t aEnd = (fl & PB_F_UNMAPPED) ? 0 : wrap32((int64_t)aStart + reflen - 1);    // getAlignmentEnd
+        const int32_t adjMq = roundDivI(wrap32((int64_t)mq * (length - clipped)), length);       // :141
+        const int32_t indelMq = adjMq;                                                           // :142 (longRead == 0)
+        const uint32_t segw = (uint32_t)((adjMq + 1) & 0xFFFF) | (hasq ? SEG_HASQ : 0u);
+        const int64_t tlo = flank, thi = (int64_t)length - flank;      // trusted read offsets [tlo, thi)  :118
+        int64_t readOffset = 0, refOffset = 0;
+        for (uint32_t k = c0; k < c1; k++) {
+            const uint32_t e = B.cigar[k]; const int op = e & 15; const int64_t len = e >> 4;
+            const int64_t locus = (int64_t)aStart + refOffset;                                   // :148
+            Seg sg; sg.loc0 = 0; sg.len = 0; sg.src = 0; sg.w = 0;
+            if (op == 0 || op == 7 || op == 8) {                                                 // M = X  :184-193
+                int64_t o0 = readOffset > tlo ? readOffset : tlo;
+                int64_t o1 = readOffset + len < thi ? readOffset + len : thi;
+                if (o1 > o0) {
+                    int64_t l0 = locus + (o0 - readOffset), l1 = l0 + (o1 - o0) - 1;
+                    if (l0 < R.start) { o0 += R.start - l0; l0 = R.start; }
+                    if (l1 > R.stop) l1 = R.stop;
+                    if (l1 >= l0) {
+                        sg.loc0 = (int32_t)(l0 - R.start); sg.len = (int32_t)(l1 - l0 + 1);
+                        sg.src = seq0 + (uint32_t)o0; sg.w = segw | (valid ? SEG_VALID : 0u);
+                        if (valid) bc += (unsigned long long)sg.len;                             // :43
+                    }
+                }
+            } else if (op == 4) {                                                                // S  :194-206
+                const int64_t clipStart = readOffset == 0 ? locus - len : locus;
+                const int64_t clipEnd = clipStart + len - 1;
+                if (clipStart >= R.start && clipStart <= R.stop) { atomicAdd(&R.r_clips[clipStart - R.start], 1); mark_rare(R, clipStart - R.start); }
+                if (clipEnd >= R.start && clipEnd <= R.stop) { atomicAdd(&R.r_clips[clipEnd - R.start], 1); mark_rare(R, clipEnd - R.start); }
+                const int64_t l0 = clipStart > R.start ? clipStart : R.start;
+                const int64_t l1 = clipEnd < R.stop ? clipEnd : R.stop;
+                if (l1 >= l0) { sg.loc0 = (int32_t)(l0 - R.start); sg.len = (int32_t)(l1 - l0 + 1); sg.w = 0; }   // badPair++ each
+            } else if (op == 1) {                                                                // I  :150-162
+                int64_t iloc = locus;
+                if (valid && readOffset >= tlo && readOffset < thi && iloc >= R.start && iloc <= R.stop && len > 0) {
+                    const uint32_t src = seq0 + (uint32_t)readOffset;
+                    int64_t j = len - 1; uint32_t rot = 0; bool dropped = false;
+                    while (iloc > 1) {
+                        uint8_t b, q; read_base(B, src + (uint32_t)j, &b, &q);
+                        if (ref_at(R, iloc - 1) != b) break;                  // refBases(iloc - 2) == insertion(len - 1)
+                        iloc -= 1; rot += 1; j = j == 0 ? len - 1 : j - 1;
+                        if (iloc < R.start) { dropped = true; break; }        // JVM: AIOOBE at pileups(index(iloc))
+                    }
+                    if (dropped) drop++;
+                    else {
+                        const int64_t i = iloc - R.start;
+                        uint8_t b0, q0; read_base(B, src, &b0, &q0);
+                        const int qual = hasq ? (int)(int8_t)q0 : (int)(int8_t)cfg.default_qual;
+                        atomicAdd(&R.r_insq[i], indelMq + 1);                 // PileUp.addInsertion, PileUp.scala:98-105
+                        atomicAdd(&R.r_q[i], qual);
+                        atomicAdd(&R.r_ins[i], 1);
+                        mark_rare(R, i);
+                        // identity of the rotated string: final[t] = orig[(t - rot) mod len]
+                        const uint32_t rm = (uint32_t)(rot % (uint32_t)len);
+                        uint64_t h = 0; bool exact = len <= 28;
+                        uint64_t hh = 1469598103934665603ull;
+                        for (int s2 = 0; s2 < 4; s2++) hh = fnv64(hh, (uint8_t)((uint64_t)len >> (8 * s2)));
+                        for (int64_t t = 0; t < len; t++) {
+                            int64_t sidx = t - rm; if (sidx < 0) sidx += len;
+                            uint8_t b, q; read_base(B, src + (uint32_t)sidx, &b, &q);
+                            const int code = b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : b == 'T' ? 3 : -1;
+                            if (code < 0) exact = false;
+                            if (exact) h |= (uint64_t)code << (2 * t);
+                            hh = fnv64(hh, b);
+                        }
+                        h = exact ? (h | ((uint64_t)len << 56)) : ((hh >> 1) | (1ull << 63));
+                        const uint32_t ei = atomicAdd(&R.sc->n_events, 1u);
+                        if (ei < R.ev_cap) {
+                            R.ev_key[ei].lk = ((uint64_t)i << 1); R.ev_key[ei].h = h;
+                            Event ev; ev.src = src; ev.len = (uint32_t)len; ev.rot = rm; ev.batch = batch_id;
+                            R.ev[ei] = ev;
+                        } else atomicOr(&R.sc->error, 2);
+                    }
+                }
+            } else if (op == 2) {                                                                // D  :163-183
+                int64_t dloc = locus, rloc = readOffset;
+                if (valid && readOffset >= tlo && readOffset < thi && dloc >= R.start && dloc <= R.stop &&
+                    dloc + len - 1 >= R.start && dloc + len - 1 <= R.stop) {
+                    bool dropped = false;
+                    while (dloc > 1 && rloc > 0 && ref_at(R, dloc - 1) == ref_at(R, dloc + len - 1)) {   // refBases(dloc-2) == refBases(dloc+len-2)
+                        dloc -= 1; rloc -= 1;
+                        if (dloc < R.start) { dropped = true; break; }        // JVM: AIOOBE at :182
+                    }
+                    if (dropped) drop++;
+                    else {
+                        // the shift re-adds read bases [rloc, readOffset) at loci rloc' + (locus + len - readOffset)
+                        // when trusted (:174-178); remove() is a no-op for valid reads (:50-58)
+                        int64_t a = rloc > tlo ? rloc : tlo, b = readOffset < thi ? readOffset : thi;
+                        if (b > a) {
+                            sg.loc0 = (int32_t)(a + (locus + len - readOffset) - R.start); sg.len = (int32_t)(b - a);
+                            sg.src = seq0 + (uint32_t)a; sg.w = segw | SEG_VALID;
+                            bc += (unsigned long long)sg.len;
+                        }
+                        const int64_t i = dloc - R.start;
+                        uint8_t b0, q0; read_base(B, seq0 + (uint32_t)readOffset, &b0, &q0);
+                        const int qual = hasq ? (int)(int8_t)q0 : (int)(int8_t)cfg.default_qual;
+                        atomicAdd(&R.r_mq[i], indelMq + 1);                   // PileUp.addDeletion, PileUp.scala:107-114
+                        atomicAdd(&R.r_delq[i], indelMq + 1);
+                        atomicAdd(&R.r_q[i], qual);
+                        atomicAdd(&R.r_del[i], 1);
+                        if (B.frag) atomicAdd(&R.r_delfrag[i], 1);
+                        mark_rare(R, i);
+                        const uint32_t ei = atomicAdd(&R.sc->n_events, 1u);
+                        if (ei < R.ev_cap) {
+                            R.ev_key[ei].lk = ((uint64_t)i << 1) | 1; R.ev_key[ei].h = (uint64_t)len;
+                            Event ev; ev.src = 0; ev.len = (uint32_t)len; ev.rot = 0; ev.batch = batch_id;
+                            R.ev[ei] = ev;
+                        } else atomicOr(&R.sc->error, 2);
+                    }
+                }
+            } else if (op == 5 || op == 3) {                                                     // H, N  :207-210
+            } else unk++;                                                                        // :211-212
+            if (sg.len > 0) {
+                const int64_t f = (int64_t)R.start + sg.loc0 + sg.len - aStart;    // exclusive end relative to pos
+                const int64_t bk = (int64_t)aStart - (R.start + sg.loc0);
+                if (f > fwd) fwd = (int)(f > 0x3fffffff ? 0x3fffffff : f);
+                if (bk > back) back = (int)(bk > 0x3fffffff ? 0x3fffffff : bk);
+            }
+            B.seg[k] = sg;
+            if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) readOffset += len;          // :214
+            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) refOffset += len;           // :215
+        }
+        rc = 1;                                                                                  // :218
+        // physCovIncr, PileUpRegion.scala:62-88
+        int32_t ins = 0;
+        if (valid && !(paired && B.tlen[r] <= 0)) {
+            int64_t s, e;
+            if (!paired) { s = aStart < aEnd ? aStart : aEnd; e = aStart > aEnd ? aStart : aEnd; }
+            else { s = aStart; e = (int64_t)aStart + B.tlen[r]; }
+            ins = wrap32(e - s); s = wrap32(s); e = wrap32(e);
+            if (s >= R.start && s <= R.stop) { atomicAdd(&R.pc_diff[s - R.start].x, 1); atomicAdd(&R.pc_diff[s - R.start].y, ins); }
+            else if (s < R.start && !(e < R.start)) { atomicAdd(&R.sc->phys_cov_start, 1); atomicAdd(&R.sc->insert_size_start, ins); }
+            if (e >= R.start && e <= R.stop) { atomicAdd(&R.pc_diff[e - R.start].x, -1); atomicAdd(&R.pc_diff[e - R.start].y, -ins); }
+        }
+        B.insert_out[r] = ins;
+    }
+    // warp-aggregate the region scalars
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bc += __shfl_xor_sync(FULL, bc, o); aligned += __shfl_xor_sync(FULL, aligned, o);
+        rc += __shfl_xor_sync(FULL, rc, o); unk += __shfl_xor_sync(FULL, unk, o); drop += __shfl_xor_sync(FULL, drop, o);
+        fwd = max(fwd, __shfl_xor_sync(FULL, fwd, o)); back = max(back, __shfl_xor_sync(FULL, back, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (bc) atomicAdd(&R.sc->base_count, bc);
+        if (aligned) atomicAdd(&R.sc->aligned_bases, aligned);
+        if (rc) atomicAdd(&R.sc->read_count, rc);
+        if (unk) atomicAdd(&R.sc->unknown_ops, unk);
+        if (drop) atomicAdd(&R.sc->dropped_oob, drop);
+        if (fwd) atomicMax(&B.reach[0], fwd);
+        if (back) atomicMax(&B.reach[1], back);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_index: win_first[k] = #reads of the batch with (pos - start) < 32*k, k = 0..n_win
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t kmin_of(const RegionDev& R, int32_t pos) {
+    const int64_t d = (int64_t)pos - R.start;
+    if (d < 0) return 0;
+    const int64_t k = (d >> 5) + 1;
+    return k > (int64_t)R.n_win + 1 ? (int64_t)R.n_win + 1 : k;
+}
+
+__global__ void __launch_bounds__(256) k_index(RegionDev R, DevBatch B) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B.n_reads) return;
+    const int64_t k1 = kmin_of(R, B.pos[r]);
+    const int64_t k0 = r == 0 ? 0 : kmin_of(R, B.pos[r - 1]);
+    for (int64_t k = k0; k < k1; k++) B.win_first[k] = (uint32_t)r;
+    if (r == B.n_reads - 1) for (int64_t k = k1; k <= R.n_win; k++) B.win_first[k] = (uint32_t)B.n_reads;
+}
+
+// region coverage and minDepth (PileUpRegion.scala:36; GenomeRegion.scala:221-224)
+__global__ void k_scalars(RegionDev R) {
+    Scalars* sc = R.sc;
+    const long long cov = roundDivL((long long)sc->base_count, R.size);
+    sc->coverage = cov;
+    int md;
+    if (R.cfg.min_depth >= 1) md = (int)R.cfg.min_depth;
+    else {
+        const double v = floor(__dadd_rn(__dmul_rn(R.cfg.min_depth, (double)cov), 0.5));   // Double.round, no FMA contraction
+        md = (int)v > R.cfg.min_min_depth ? (int)v : R.cfg.min_min_depth;
+    }
+    sc->min_depth = md;
+}
+
+// ---------------------------------------------------------------------------------------------
+// indel evidence: sorted events -> one Group per (locus, kind)
+// ---------------------------------------------------------------------------------------------
+struct EventKeyLess {
+    __host__ __device__ bool operator()(const EventKey& a, const EventKey& b) const {
+        return a.lk < b.lk || (a.lk == b.lk && a.h < b.h);
+    }
+};
+
+__device__ __forceinline__ bool key_lt(const EventKey& a, uint64_t lk, uint64_t h) { return a.lk < lk || (a.lk == lk && a.h < h); }
+
+// first index in [lo, hi) whose key is >= (lk, h)
+__device__ __forceinline__ uint32_t key_lower(const EventKey* k, uint32_t lo, uint32_t hi, uint64_t lk, uint64_t h) {
+    while (lo < hi) { uint32_t m = lo + ((hi - lo) >> 1); if (key_lt(k[m], lk, h)) lo = m + 1; else hi = m; }
+    return lo;
+}
+
+// byte t of the string of event e (insertion: rotated read bases; deletion: raw reference bytes)
+__device__ __forceinline__ uint8_t event_byte(const RegionDev& R, const DevBatch* batches, uint64_t lk, const Event& e, uint32_t t) {
+    if (lk & 1) return ref_at(R, (int64_t)R.start + (int64_t)(lk >> 1) + t);     // refBases.slice(dloc-1, dloc+len-1)
+    int64_t s = (int64_t)t - e.rot; if (s < 0) s += e.len;
+    uint8_t b, q; read_base(batches[e.batch], e.src + (uint32_t)s, &b, &q);
+    return b;
+}
+
+// `keys` sorted, `perm[i]` = original event index of sorted position i
+__global__ void __launch_bounds__(256) k_groups(RegionDev R, const DevBatch* batches, const EventKey* keys,
+                                                const uint32_t* perm, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t lk = keys[i].lk;
+    if (i > 0 && keys[i - 1].lk == lk) return;                       // not a group start
+    const uint32_t ge = key_lower(keys, i, n, lk + 1, 0);            // group = [i, ge)
+    const uint32_t len = ge - i;
+    // a strict-majority string (PileUp.scala:219-220) must own the median of the sorted group
+    const uint32_t mid = i + (len >> 1);
+    const uint64_t h = keys[mid].h;
+    const uint32_t rs = key_lower(keys, i, ge, lk, h);
+    const uint32_t re = (h == ~0ull) ? ge : key_lower(keys, rs, ge, lk, h + 1);
+    uint32_t cnt = re - rs;
+    const Event wev = R.ev[perm[rs]];
+    // hashed identities (long / non-ACGT insertions): make sure the run really is one string
+    if ((h >> 63) && !(lk & 1)) {
+        uint32_t same = 0;
+        for (uint32_t j = rs; j < re; j++) {
+            const Event e2 = R.ev[perm[j]];
+            bool eq = e2.len == wev.len;
+            for (uint32_t t = 0; eq && t < wev.len; t++) eq = event_byte(R, batches, lk, e2, t) == event_byte(R, batches, lk, wev, t);
+            same += eq;
+        }
+        if (same != cnt) atomicOr(&R.sc->error, 4);                  // 63-bit hash collision (never observed)
+    }
+    Group g;
+    g.loc = (int32_t)(lk >> 1); g.kind = (int32_t)(lk & 1) + 1; g.list_len = (int32_t)len;
+    const bool majority = cnt >= 2 && cnt > len / 2;
+    g.win_count = majority ? (int32_t)cnt : 0;                       // only a strict majority is ever consumed
+    g.win_len = majority ? (int32_t)wev.len : 0;
+    g.win_ev = perm[rs]; g.pad = 0; g.str_off = 0;
+    int has_n = 0;
+    if (majority) for (uint32_t t = 0; t < wev.len; t++) has_n |= event_byte(R, batches, lk, wev, t) == 'N';   // PileUp.scala:222
+    g.win_has_n = has_n;
+    const uint32_t gi = atomicAdd(&R.sc->n_groups, 1u);
+    if (gi < R.groups_cap) {
+        R.groups[gi] = g;
+        ((lk & 1) ? R.r_gdel : R.r_gins)[g.loc] = gi + 1;            // locus already has its rare bit (k_prep)
+    } else atomicOr(&R.sc->error, 2);
+}
+
+__global__ void __launch_bounds__(128) k_indel_strings(RegionDev R, const DevBatch* batches, uint32_t n_groups) {
+    const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= n_groups) return;
+    Group g = R.groups[gi];
+    const uint64_t off = atomicAdd(&R.sc->str_bytes, (unsigned long long)g.win_len);
+    R.groups[gi].str_off = (int64_t)off;
+    if (off + g.win_len > R.str_cap) { atomicOr(&R.sc->error, 2); return; }
+    const uint64_t lk = ((uint64_t)g.loc << 1) | (uint64_t)(g.kind - 1);
+    const Event e = R.ev[g.win_ev];
+    for (int32_t t = 0; t < g.win_len; t++) R.str_pool[off + t] = event_byte(R, batches, lk, e, (uint32_t)t);
+}
+
+// sparse cleanup of the group-index planes once every consumer is done
+__global__ void __launch_bounds__(128) k_groups_clear(RegionDev R, uint32_t n_groups) {
+    const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= n_groups) return;
+    const Group g = R.groups[gi];
+    (g.kind == 2 ? R.r_gdel : R.r_gins)[g.loc] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// physCov: PileUpRegion.computePhysCov (PileUpRegion.scala:90-100) as a 3-kernel prefix sum over
+// int2 (physCov, insertSize) with 32-bit wrap-around; consumes and re-zeroes the diff plane.
+// ---------------------------------------------------------------------------------------------
+static constexpr int SCAN_THREADS = 256;
+static constexpr int SCAN_ITEMS = 8;
+static constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint2 warp_incl_scan(uint2 v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned x = __shfl_up_sync(FULL, v.x, o), y = __shfl_up_sync(FULL, v.y, o);
+        if (lane >= o) { v.x += x; v.y += y; }
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan1(RegionDev R, uint2* block_sums) {
+    __shared__ uint2 wsum[SCAN_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    uint2 acc = make_uint2(0, 0);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const int64_t i = base + (int64_t)k * SCAN_THREADS + threadIdx.x;
+        if (i < R.size) { const int2 d = R.pc_diff[i]; acc.x += (unsigned)d.x; acc.y += (unsigned)d.y; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { acc.x += __shfl_xor_sync(FULL, acc.x, o); acc.y += __shfl_xor_sync(FULL, acc.y, o); }
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint2 t = make_uint2(0, 0);
+        for (int w = 0; w < SCAN_THREADS / 32; w++) { t.x += wsum[w].x; t.y += wsum[w].y; }
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+// single block: exclusive scan of the block sums, seeded with the carry-in (:91-92)
+__global__ void __launch_bounds__(1024) k_scan2(RegionDev R, uint2* block_sums, int nblocks) {
+    __shared__ uint2 wtot[32];
+    __shared__ uint2 carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = make_uint2((unsigned)R.sc->phys_cov_start, (unsigned)R.sc->insert_size_start);
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        uint2 v = i < nblocks ? block_sums[i] : make_uint2(0, 0);
+        const uint2 inc = warp_incl_scan(v, lane);
+        if (lane == 31) wtot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) { uint2 t = wtot[lane]; t = warp_incl_scan(t, lane); wtot[lane] = t; }
+        __syncthreads();
+        uint2 ex = make_uint2(inc.x - v.x, inc.y - v.y);
+        if (warp > 0) { ex.x += wtot[warp - 1].x; ex.y += wtot[warp - 1].y; }
+        const uint2 c = carry_s;
+        if (i < nblocks) block_sums[i] = make_uint2(ex.x + c.x, ex.y + c.y);
+        __syncthreads();
+        if (threadIdx.x == 0) { carry_s.x += wtot[31].x; carry_s.y += wtot[31].y; }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan3(RegionDev R, const uint2* block_sums) {
+    __shared__ uint2 wtot[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // blocked arrangement: thread t owns items [t*ITEMS, t*ITEMS + ITEMS) of the tile
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint2 v[SCAN_ITEMS];
+    uint2 run = make_uint2(0, 0);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const int64_t i = base + k;
+        int2 d = make_int2(0, 0);
+        if (i < R.size) { d = R.pc_diff[i]; R.pc_diff[i] = make_int2(0, 0); }
+        run.x += (unsigned)d.x; run.y += (unsigned)d.y;
+        v[k] = run;
+    }
+    const uint2 inc = warp_incl_scan(run, lane);
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    uint2 off = block_sums[blockIdx.x];
+    off.x += inc.x - run.x; off.y += inc.y - run.y;
+    for (int w = 0; w < warp; w++) { off.x += wtot[w].x; off.y += wtot[w].y; }
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const int64_t i = base + k;
+        if (i < R.size) {
+            const int32_t pc = (int32_t)(v[k].x + off.x);
+            int32_t is = (int32_t)(v[k].y + off.y);
+            if (pc > 0) is /= pc;                                                               // :97-99
+            R.o_pc[i] = pc; R.o_is[i] = is;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_pileup: the hot kernel.
+//
+// One warp owns a window of 32 consecutive loci (lane <-> locus) and keeps the ten hot counters
+// of PileUp.add (PileUp.scala:75-84) in registers: no atomics on the per-base path.  Candidate
+// segments are fetched 32 at a time with one coalesced 512-byte load (lane <-> descriptor); a
+// ballot keeps only those that overlap the window, and their descriptors are broadcast with
+// shuffles.  For each overlapping segment every lane reads its own (quality, 2-bit base) pair --
+// consecutive lanes read consecutive bytes -- and accumulates.  The epilogue merges the sparse
+// contributions, runs BaseCall and pass-1 classification and writes every per-locus output once.
+// ---------------------------------------------------------------------------------------------
+static constexpr int PILEUP_WARPS = 8;
+
+template <bool MINQ>
+__global__ void __launch_bounds__(PILEUP_WARPS * 32) k_pileup(RegionDev R, const DevBatch* __restrict__ batches, int n_batches) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * PILEUP_WARPS + (threadIdx.x >> 5);
+    if (w >= R.n_win) return;
+    const int32_t w0 = (int32_t)(w << 5);
+    const int32_t loc = w0 + lane;
+    const int min_qual = R.cfg.min_qual;
+    const uint32_t defq = (uint32_t)(int)(int8_t)R.cfg.default_qual;
+
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    uint64_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+    uint32_t mqS = 0, qS = 0, bp = 0, fragN = 0;
+
+    for (int b = 0; b < n_batches; b++) {
+        const DevBatch& B = batches[b];
+        if (B.n_reads == 0) continue;
+        const uint32_t nbefore = c0 + c1 + c2 + c3;
+        const int32_t fwd = B.reach[0], back = B.reach[1];
+        // candidate reads: (pos - start) in (w0 - fwd, w0 + 32 + back)
+        int64_t x = (int64_t)w0 - fwd + 1; if (x < 0) x = 0;
+        const int64_t klo = x >> 5;
+        int64_t khi = (((int64_t)w0 + 32 + back) + 31) >> 5; if (khi > R.n_win) khi = R.n_win;
+        const uint32_t rlo = B.win_first[klo];
+        const uint32_t rhi = (((int64_t)w0 + 32 + back) > ((int64_t)R.n_win << 5)) ? (uint32_t)B.n_reads : B.win_first[khi];
+        const uint32_t slo = B.cigar_off[rlo], shi = B.cigar_off[rhi];
+        const uint8_t* __restrict__ quals = B.quals;
+        const uint8_t* __restrict__ bases2 = B.bases2;
+        for (uint32_t sb = slo; sb < shi; sb += 32) {
+            Seg mine; mine.loc0 = 0; mine.len = 0; mine.src = 0; mine.w = 0;
+            if (sb + lane < shi) mine = B.seg[sb + lane];
+            const bool ov = mine.len > 0 && mine.loc0 < w0 + 32 && mine.loc0 + mine.len > w0;
+            unsigned m = __ballot_sync(FULL, ov);
+            while (m) {
+                const int j = __ffs(m) - 1; m &= m - 1;
+                const int32_t sl0 = __shfl_sync(FULL, mine.loc0, j);
+                const int32_t sln = __shfl_sync(FULL, mine.len, j);
+                const uint32_t ssrc = __shfl_sync(FULL, mine.src, j);
+                const uint32_t sw = __shfl_sync(FULL, mine.w, j);
+                const uint32_t off = (uint32_t)(loc - sl0);
+                if (off < (uint32_t)sln) {
+                    if (sw & SEG_VALID) {
+                        const uint32_t idx = ssrc + off;
+                        const uint32_t qb = quals[idx];
+                        const uint32_t code = (bases2[idx >> 2] >> ((idx & 3) << 1)) & 3;
+                        if (!(qb & 0x80)) {                               // countable base (PileUp.scala:46-52)
+                            const uint32_t q = (sw & SEG_HASQ) ? qb : defq;
+                            if (!MINQ || (int)q >= min_qual) {            // PileUp.scala:77
+                                const uint32_t mq1 = sw & 0xFFFF;
+                                const uint32_t qm = q * mq1;
+                                c0 += code == 0; c1 += code == 1; c2 += code == 2; c3 += code == 3;
+                                q0 += code == 0 ? qm : 0; q1 += code == 1 ? qm : 0;
+                                q2 += code == 2 ? qm : 0; q3 += code == 3 ? qm : 0;
+                                mqS += mq1; qS += q;
+                            }
+                        }
+                    } else bp++;                                          // PileUpRegion.scala:45
+                }
+            }
+        }
+        if (B.frag) fragN += (c0 + c1 + c2 + c3) - nbefore;
+    }
+
+    // ---- epilogue: merge sparse contributions, BaseCall, pass-1 classification, flush -------
+    const bool inr = loc < R.size;
+    const uint32_t rb = R.rare_bits[w];
+    int32_t r_ins = 0, r_insq = 0, r_del = 0, r_delq = 0, r_q = 0, r_mq = 0, r_clips = 0, r_delfrag = 0;
+    uint32_t gi = 0, gd = 0;
+    if (inr && ((rb >> lane) & 1)) {
+        r_ins = R.r_ins[loc]; r_insq = R.r_insq[loc]; r_del = R.r_del[loc]; r_delq = R.r_delq[loc];
+        r_q = R.r_q[loc]; r_mq = R.r_mq[loc]; r_clips = R.r_clips[loc]; r_delfrag = R.r_delfrag[loc];
+        gi = R.r_gins[loc]; gd = R.r_gdel[loc];
+        R.r_ins[loc] = 0; R.r_insq[loc] = 0; R.r_del[loc] = 0; R.r_delq[loc] = 0;
+        R.r_q[loc] = 0; R.r_mq[loc] = 0; R.r_clips[loc] = 0; R.r_delfrag[loc] = 0;
+    }
+    if (rb && lane == 0) R.rare_bits[w] = 0;
+    uint32_t cand = 0;
+    if (inr) {
+        CallIn in;
+        in.c[0] = c0; in.c[1] = c1; in.c[2] = c2; in.c[3] = c3;
+        in.q[0] = (int64_t)q0; in.q[1] = (int64_t)q1; in.q[2] = (int64_t)q2; in.q[3] = (int64_t)q3;
+        in.mqSum = (int32_t)(mqS + (uint32_t)r_mq); in.qSum = (int32_t)(qS + (uint32_t)r_q);
+        in.ins = r_ins; in.del = r_del; in.insQual = r_insq; in.delQual = r_delq;
+        in.gins = gi ? &R.groups[gi - 1] : nullptr; in.gdel = gd ? &R.groups[gd - 1] : nullptr;
+        int32_t ilen = 0;
+        const uint64_t call = compute_call(R.cfg, in, &ilen);
+        const int64_t n = (int64_t)c0 + c1 + c2 + c3;
+        const int64_t depth = n + r_del;
+        const int64_t qtot = in.q[0] + in.q[1] + in.q[2] + in.q[3];
+        uint32_t fl = 0;
+        if (R.sc->read_count != 0)                                       // GenomeRegion.scala:229-231
+            fl = classify(call, depth, R.sc->min_depth, ref_class(ref_at(R, (int64_t)R.start + loc)), R.cfg.fix_amb);
+        reinterpret_cast<int4*>(R.o_cnt)[loc] = make_int4((int)c0, (int)c1, (int)c2, (int)c3);
+        reinterpret_cast<longlong2*>(R.o_qs)[2 * (int64_t)loc] = make_longlong2((long long)q0, (long long)q1);
+        reinterpret_cast<longlong2*>(R.o_qs)[2 * (int64_t)loc + 1] = make_longlong2((long long)q2, (long long)q3);
+        R.o_mq[loc] = in.mqSum; R.o_q[loc] = in.qSum; R.o_bp[loc] = (int32_t)bp;
+        R.o_del[loc] = r_del; R.o_delq[loc] = r_delq; R.o_ins[loc] = r_ins; R.o_insq[loc] = r_insq;
+        R.o_clips[loc] = r_clips;
+        R.o_cov[loc] = wrap32(depth);                                    // GenomeRegion.scala:247
+        R.o_frag[loc] = (int32_t)(fragN + (uint32_t)r_delfrag);          // GenomeRegion.scala:296-298
+        R.o_wq[loc] = (int8_t)(uint8_t)roundDivL(qtot, in.mqSum);        // PileUp.scala:60-62, .toByte
+        R.o_wmq[loc] = (int8_t)(uint8_t)roundDivL(qtot, in.qSum);        // PileUp.scala:56-58, .toByte
+        R.o_flags[loc] = (uint8_t)fl;
+        R.o_call[loc] = call;
+        if ((fl & PB_FL_CHANGED) && ((fl >> PB_FL_KIND_SHIFT) & 3) == PB_KIND_DEL) {
+            cand = 1; R.cand_len[loc] = ilen;
+            const uint32_t ci = atomicAdd(&R.sc->n_cand, 1u);
+            if (ci < R.cand_cap) R.cand[ci] = make_int2(loc, r_del); else atomicOr(&R.sc->error, 2);
+        }
+    }
+    (void)cand;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_spill: GenomeRegion.scala:259-264.  Pass 1 walks loci in ascending order; a homozygous
+// deletion called at locus i marks i+1 .. i+len-1 deleted and adds its `deletions` to theirs;
+// deleted loci make no calls.  Candidates (computed in parallel, ignoring `deleted`) are sorted
+// by locus, accepted/rejected with a sequential watermark, then applied in parallel.
+// Single CTA; the candidate list is tiny (one entry per homozygous deletion call).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bitonic_sort_by_x(int2* a, uint32_t npow2) {
+    for (uint32_t k = 2; k <= npow2; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < npow2; t += blockDim.x) {
+                const uint32_t ixj = t ^ j;
+                if (ixj > t) {
+                    const int2 A = a[t], Bv = a[ixj];
+                    const bool up = (t & k) == 0;
+                    if ((A.x > Bv.x) == up) { a[t] = Bv; a[ixj] = A; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+__global__ void __launch_bounds__(1024) k_spill(RegionDev R, int2* scratch, uint32_t scratch_cap) {
+    extern __shared__ int2 sm[];
+    const uint32_t n = min(R.sc->n_cand, R.cand_cap);
+    if (n == 0) return;
+    uint32_t p2 = 1; while (p2 < n) p2 <<= 1;
+    int2* a = (p2 <= 4096) ? sm : scratch;            // 32 KB of shared memory, else the global scratch
+    if (p2 > scratch_cap && a == scratch) { if (threadIdx.x == 0) atomicOr(&R.sc->error, 2); return; }
+    for (uint32_t t = threadIdx.x; t < p2; t += blockDim.x) a[t] = t < n ? R.cand[t] : make_int2(0x7fffffff, 0);
+    __syncthreads();
+    bitonic_sort_by_x(a, p2);
+    // sequential watermark: y < 0 marks a rejected candidate
+    if (threadIdx.x == 0) {
+        int64_t deleted_until = -1;
+        for (uint32_t t = 0; t < n; t++) {
+            const int32_t loc = a[t].x;
+            if (loc <= deleted_until) { a[t].y = -1 - a[t].y; continue; }    // it is deleted: makes no call
+            const int64_t end = (int64_t)loc + R.cand_len[loc] - 1;
+            if (end > deleted_until) deleted_until = end;
+        }
+    }
+    __syncthreads();
+    // apply: every deleted locus belongs to exactly one accepted deletion
+    for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
+        const int32_t loc = a[t].x, d = a[t].y;
+        if (d < 0) continue;
+        const int32_t L = R.cand_len[loc];
+        for (int32_t j = 1; j < L; j++) {
+            const int64_t i = (int64_t)loc + j;
+            const int32_t nd = wrap32((int64_t)R.o_del[i] + d);                                  // :263
+            R.o_del[i] = nd;
+            const int4 c = reinterpret_cast<const int4*>(R.o_cnt)[i];
+            const longlong2 qa = reinterpret_cast<const longlong2*>(R.o_qs)[2 * i], qb = reinterpret_cast<const longlong2*>(R.o_qs)[2 * i + 1];
+            CallIn in;
+            in.c[0] = c.x; in.c[1] = c.y; in.c[2] = c.z; in.c[3] = c.w;
+            in.q[0] = qa.x; in.q[1] = qa.y; in.q[2] = qb.x; in.q[3] = qb.y;
+            in.mqSum = R.o_mq[i]; in.qSum = R.o_q[i]; in.ins = R.o_ins[i]; in.del = nd;
+            in.insQual = R.o_insq[i]; in.delQual = R.o_delq[i];
+            const uint32_t gi = R.r_gins[i], gd = R.r_gdel[i];
+            in.gins = gi ? &R.groups[gi - 1] : nullptr; in.gdel = gd ? &R.groups[gd - 1] : nullptr;
+            R.o_call[i] = compute_call(R.cfg, in, nullptr);          // what Vcf.writeRecord recomputes (Vcf.scala:78-79)
+            R.o_cov[i] = wrap32((int64_t)c.x + c.y + c.z + c.w + nd);                            // :247 sees the spilled count
+            R.o_flags[i] = PB_FL_DELETED;                                                        // :262, and :255 makes no call
+        }
+    }
+}
+
+}  // namespace pb

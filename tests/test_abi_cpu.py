@@ -1,0 +1,80 @@
+"""CPU-only checks of the boundary: the C-ABI library loads, exports every symbol the header
+declares, and the host packer agrees with the numpy packer.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import random
+import re
+
+import numpy as np
+
+from pilon_b200 import _capi as capi
+from pilon_b200.packing import pack_records
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "pilon_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pb_[a-z_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load_library()
+    names = declared_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), "libpilonb200.so does not export %s" % n
+    assert lib.pb_abi_version() == 1
+
+
+def test_struct_sizes_match_header():
+    # sizes implied by the header's field lists (LP64)
+    assert C.sizeof(capi.pb_config) == 40
+    assert C.sizeof(capi.pb_batch) == 4 * 8 + 13 * 8 + 8
+    assert C.sizeof(capi.pb_indel) == 32
+    assert C.sizeof(capi.pb_region_result) == 4 * 8 + 4 * 4 + 2 * 8 + 18 * 8 + 4 * 8
+
+
+def test_engine_rejects_bad_arguments_without_a_gpu():
+    lib = capi.load_library()
+    h = C.c_void_p()
+    cfg = capi.pb_config(min_qual=-1, default_qual=10, flank=10, min_min_depth=5, min_depth=0.1)
+    assert lib.pb_create(0, C.byref(cfg), C.byref(h)) == capi.PB_ERR_UNSUPPORTED
+    assert b"min_qual" in lib.pb_last_error()
+
+
+def test_c_packer_matches_numpy_packer():
+    lib = capi.load_library()
+    for seed in range(5):
+        contig, start, stop, reads = H.random_case(seed)
+        want = pack_records(reads)
+        pk = C.c_void_p()
+        assert lib.pb_packer_create(C.byref(pk)) == 0
+        for r in reads:
+            cig = np.array([(l << 4) | capi.CIGAR_OPS.index(op) for op, l in r.cigar], np.uint32)
+            seq = np.frombuffer(r.bases, np.uint8)
+            # BAM stores missing qualities as 0xFF bytes
+            q = np.frombuffer(r.quals if len(r.quals) else b"\xff" * len(r.bases), np.uint8)
+            flags = 0
+            for bit, on in ((1, r.paired), (2, r.proper), (4, r.mate_same_ref), (16, r.unmapped), (32, r.reverse)):
+                flags |= bit if on else 0
+            assert lib.pb_packer_add(pk, r.pos, r.tlen, r.mapq, flags, cig.ctypes.data, len(cig),
+                                     seq.ctypes.data, q.ctypes.data, len(seq)) == 0
+        b = capi.pb_batch()
+        assert lib.pb_packer_view(pk, C.byref(b)) == 0
+        assert (b.n_reads, b.n_cigar, b.n_seq, b.n_exc) == (want.n_reads, len(want.cigar), len(want.quals), len(want.exc_idx))
+
+        def arr(ptr, n, dt):
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(dt)), shape=(max(n, 1),))[:n].copy()
+        assert np.array_equal(arr(b.pos, b.n_reads, C.c_int32), want.pos)
+        assert np.array_equal(arr(b.flags, b.n_reads, C.c_uint8), want.flags)
+        assert np.array_equal(arr(b.cigar, b.n_cigar, C.c_uint32), want.cigar)
+        assert np.array_equal(arr(b.seq_off, b.n_reads, C.c_uint32), want.seq_off)
+        assert np.array_equal(arr(b.quals, b.n_seq, C.c_uint8), want.quals)
+        assert np.array_equal(arr(b.bases2, b.n_seq // 4, C.c_uint8), want.bases2)
+        assert np.array_equal(arr(b.exc_idx, b.n_exc, C.c_uint32), want.exc_idx)
+        assert np.array_equal(arr(b.exc_base, b.n_exc, C.c_uint8), want.exc_base)
+        assert np.array_equal(arr(b.exc_qual, b.n_exc, C.c_uint8), want.exc_qual)
+        lib.pb_packer_destroy(pk)

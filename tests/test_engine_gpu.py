@@ -1,0 +1,212 @@
+"""Parity tests proper: the CUDA engine, called through the C ABI, against the oracles.
+Bit-exact on every counter, flag and call record (integer path; no floating-point tolerance)."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import pilon_oracle as po
+from pilon_b200 import _capi as capi
+from pilon_b200.engine import Engine, EngineConfig, PileUpRegion
+from pilon_b200.packing import pack_records
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def eng_cfg(cfg: po.Config) -> EngineConfig:
+    return EngineConfig(cfg.minQual, cfg.minMq, cfg.flank, cfg.defaultQual, cfg.minMinDepth, cfg.minDepth,
+                        cfg.oldIndel, cfg.iupac, cfg.fixAmb)
+
+
+@pytest.fixture(scope="module")
+def engine():
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def run_both(engine, contig, start, stop, groups, cfg=None):
+    packed = [(pack_records(g), f) for g, f in groups]
+    res, ins = engine.run_region(contig, start, stop, packed)
+    ref, ins_ref = H.run_c_oracle(contig, start, stop, packed, cfg)
+    H.assert_results_equal(res, ref, "engine vs C oracle")
+    for a, b in zip(ins, ins_ref):
+        assert np.array_equal(a, b)
+    return res, ins
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_random_cases_match_both_oracles(seed):
+    contig, start, stop, reads = H.random_case(seed)
+    rng = random.Random(seed * 7 + 1)
+    groups = H.split_batches(reads, rng)
+    cfg = po.Config()
+    if seed % 5 == 1:
+        cfg = po.Config(minQual=7, minMq=2, flank=rng.choice([0, 3, 10]), defaultQual=rng.choice([3, 10, 15]))
+    if seed % 7 == 3:
+        cfg.oldIndel = True
+    if seed % 11 == 4:
+        cfg.minDepth = 3.0
+    if seed % 13 == 5:
+        cfg.fixAmb = True
+    e = Engine(0, eng_cfg(cfg))
+    try:
+        res, ins = run_both(e, contig, start, stop, groups, cfg)
+        py = H.run_py_oracle(contig, start, stop, groups, cfg)
+        H.assert_matches_py(res, ins, py, "engine vs python oracle, seed %d" % seed)
+    finally:
+        e.close()
+
+
+def test_kat1_through_c_abi(engine):
+    ref = (b"ACGT" * 30)[:100]
+    rd = po.Read(pos=11, cigar=[("M", 30)], bases=ref[10:40], quals=bytes([30]) * 30, mapq=60)
+    res, ins = engine.run_region(ref, 1, 100, [(pack_records([rd]), True)])
+    assert res.c.base_count == 10 and res.c.read_count == 1 and int(ins[0][0]) == 29
+    cnt, qs = res["base_count4"], res["qual_sum4"]
+    for locus in range(1, 101):
+        i = locus - 1
+        if 21 <= locus <= 30:
+            bi = b"ACGT".index(ref[i])
+            assert cnt[i][bi] == 1 and cnt[i].sum() == 1 and qs[i][bi] == 1830
+            assert res["mq_sum"][i] == 61 and res["q_sum"][i] == 30
+        else:
+            assert cnt[i].sum() == 0
+        assert res["phys_cov"][i] == (1 if 11 <= locus <= 39 else 0)
+        assert res["insert_size"][i] == (29 if 11 <= locus <= 39 else 0)
+
+
+def test_kat7_deletion_shift_through_c_abi(engine):
+    ref = bytearray(b"C" * 300)
+    for l in range(101, 105):
+        ref[l - 1] = ord("A")
+    ref[99], ref[104] = ord("G"), ord("T")
+    ref = bytes(ref)
+    pos = 101 - 47
+    rb = ref[pos - 1:pos - 1 + 50] + ref[104:104 + 50]
+    rd = po.Read(pos=pos, cigar=[("M", 50), ("D", 1), ("M", 50)], bases=rb, quals=bytes([30]) * 100, mapq=60)
+    res, _ = engine.run_region(ref, 1, 300, [(pack_records([rd]), True)])
+    assert [int(res["base_count4"][l - 1][0]) for l in (101, 102, 103, 104)] == [1, 2, 2, 1]
+    assert res["deletions"][100] == 1 and res.c.base_count == 83
+    ind = res.indels()
+    assert len(ind) == 1 and ind[0]["locus_index"] == 100 and ind[0]["kind"] == 2 and ind[0]["list_len"] == 1
+
+
+def test_empty_region_and_zero_reads(engine):
+    contig = H.random_contig(random.Random(3), 500)
+    empty = pack_records([])
+    res, _ = engine.run_region(contig, 10, 400, [(empty, True)])
+    ref, _ = H.run_c_oracle(contig, 10, 400, [(empty, True)])
+    H.assert_results_equal(res, ref)
+    assert res.c.read_count == 0 and not res["flags"].any()
+    res2, _ = engine.run_region(contig, 10, 400, [])
+    H.assert_results_equal(res2, ref)
+
+
+def test_unsorted_batch_is_rejected(engine):
+    contig = H.random_contig(random.Random(4), 300)
+    q = bytes([30]) * 20
+    a = po.Read(pos=100, cigar=[("M", 20)], bases=contig[99:119].upper(), quals=q)
+    b = po.Read(pos=50, cigar=[("M", 20)], bases=contig[49:69].upper(), quals=q)
+    with pytest.raises(capi.EngineError) as ei:
+        engine.run_region(contig, 1, 300, [(pack_records([a, b]), True)])
+    assert ei.value.code == capi.PB_ERR_UNSORTED
+    # the engine must be reusable (and clean) after a failed region
+    res, _ = engine.run_region(contig, 1, 300, [(pack_records([b, a]), True)])
+    ref, _ = H.run_c_oracle(contig, 1, 300, [(pack_records([b, a]), True)])
+    H.assert_results_equal(res, ref)
+
+
+def test_engine_reuse_across_regions_leaves_no_residue(engine):
+    # sparse planes are self-cleaning: a second, different region on the same handle must be exact
+    for seed in (101, 102, 103, 104):
+        contig, start, stop, reads = H.random_case(seed, contig_len=700, n_reads=300)
+        run_both(engine, contig, start, stop, [(reads, True)])
+
+
+@pytest.mark.parametrize("seed,depth", [(1, 30), (2, 120)])
+def test_medium_synthetic_region(engine, seed, depth):
+    """A few tens of thousands of loci: many windows, halo reads on both sides, chunk boundaries."""
+    rng = random.Random(seed)
+    n = 30000
+    contig = H.random_contig(rng, n, n_runs=4)
+    start, stop = 2001, 26000
+    nreads = depth * (stop - start + 2000) // 100
+    reads = [H.random_read(rng, contig, start - 1000, stop + 1000, max_len=110) for _ in range(nreads)]
+    for _ in range(30):
+        reads += H.planted_indel_cluster(rng, contig, start, stop)
+        reads += H.planted_snp_cluster(rng, contig, start, stop)
+    reads.sort(key=lambda r: r.pos)
+    half = [r for i, r in enumerate(reads) if i % 3 != 0], [r for i, r in enumerate(reads) if i % 3 == 0]
+    res, _ = run_both(engine, contig, start, stop, [(half[0], True), (half[1], False)])
+    fl = res["flags"]
+    assert (fl & capi.PB_FL_CONFIRMED).any() and (fl & capi.PB_FL_CHANGED).any() and (fl & capi.PB_FL_DELETED).any()
+
+
+def test_high_depth_single_locus_contention(engine):
+    """5000x on a tiny region (config 5's shape): every read hits the same windows."""
+    rng = random.Random(9)
+    contig = H.random_contig(rng, 600)
+    reads = []
+    for _ in range(5000):
+        pos = rng.randint(1, 450)
+        L = min(100, 600 - pos + 1)
+        b = bytearray(contig[pos - 1:pos - 1 + L].upper())
+        if rng.random() < 0.3:
+            b[rng.randrange(L)] = rng.choice(b"ACGT")
+        reads.append(po.Read(pos=pos, cigar=[("M", L)], bases=bytes(b), quals=bytes(rng.randint(2, 41) for _ in range(L)),
+                             mapq=rng.choice([0, 20, 60]), paired=True, proper=rng.random() < 0.97,
+                             tlen=rng.choice([300, -300])))
+    reads.sort(key=lambda r: r.pos)
+    run_both(engine, contig, 1, 600, [(reads, True)])
+
+
+def test_determinism(engine):
+    contig, start, stop, reads = H.random_case(77, contig_len=2000, n_reads=900)
+    packed = [(pack_records(reads), True)]
+    a, _ = engine.run_region(contig, start, stop, packed)
+    b, _ = engine.run_region(contig, start, stop, packed)
+    H.assert_results_equal(a, b)
+
+
+def test_compute_timed_is_repeatable_and_leaves_engine_clean(engine):
+    contig, start, stop, reads = H.random_case(55, contig_len=3000, n_reads=1500)
+    packed = pack_records(reads)
+    engine.region_begin(contig, start, stop)
+    engine.add_batch(packed, True)
+    tot, pil, launches = engine.compute_timed(3)
+    assert tot > 0 and pil > 0 and launches >= 3 * 6
+    from pilon_b200.packing import ResultBuffers
+    res = ResultBuffers(stop + 1 - start, indels_cap=1 << 16, indel_bytes_cap=1 << 20)
+    engine.finish(res, [np.zeros(packed.n_reads, np.int32)])
+    ref, _ = H.run_c_oracle(contig, start, stop, [(packed, True)])
+    H.assert_results_equal(res, ref)
+
+
+def test_facade_mirrors_reference_surface():
+    contig, start, stop, reads = H.random_case(12, contig_len=600, n_reads=250)
+    pur = PileUpRegion("c", start, stop, contig)
+    gr = po.GenomeRegionHot(contig, start, stop)
+    gr.initializePileUps(oob_drop=True)
+    rets = [pur.addRead(r, contig) for r in reads]
+    gr.processBam(reads, "frags")
+    assert rets == [x[0] for x in gr.insert_sizes]
+    pur.postProcess()
+    gr.postProcess()
+    o = gr.pileUpRegion
+    assert (pur.readCount, pur.baseCount, pur.coverage, pur.minDepth) == (o.readCount, o.baseCount, o.coverage, gr.minDepth)
+    for i in range(pur.size):
+        a, b = pur[i], o[i]
+        assert (a.depth, a.count, a.badPair, a.physCov, a.insertSize, a.clips, a.deletions, a.insertions) == \
+               (b.depth, b.count, b.badPair, b.physCov, b.insertSize, b.clips, b.deletions, b.insertions)
+        assert (a.weightedQual, a.weightedMq, a.meanQual, a.meanMq, a.insPct, a.delPct) == \
+               (b.weightedQual, b.weightedMq, b.meanQual, b.meanMq, b.insPct, b.delPct)
+        assert str(a.baseCount) == str(b.baseCount) and a.qualSum.toStringPct() == b.qualSum.toStringPct()
+        ca, cb = a.baseCall(), b.baseCall()
+        assert (ca.base, ca.altBase, ca.homo, ca.score, ca.q, ca.highConfidence, ca.called, ca.indel, ca.homoIndel) == \
+               (cb.base, cb.altBase, cb.homo, cb.score, cb.q, cb.highConfidence, cb.called, cb.indel, cb.homoIndel)
+        assert (ca.insertion, ca.deletion, ca.callString(), ca.baseSum, ca.altBaseSum) == \
+               (cb.insertion, cb.deletion, cb.callString(), cb.baseSum, cb.altBaseSum)
+    kinds = {po.SNP: 0, po.INS: 1, po.DEL: 2, po.AMB: 3}
+    assert pur.changes() == sorted((i, kinds[k]) for i, (k, _) in gr.changeMap.items())
