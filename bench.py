@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py -- aligned pileup bases/sec of the pileup + BaseCall hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--scale 1.0]
+  python bench.py --impl reference ...      # the CPU restatement of the reference path on host cores
+
+A "step" is one pass of the whole hot path (prep -> physCov scan -> indel grouping -> pileup+BaseCall
+-> deletion spill) over every region of the workload.  `value` is measured with the packed read
+batches already resident in HBM (CUDA events on the engine streams); `e2e` runs the same regions
+through the public C ABI from pinned HOST buffers, host->device copies of the reads and the
+device->host copy of the per-locus results inside the timed region.
+
+Under torchrun each rank owns one GPU and its own copy-sized workload (regions are independent, no
+data-path collective): scaling is weak, the job value is total bases / max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "aligned pileup bases/sec"
+UNIT = "bases/s"
+# planes the Scala driver reads back for `--fix snps,indels --changes` (GenomeRegion.scala:247-253 +
+# flags + call record for the change list); --vcf needs every counter
+FIX_PLANES = ["coverage_arr", "bad_pair", "phys_cov", "insert_size", "weighted_qual", "weighted_mq", "clips",
+              "frag_coverage", "flags", "call"]
+
+
+def algorithmic_bytes(aligned: int, n_reads: int, n_cigar: int, loci: int) -> float:
+    """per aligned base 1.25 B (2-bit base + quality) + per read 24 B + 4 B per CIGAR op
+    + per locus 88 B counters out + 1 B reference in + 8 B call record out."""
+    return 1.25 * aligned + 24.0 * n_reads + 4.0 * n_cigar + 97.0 * loci
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------
+class Region:
+    def __init__(self, wl, ci, start, stop, contig_np):
+        self.ci, self.start, self.stop = ci, start, stop
+        self.size = stop + 1 - start
+        self.contig = contig_np                      # whole contig, uint8
+        self.batches = wl.region_batches(ci, start, stop)
+        self.aligned = sum(b.aligned_bases for b in self.batches)
+        self.n_reads = sum(b.n_reads for b in self.batches)
+        self.n_cigar = sum(b.c.n_cigar for b in self.batches)
+        self.alg_bytes = algorithmic_bytes(self.aligned, self.n_reads, self.n_cigar, self.size)
+
+
+def build_workload(name, scale, seed_shift, threads):
+    from pilon_b200 import synth
+    os.environ.setdefault("OMP_NUM_THREADS", str(max(1, threads)))
+    wl = synth.workload(name, scale)
+    wl.seed += 1000 * seed_shift
+    contigs = {}
+    regions = []
+    for ci, a, b in wl.regions():
+        if ci not in contigs:
+            contigs[ci] = wl.contig_bases(ci)
+        regions.append(Region(wl, ci, a, b, contigs[ci]))
+    return wl, regions
+
+
+_BATCH_FIELDS = [("pos", "n_reads", 4), ("tlen", "n_reads", 4), ("read_len", "n_reads", 4), ("mapq", "n_reads", 1),
+                 ("flags", "n_reads", 1), ("cigar_off", "n_reads+1", 4), ("cigar", "n_cigar", 4),
+                 ("seq_off", "n_reads", 4), ("quals", "n_seq", 1), ("bases2", "n_seq/4", 1),
+                 ("exc_idx", "n_exc", 4), ("exc_base", "n_exc", 1), ("exc_qual", "n_exc", 1)]
+
+
+def _field_bytes(c, count, width):
+    n = {"n_reads": c.n_reads, "n_reads+1": c.n_reads + 1, "n_cigar": c.n_cigar, "n_seq": c.n_seq,
+         "n_seq/4": c.n_seq // 4, "n_exc": c.n_exc}[count]
+    return int(n) * width
+
+
+def device_batch(torch, c, dev):
+    """Copy one host pb_batch to the GPU; returns (pb_batch with PB_MEM_DEVICE, keepalive tensors)."""
+    from pilon_b200 import _capi as capi
+    d = capi.pb_batch()
+    d.n_reads, d.n_cigar, d.n_seq, d.n_exc = c.n_reads, c.n_cigar, c.n_seq, c.n_exc
+    keep = []
+    for name, count, width in _BATCH_FIELDS:
+        nb = _field_bytes(c, count, width)
+        t = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+        if nb:
+            host = np.ctypeslib.as_array(C.cast(getattr(c, name), C.POINTER(C.c_uint8)), shape=(nb,))
+            t[:nb].copy_(torch.from_numpy(host))
+        keep.append(t)
+        setattr(d, name, t.data_ptr())
+    d.mem = capi.PB_MEM_DEVICE
+    return d, keep
+
+
+def pin_batch(torch, c):
+    """cudaHostRegister every array of a host batch so that H2D copies are true async DMA."""
+    rt = torch.cuda.cudart()
+    n = 0
+    for name, count, width in _BATCH_FIELDS:
+        nb = _field_bytes(c, count, width)
+        if nb:
+            rt.cudaHostRegister(getattr(c, name), nb, 0)
+            n += nb
+    return n
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the C restatement of the reference path on host cores
+# ---------------------------------------------------------------------------------------------
+def oracle_lib():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+    from pilon_b200 import _capi as capi
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libpilon_oracle.so"))
+    lib.po_region_new.restype = C.c_void_p
+    lib.po_region_new.argtypes = [C.POINTER(capi.pb_config), C.c_void_p, C.c_int64, C.c_int32, C.c_int32]
+    lib.po_region_add_batch.argtypes = [C.c_void_p, C.POINTER(capi.pb_batch), C.c_int, C.c_int, C.c_void_p]
+    lib.po_region_finish.argtypes = [C.c_void_p, C.POINTER(capi.pb_region_result)]
+    lib.po_region_free.argtypes = [C.c_void_p]
+    return lib
+
+
+def oracle_region(lib, reg, planes=FIX_PLANES):
+    from pilon_b200.engine import EngineConfig
+    from pilon_b200.packing import ResultBuffers
+    cfg = EngineConfig().to_c()
+    h = lib.po_region_new(C.byref(cfg), reg.contig.ctypes.data, len(reg.contig), reg.start, reg.stop)
+    for b in reg.batches:
+        assert lib.po_region_add_batch(h, C.byref(b.c), int(b.frag), 0, None) == 0
+    res = ResultBuffers(reg.size, planes)
+    assert lib.po_region_finish(h, C.byref(res.c)) == 0
+    lib.po_region_free(h)
+    return res
+
+
+def time_oracle(regions, threads):
+    lib = oracle_lib()
+    t0 = time.perf_counter()
+    if threads <= 1:
+        for r in regions:
+            oracle_region(lib, r)
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(lambda r: oracle_region(lib, r), regions))
+    return time.perf_counter() - t0
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncpu = os.cpu_count() or 1
+    wl, regions = build_workload(args.workload, args.scale, 0, ncpu)
+    # bounded sample: the regions of at most 3 Mb (largest first), one per thread
+    sample = sorted([r for r in regions if r.size <= 3_000_000] or regions[:1], key=lambda r: -r.size)
+    threads = min(ncpu, len(sample))
+    for _ in range(args.warmup):
+        time_oracle(sample[:threads], threads)
+    ts = [time_oracle(sample, threads) for _ in range(args.steps)]
+    bases = sum(r.aligned for r in sample)
+    t = sum(ts) / len(ts)
+    val = bases / t
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+           "config": {"workload": "%s: %s" % (wl.name, wl.description), "scale": args.scale,
+                      "sample": "%d regions <= 3 Mb, %d aligned bases per step" % (len(sample), bases)},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                            "sample": "%d regions of %s (<= 3 Mb each), %d aligned bases, region-parallel over %d threads; "
+                                      "the reference itself is single-threaded (Pilon.scala:219-222)" % (
+                                          len(sample), wl.name, bases, threads)},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from pilon_b200 import build as pbuild
+    pbuild.build()
+    from pilon_b200.engine import Engine
+    from pilon_b200.packing import ResultBuffers
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ncpu = os.cpu_count() or 1
+    wl, regions = build_workload(args.workload, args.scale, rank, max(1, ncpu // max(world, 1)))
+    total_aligned = sum(r.aligned for r in regions)
+    total_loci = sum(r.size for r in regions)
+
+    # ---- device-resident arm -------------------------------------------------------------
+    engines, keep = [], []
+    for r in regions:
+        e = Engine(local)
+        e.region_begin(r.contig, r.start, r.stop)
+        for b in r.batches:
+            d, k = device_batch(torch, b.c, dev)
+            keep.append(k)
+            e.add_batch(d, b.frag)
+        engines.append(e)
+    torch.cuda.synchronize()
+
+    def step():
+        tot = pil = 0.0
+        launches = 0
+        for e in engines:
+            a, p, n = e.compute_timed(1)
+            tot += a; pil += p; launches += n
+        return tot, pil, launches
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    wall0 = time.perf_counter()
+    dev_ms = pil_ms = 0.0
+    launches = 0
+    for _ in range(args.steps):
+        a, p, n = step()
+        dev_ms += a; pil_ms += p; launches += n
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - wall0)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end arm: host buffers -> C ABI -> host results -------------------------------
+    for e in engines:
+        e.close()
+    engines, keep = [], []
+    torch.cuda.empty_cache()
+    h2d = sum(pin_batch(torch, b.c) for r in regions for b in r.batches) + sum(r.size + 1 for r in regions)
+    planes = FIX_PLANES if args.planes == "fix" else None
+    n_workers = 3
+    max_size = max(r.size for r in regions)
+    workers = [(Engine(local), ResultBuffers(max_size, planes, indels_cap=1 << 20, indel_bytes_cap=1 << 23, pinned=True))
+               for _ in range(n_workers)]
+    from pilon_b200 import _capi as capi
+    per_locus = sum(np.dtype(dt).itemsize * per for name, dt, per in capi.RESULT_PLANES if planes is None or name in planes)
+    d2h = per_locus * total_loci
+
+    def e2e_region(slot, r):
+        eng, res = workers[slot]
+        res.c.size = r.size
+        eng.region_begin(r.contig, r.start, r.stop)
+        for b in r.batches:
+            eng.add_batch(b, b.frag)
+        eng.finish(res)
+        return int(res.c.aligned_bases)
+
+    def e2e_step():
+        order = sorted(range(len(regions)), key=lambda i: -regions[i].aligned)
+        lock = threading.Lock()
+        done = [0]
+
+        def work(slot):
+            while True:
+                with lock:
+                    if not order:
+                        return
+                    i = order.pop(0)
+                done[0] += e2e_region(slot, regions[i])
+        ts = [threading.Thread(target=work, args=(s,)) for s in range(n_workers)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        return done[0]
+
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    got = 0
+    for _ in range(e2e_steps):
+        got += e2e_step()
+    ev1.record()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    assert got == total_aligned * e2e_steps, (got, total_aligned)
+    for eng, _ in workers:
+        eng.close()
+
+    # ---- aggregate over ranks -----------------------------------------------------------------
+    vals = torch.tensor([dev_ms / args.steps, pil_ms / args.steps, wall_ms / args.steps, e2e_s], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(total_aligned), float(launches), float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    step_ms, pileup_ms, wall_step_ms, e2e_sec = [float(x) for x in vals.tolist()]
+    job_aligned, job_launches, job_h2d, job_d2h = [float(x) for x in sums.tolist()]
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        alg = sum(r.alg_bytes for r in regions)                 # this rank's launches
+        achieved = alg / (pileup_ms * 1e-3) / 1e9               # GB/s over the pileup kernel's launches of one step
+        depth = total_aligned / total_loci
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            sample = sorted(regions, key=lambda r: abs(r.size - 2_000_000))[:3]
+            t = time_oracle(sample, 1)
+            sb = sum(r.aligned for r in sample)
+            cpu = {"value": sb / t, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": "C restatement of the reference path (oracle/pilon_oracle.c), 1 thread like the reference, "
+                             "%d regions of %s (%d loci, %d aligned bases), %.1f s" % (
+                                 len(sample), wl.name, sum(r.size for r in sample), sb, t)}
+        out = {"metric": METRIC, "value": job_aligned / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+               "config": {"workload": "%s: %s" % (wl.name, wl.description), "scale": args.scale,
+                          "regions_per_gpu": len(regions), "loci_per_gpu": total_loci, "reads_per_gpu": sum(r.n_reads for r in regions),
+                          "aligned_bases_per_gpu": total_aligned, "mean_depth": depth, "l2": "inputs_exceed_l2 (%.1f GB per step)" % (h2d / 1e9),
+                          "timing": "sum of per-region CUDA-event intervals on the engine streams; wall_ms_per_step is the host clock around the same steps",
+                          "e2e_planes": args.planes},
+               "wall_ms_per_step": wall_step_ms,
+               "e2e": {"value": job_aligned / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": job_h2d, "d2h_bytes_per_step": job_d2h,
+                       "ms_per_step": 1e3 * e2e_sec, "streams_per_gpu": n_workers},
+               "gpu_launches": int(job_launches),
+               "roofline": {"bound": "hbm", "kernel": "k_pileup", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                            "algorithmic_bytes_per_base": alg / total_aligned,
+                            "pileup_ms_per_step": pileup_ms, "pileup_share_of_step": pileup_ms / step_ms},
+               "cpu_baseline": cpu, "clocks": clocks}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrinks the genome (not the depth); 1.0 = the BASELINE config")
+    ap.add_argument("--planes", default="fix", choices=["fix", "vcf"], help="per-locus results copied back in the e2e arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

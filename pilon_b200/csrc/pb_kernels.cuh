@@ -477,10 +477,9 @@ __global__ void __launch_bounds__(PILEUP_WARPS * 32) k_pileup(RegionDev R, const
         const uint32_t nbefore = c0 + c1 + c2 + c3;
         const int32_t fwd = B.reach[0], back = B.reach[1];
         // candidate reads: (pos - start) in (w0 - fwd, w0 + 32 + back)
-        int64_t x = (int64_t)w0 - fwd + 1; if (x < 0) x = 0;
-        const int64_t klo = x >> 5;
+        const int64_t x = (int64_t)w0 - fwd + 1;
         int64_t khi = (((int64_t)w0 + 32 + back) + 31) >> 5; if (khi > R.n_win) khi = R.n_win;
-        const uint32_t rlo = B.win_first[klo];
+        const uint32_t rlo = x <= 0 ? 0u : B.win_first[x >> 5];    // x <= 0: reads left of the region count too
         const uint32_t rhi = (((int64_t)w0 + 32 + back) > ((int64_t)R.n_win << 5)) ? (uint32_t)B.n_reads : B.win_first[khi];
         const uint32_t slo = B.cigar_off[rlo], shi = B.cigar_off[rhi];
         const uint8_t* __restrict__ quals = B.quals;

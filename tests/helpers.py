@@ -302,7 +302,8 @@ def random_case(seed: int, contig_len: int = 400, n_reads: int = 120, start: Opt
     return contig, start, stop, reads
 
 
-def planted_indel_cluster(rng: random.Random, contig: bytes, start: int, stop: int) -> List[po.Read]:
+def planted_indel_cluster(rng: random.Random, contig: bytes, start: int, stop: int,
+                          depth_range=(4, 14), fracs=(1.0, 0.9, 0.5, 0.3)) -> List[po.Read]:
     out: List[po.Read] = []
     n = len(contig)
     for _ in range(rng.randint(1, 3)):
@@ -313,8 +314,8 @@ def planted_indel_cluster(rng: random.Random, contig: bytes, start: int, stop: i
         kind = rng.choice("ID")
         k = rng.randint(1, 5)
         insb = bytes(rng.choice(b"ACGT") for _ in range(k))
-        depth = rng.randint(4, 14)
-        frac = rng.choice([1.0, 0.9, 0.5, 0.3])
+        depth = rng.randint(*depth_range)
+        frac = rng.choice(fracs)
         for d in range(depth):
             pos = site - rng.randint(12, L - 14)
             left = site - pos
@@ -343,7 +344,8 @@ def planted_indel_cluster(rng: random.Random, contig: bytes, start: int, stop: i
     return out
 
 
-def planted_snp_cluster(rng: random.Random, contig: bytes, start: int, stop: int) -> List[po.Read]:
+def planted_snp_cluster(rng: random.Random, contig: bytes, start: int, stop: int,
+                        depth_range=(8, 16)) -> List[po.Read]:
     """Depth at one site with two alleles: hom-alt (SNP), ref/alt het, or alt1/alt2 het (AMB)."""
     out: List[po.Read] = []
     n = len(contig)
@@ -355,7 +357,7 @@ def planted_snp_cluster(rng: random.Random, contig: bytes, start: int, stop: int
     alts = [b for b in b"ACGT" if b != ref[0]]
     rng.shuffle(alts)
     mode = rng.choice(["hom", "het_ref", "het_alt"])
-    for d in range(rng.randint(8, 16)):
+    for d in range(rng.randint(*depth_range)):
         pos = site - rng.randint(11, L - 12)
         if pos < 1 or pos + L - 1 > n:
             continue
@@ -379,3 +381,30 @@ def split_batches(reads: Sequence[po.Read], rng: random.Random):
     for r in reads:
         groups[rng.randrange(k)].append(r)
     return [(g, rng.random() < 0.7) for g in groups]
+
+
+def clean_case(seed: int, n: int = 30000, start: int = 2001, stop: int = 26000, depth: int = 12, n_sites: int = 40):
+    """Paired, mostly-perfect reads over a long region (halo reads on both sides) plus planted
+    variant clusters deep enough to be called: exercises SNP / AMB / INS / DEL / deleted-spill."""
+    rng = random.Random(seed)
+    contig = random_contig(rng, n, lower_frac=0.005, n_runs=3)
+    L = 100
+    reads: List[po.Read] = []
+    nfrag = depth * (stop - start + 1200) // (2 * L)
+    for _ in range(nfrag):
+        ins = max(2 * L // 2 + 20, int(rng.gauss(300, 30)))
+        p1 = rng.randint(max(1, start - 600), min(n - ins, stop + 300))
+        p2 = p1 + ins - L
+        for pos, tl, rev in ((p1, ins, False), (p2, -ins, True)):
+            b = bytearray(contig[pos - 1:pos - 1 + L].upper())
+            for i in range(L):
+                if rng.random() < 0.003:
+                    b[i] = rng.choice(b"ACGTN")
+            reads.append(po.Read(pos=pos, cigar=[("M", L)], bases=bytes(b), quals=bytes(rng.randint(15, 40) for _ in range(L)),
+                                 mapq=rng.choice([60, 60, 60, 60, 30, 0]), paired=True, proper=rng.random() < 0.98,
+                                 tlen=tl, reverse=rev))
+    for _ in range(n_sites):
+        reads += planted_indel_cluster(rng, contig, start, stop, depth_range=(2 * depth, 3 * depth), fracs=(1.0, 0.95, 0.5))
+        reads += planted_snp_cluster(rng, contig, start, stop, depth_range=(2 * depth, 3 * depth))
+    reads.sort(key=lambda r: r.pos)
+    return contig, start, stop, reads

@@ -140,8 +140,20 @@ def test_medium_synthetic_region(engine, seed, depth):
     reads.sort(key=lambda r: r.pos)
     half = [r for i, r in enumerate(reads) if i % 3 != 0], [r for i, r in enumerate(reads) if i % 3 == 0]
     res, _ = run_both(engine, contig, start, stop, [(half[0], True), (half[1], False)])
+    assert (res["flags"] & capi.PB_FL_CONFIRMED).any()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_clean_region_with_planted_variants_calls_everything(engine, seed):
+    contig, start, stop, reads = H.clean_case(seed)
+    res, _ = run_both(engine, contig, start, stop, [(reads, True)])
     fl = res["flags"]
-    assert (fl & capi.PB_FL_CONFIRMED).any() and (fl & capi.PB_FL_CHANGED).any() and (fl & capi.PB_FL_DELETED).any()
+    kind = (fl >> capi.PB_FL_KIND_SHIFT) & 3
+    changed = (fl & capi.PB_FL_CHANGED) != 0
+    assert (fl & capi.PB_FL_CONFIRMED).sum() > 0.8 * len(fl)
+    for k in (capi.PB_KIND_SNP, capi.PB_KIND_INS, capi.PB_KIND_DEL):
+        assert (changed & (kind == k)).any(), "no call of kind %d" % k
+    assert (fl & capi.PB_FL_DELETED).any() and (fl & capi.PB_FL_AMBIGUOUS).any()
 
 
 def test_high_depth_single_locus_contention(engine):
