@@ -342,7 +342,9 @@ def run_gpu_arm(args):
                     if not order:
                         return
                     i = order.pop(0)
-                done[0] += e2e_region(slot, regions[i])
+                v = e2e_region(slot, regions[i])
+                with lock:
+                    done[0] += v
         ts = [threading.Thread(target=work, args=(s,)) for s in range(n_workers)]
         [t.start() for t in ts]
         [t.join() for t in ts]
