@@ -66,14 +66,16 @@ typedef struct pb_config {
 /* Base / quality packing.  Each read owns a run of `read_len` bases starting at base index
  * seq_off[r] (a multiple of 4) inside the batch:
  *   bases2[i >> 2] >> (2 * (i & 3)) & 3   = 0,1,2,3 for A,C,G,T
- *   quals[i]                               = phred quality, 0..127; bit 7 set marks a base the
+ *   quals[i]                               = phred quality, 0..127, or exactly 0x80 for a base the
  *                                            per-locus counters can never count: a read byte that
  *                                            is not exactly 'A','C','G','T' (PileUp.scala:46-52) or
  *                                            a quality byte >= 128 (a negative JVM Byte).
- * Every base with bit 7 set has one entry in the sparse exception table (sorted by base index)
- * holding its original ASCII letter and raw quality byte, so the rare paths that need them
- * (indel strings, indel anchor qualities, left-shift comparisons) stay bit-exact.
- * For reads without PB_F_HAS_QUALS the quality bytes carry only bit 7. */
+ * Every 0x80 base has one entry in the sparse exception table (sorted by base index) holding its
+ * original ASCII letter and raw quality byte, so the rare paths that need them (indel strings,
+ * indel anchor qualities, left-shift comparisons) stay bit-exact.
+ * `quals` and `bases2` must be 16-byte aligned and readable for 16 bytes past their last element
+ * (the kernels fetch them in aligned 16-byte blocks); the engine's own H2D staging guarantees it.
+ * For reads without PB_F_HAS_QUALS the quality bytes are 0x00 / 0x80 only. */
 #define PB_MEM_HOST    0   /* pointers are host memory (pinned preferred); engine copies H2D   */
 #define PB_MEM_DEVICE  1   /* pointers are device memory on the engine's GPU; used in place    */
 

@@ -6,13 +6,14 @@
 // + GenomeRegion.postProcess pass 1, GenomeRegion.scala:214-272) and read everything back.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include <cub/device/device_merge_sort.cuh>
 
-#include "pb_kernels.cuh"
+#include "pb_pileup2.cuh"
 
 using namespace pb;
 
@@ -70,6 +71,7 @@ struct pb_engine {
     int64_t launches = 0;
     float last_pileup_ms = 0.f;
     bool dirty = false;              // rare planes may be non-zero after a failed run
+    int pileup_version = 2;          // PB_PILEUP=1 selects the first-generation kernel (A/B runs)
 };
 
 static int free_batches(pb_engine* e) {
@@ -96,6 +98,9 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
     e->cfg.min_qual = c->min_qual; e->cfg.min_mq = c->min_mq; e->cfg.flank = c->flank;
     e->cfg.default_qual = c->default_qual; e->cfg.min_min_depth = c->min_min_depth;
     e->cfg.old_indel = c->old_indel; e->cfg.fix_amb = c->fix_amb; e->cfg.min_depth = c->min_depth;
+    if (const char* v = getenv("PB_PILEUP")) e->pileup_version = atoi(v) == 1 ? 1 : 2;
+    CK(cudaFuncSetAttribute(k_pileup2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * P2_WARPS)));
+    CK(cudaFuncSetAttribute(k_pileup2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * P2_WARPS)));
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
     CK(cudaEventCreate(&e->evp0)); CK(cudaEventCreate(&e->evp1));
@@ -190,7 +195,7 @@ template <class T>
 static int stage(pb_engine* e, HostBatch& hb, const T* src, size_t n, int mem, const T** dst) {
     if (mem == PB_MEM_DEVICE) { *dst = src; return PB_OK; }
     void* p = nullptr;
-    CK(cudaMallocAsync(&p, n * sizeof(T) + 16, e->stream));
+    CK(cudaMallocAsync(&p, n * sizeof(T) + 64, e->stream));   // kernels fetch aligned 16-byte blocks
     hb.owned.push_back(p);
     if (n) CK(cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
     *dst = (const T*)p;
@@ -284,9 +289,16 @@ static int compute(pb_engine* e, bool time_pileup) {
         k_groups<<<(n_ev + 255) / 256, 256, 0, s>>>(R, dB, R.ev_key, e->perm.as<uint32_t>(), n_ev); e->launches++;
     }
     if (time_pileup) CK(cudaEventRecord(e->evp0, s));
-    const unsigned grid = (unsigned)((R.n_win + PILEUP_WARPS - 1) / PILEUP_WARPS);
-    if (e->cfg.min_qual > 0) k_pileup<true><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
-    else k_pileup<false><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
+    if (e->pileup_version == 1) {
+        const unsigned grid = (unsigned)((R.n_win + PILEUP_WARPS - 1) / PILEUP_WARPS);
+        if (e->cfg.min_qual > 0) k_pileup<true><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
+        else k_pileup<false><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
+    } else {
+        const unsigned grid = (unsigned)((R.n_win + P2_WARPS - 1) / P2_WARPS);
+        const size_t smem = sizeof(WarpSmem) * P2_WARPS;
+        if (e->cfg.min_qual > 0) k_pileup2<true><<<grid, P2_WARPS * 32, smem, s>>>(R, dB, nb);
+        else k_pileup2<false><<<grid, P2_WARPS * 32, smem, s>>>(R, dB, nb);
+    }
     e->launches++;
     if (time_pileup) CK(cudaEventRecord(e->evp1, s));
     // deletion spill: candidates are bounded by the number of deletion groups
@@ -435,7 +447,7 @@ extern "C" int pb_packer_add(pb_packer* p, int32_t pos, int32_t tlen, int32_t ma
         const uint8_t q = hasq ? qual[j] : 0;
         const size_t i = off + (size_t)j;
         if (code < 0 || q >= 128) {
-            p->quals[i] = (uint8_t)((q & 0x7F) | 0x80);
+            p->quals[i] = 0x80;
             p->exc_idx.push_back((uint32_t)i); p->exc_base.push_back(c); p->exc_qual.push_back(q);
         } else p->quals[i] = q;
         if (code > 0) p->bases2[i >> 2] |= (uint8_t)(code << (2 * (i & 3)));

@@ -231,7 +231,7 @@ int gen_read(const ps_params& P, const Window& W, const ReadKey& rk, uint8_t* q_
         if (isN) { b = 'N'; q = 2; }
         const int code = b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : b == 'T' ? 3 : -1;
         if (code < 0) {
-            q_out[i] = (uint8_t)(q | 0x80);
+            q_out[i] = 0x80;
             exc_idx.push_back(seq_base + (uint32_t)i); exc_base.push_back(b); exc_qual.push_back(q);
         } else { q_out[i] = q; b2_out[i >> 2] |= (uint8_t)(code << (2 * (i & 3))); }
     }

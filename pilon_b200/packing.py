@@ -130,7 +130,7 @@ def pack_soa(pos, tlen, mapq, flags, read_len, cigar_off, cigar, ascii_off, seq,
     code = _BASE_CODE[letters]
     exc = (code == 255) | (q >= 128)
     quals = np.zeros(n_seq, np.uint8)
-    quals[dst] = np.where(exc, (q & 0x7F) | 0x80, q)
+    quals[dst] = np.where(exc, 0x80, q)
     code2 = np.where(code == 255, 0, code).astype(np.uint8)
     codes_full = np.zeros(n_seq, np.uint8)
     codes_full[dst] = code2
