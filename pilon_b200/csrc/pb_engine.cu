@@ -13,7 +13,7 @@
 
 #include <cub/device/device_merge_sort.cuh>
 
-#include "pb_pileup2.cuh"
+#include "pb_pileup3.cuh"
 
 using namespace pb;
 
@@ -71,7 +71,7 @@ struct pb_engine {
     int64_t launches = 0;
     float last_pileup_ms = 0.f;
     bool dirty = false;              // rare planes may be non-zero after a failed run
-    int pileup_version = 2;          // PB_PILEUP=1 selects the first-generation kernel (A/B runs)
+    int pileup_version = 3;          // PB_PILEUP=1|2 selects an earlier kernel generation (A/B runs)
 };
 
 static int free_batches(pb_engine* e) {
@@ -98,7 +98,9 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
     e->cfg.min_qual = c->min_qual; e->cfg.min_mq = c->min_mq; e->cfg.flank = c->flank;
     e->cfg.default_qual = c->default_qual; e->cfg.min_min_depth = c->min_min_depth;
     e->cfg.old_indel = c->old_indel; e->cfg.fix_amb = c->fix_amb; e->cfg.min_depth = c->min_depth;
-    if (const char* v = getenv("PB_PILEUP")) e->pileup_version = atoi(v) == 1 ? 1 : 2;
+    if (const char* v = getenv("PB_PILEUP")) { const int pv = atoi(v); if (pv >= 1 && pv <= 3) e->pileup_version = pv; }
+    CK(cudaFuncSetAttribute(k_pileup3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem3)));
+    CK(cudaFuncSetAttribute(k_pileup3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem3)));
     CK(cudaFuncSetAttribute(k_pileup2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * P2_WARPS)));
     CK(cudaFuncSetAttribute(k_pileup2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * P2_WARPS)));
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -278,6 +280,7 @@ static int compute(pb_engine* e, bool time_pileup) {
     e->launches += 3;
     CK(cudaEventSynchronize(e->ev_sc));
     if (e->h_sc->error & 1) return fail(PB_ERR_UNSORTED, "a batch is not sorted by pos");
+    if (e->h_sc->error & 8) return fail(PB_ERR_CUDA, "pipeline barrier timed out (internal protocol error)");
     if (e->h_sc->error) return fail(PB_ERR_CUDA, "internal capacity error in k_prep");
     const uint32_t n_ev = e->h_sc->n_events;
     if (n_ev) {
@@ -293,6 +296,10 @@ static int compute(pb_engine* e, bool time_pileup) {
         const unsigned grid = (unsigned)((R.n_win + PILEUP_WARPS - 1) / PILEUP_WARPS);
         if (e->cfg.min_qual > 0) k_pileup<true><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
         else k_pileup<false><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
+    } else if (e->pileup_version == 3) {
+        const unsigned grid = (unsigned)((R.n_win + P3_CW - 1) / P3_CW);
+        if (e->cfg.min_qual > 0) k_pileup3<true><<<grid, (P3_CW + 1) * 32, sizeof(Smem3), s>>>(R, dB, nb);
+        else k_pileup3<false><<<grid, (P3_CW + 1) * 32, sizeof(Smem3), s>>>(R, dB, nb);
     } else {
         const unsigned grid = (unsigned)((R.n_win + P2_WARPS - 1) / P2_WARPS);
         const size_t smem = sizeof(WarpSmem) * P2_WARPS;
