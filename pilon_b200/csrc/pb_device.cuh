@@ -47,12 +47,18 @@ struct DevBatch {
     const uint32_t* exc_idx;
     const uint8_t *exc_base, *exc_qual;
     Seg* seg;               // [n_cigar]
-    uint32_t* win_first;    // [n_win + 1]  #reads with (pos - start) < 32*k
+    uint32_t* win_first;    // [n_win + 1]  cigar_off[#reads with (pos - start) < 32*k]: first candidate segment slot
     int32_t* insert_out;    // [n_reads]    addRead return values (PileUpRegion.scala:219)
     int32_t* reach;         // [2] device scalars: max forward reach, max backward reach (loci)
     int32_t frag;           // counts toward fragCoverage (GenomeRegion.scala:291,296)
+    int32_t fwd, back;      // host copy of reach[0..1], filled in after k_prep (saves a dependent load per tile)
     int32_t pad;
 };
+
+// k_prep spreads its per-warp partial sums over SC_SLOTS slots (same-address L2 atomics serialise);
+// k_scalars folds them into the Scalars block.
+static constexpr int SC_SLOTS = 64;
+struct ScalarSlot { unsigned long long base_count, aligned_bases; int read_count, unknown_ops, dropped_oob, pad; };
 
 struct Scalars {
     unsigned long long base_count;      // PileUpRegion.baseCount
@@ -79,19 +85,20 @@ struct RegionDev {
     int32_t ref_locus0;         // locus of ref[0]  (= max(start - 1, 1))
     const uint8_t* ref;         // raw contig bytes for loci [ref_locus0, stop]
     Cfg cfg;
+    int32_t read_count, min_depth;   // host copies of the region scalars, valid for kernels launched after k_scalars' read-back
     Scalars* sc;
     // sparse ("rare") per-locus planes, zero between regions; written by k_prep with atomics,
     // consumed and re-zeroed by the pileup epilogue wherever rare_bits says so
     int32_t *r_ins, *r_insq, *r_del, *r_delq, *r_q, *r_mq, *r_clips, *r_delfrag;
     uint32_t *r_gins, *r_gdel;  // group index + 1 of the locus' insertion / deletion evidence
     uint32_t* rare_bits;        // [n_win] bit l set = locus 32*w + l has any rare contribution
-    int32_t* cand_len;          // deletion length of a pass-1 DEL candidate (valid where flagged)
     int2* pc_diff;              // physCov / insertSize difference array (PileUpRegion.scala:62-88)
     // events
     EventKey* ev_key; Event* ev; uint32_t ev_cap;
     Group* groups; uint32_t groups_cap;
     uint8_t* str_pool; uint64_t str_cap;
-    int2* cand;  uint32_t cand_cap;     // unordered pass-1 DEL candidates: (locus index, deletions)
+    int4* cand;  uint32_t cand_cap;     // unordered pass-1 DEL candidates: (locus index, deletions, length, -)
+    ScalarSlot* slots;                  // [SC_SLOTS] k_prep partial sums
     // outputs (final state)
     int32_t* o_cnt;   // [size*4]
     int64_t* o_qs;    // [size*4]

@@ -29,6 +29,11 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 namespace {
 
+// device/pinned scalar block: Scalars followed by the per-batch reach pairs (k_prep's atomicMax targets)
+constexpr size_t SC_BYTES = 8192;
+constexpr size_t SC_REACH_OFF = sizeof(Scalars) + sizeof(ScalarSlot) * SC_SLOTS;
+constexpr size_t MAX_BATCHES = (SC_BYTES - SC_REACH_OFF) / 8;
+
 // grow-only device buffer, zero-filled on growth when asked (the "rare" planes rely on it)
 struct DBuf {
     void* p = nullptr; size_t cap = 0;
@@ -63,7 +68,7 @@ struct pb_engine {
     std::vector<HostBatch> batches;
     DBuf d_batches;                  // DevBatch[] image
     // per-locus buffers
-    DBuf ref, rare[10], rare_bits, cand_len, pc_diff, block_sums, scalars;
+    DBuf ref, rare[10], rare_bits, pc_diff, block_sums, scalars;
     DBuf o_cnt, o_qs, o_i32[12], o_wq, o_wmq, o_flags, o_call;
     // event buffers
     DBuf ev_key, ev, perm, groups, cand, spill_scratch, str_pool, cub_tmp;
@@ -107,7 +112,7 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
     CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
     CK(cudaEventCreate(&e->evp0)); CK(cudaEventCreate(&e->evp1));
     CK(cudaEventCreateWithFlags(&e->ev_sc, cudaEventDisableTiming));
-    CK(cudaMallocHost(&e->h_sc, sizeof(Scalars)));
+    CK(cudaMallocHost(&e->h_sc, SC_BYTES));
     cudaMemPool_t pool;
     CK(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;
@@ -122,7 +127,7 @@ extern "C" int pb_destroy(pb_engine* e) {
     cudaStreamSynchronize(e->stream);
     free_batches(e);
     cudaStreamSynchronize(e->stream);
-    DBuf* all[] = {&e->d_batches, &e->ref, &e->rare_bits, &e->cand_len, &e->pc_diff, &e->block_sums, &e->scalars,
+    DBuf* all[] = {&e->d_batches, &e->ref, &e->rare_bits, &e->pc_diff, &e->block_sums, &e->scalars,
                    &e->o_cnt, &e->o_qs, &e->o_wq, &e->o_wmq, &e->o_flags, &e->o_call, &e->ev_key, &e->ev, &e->perm,
                    &e->groups, &e->cand, &e->spill_scratch, &e->str_pool, &e->cub_tmp};
     for (DBuf* b : all) b->release();
@@ -165,9 +170,8 @@ extern "C" int pb_region_begin(pb_engine* e, const uint8_t* contig, int64_t cont
     for (auto& b : e->rare) CK(b.ensure(n4, true, s));
     CK(e->rare_bits.ensure((size_t)R.n_win * 4, true, s));
     CK(e->pc_diff.ensure((size_t)S * 8, true, s));
-    CK(e->cand_len.ensure(n4, false, s));
-    CK(e->scalars.ensure(sizeof(Scalars), false, s));
-    CK(cudaMemsetAsync(e->scalars.p, 0, sizeof(Scalars), s));
+    CK(e->scalars.ensure(SC_BYTES, false, s));
+    CK(cudaMemsetAsync(e->scalars.p, 0, SC_BYTES, s));
     CK(e->o_cnt.ensure((size_t)S * 16, false, s)); CK(e->o_qs.ensure((size_t)S * 32, false, s));
     for (auto& b : e->o_i32) CK(b.ensure(n4, false, s));
     CK(e->o_wq.ensure((size_t)S, false, s)); CK(e->o_wmq.ensure((size_t)S, false, s));
@@ -175,11 +179,12 @@ extern "C" int pb_region_begin(pb_engine* e, const uint8_t* contig, int64_t cont
     const int nblocks = (int)((S + SCAN_TILE - 1) / SCAN_TILE);
     CK(e->block_sums.ensure((size_t)nblocks * 8, false, s));
     R.sc = e->scalars.as<Scalars>();
+    R.slots = reinterpret_cast<ScalarSlot*>(static_cast<uint8_t*>(e->scalars.p) + sizeof(Scalars));
     R.r_ins = e->rare[0].as<int32_t>(); R.r_insq = e->rare[1].as<int32_t>(); R.r_del = e->rare[2].as<int32_t>();
     R.r_delq = e->rare[3].as<int32_t>(); R.r_q = e->rare[4].as<int32_t>(); R.r_mq = e->rare[5].as<int32_t>();
     R.r_clips = e->rare[6].as<int32_t>(); R.r_delfrag = e->rare[7].as<int32_t>();
     R.r_gins = e->rare[8].as<uint32_t>(); R.r_gdel = e->rare[9].as<uint32_t>();
-    R.rare_bits = e->rare_bits.as<uint32_t>(); R.cand_len = e->cand_len.as<int32_t>();
+    R.rare_bits = e->rare_bits.as<uint32_t>();
     R.pc_diff = e->pc_diff.as<int2>();
     R.o_cnt = e->o_cnt.as<int32_t>(); R.o_qs = e->o_qs.as<int64_t>();
     int32_t** o32[] = {&R.o_mq, &R.o_q, &R.o_pc, &R.o_is, &R.o_bp, &R.o_del, &R.o_delq, &R.o_ins, &R.o_insq,
@@ -227,7 +232,8 @@ extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, in
     CK(cudaMallocAsync(&p, ((size_t)b->n_cigar + 1) * sizeof(Seg), e->stream)); hb.owned.push_back(p); d.seg = (Seg*)p;
     CK(cudaMallocAsync(&p, ((size_t)e->R.n_win + 2) * 4, e->stream)); hb.owned.push_back(p); d.win_first = (uint32_t*)p;
     CK(cudaMallocAsync(&p, (n + 1) * 4, e->stream)); hb.owned.push_back(p); d.insert_out = (int32_t*)p;
-    CK(cudaMallocAsync(&p, 16, e->stream)); hb.owned.push_back(p); d.reach = (int32_t*)p;
+    if (e->batches.size() > MAX_BATCHES) return fail(PB_ERR_INVALID, "too many batches in one region");
+    d.reach = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(e->scalars.p) + SC_REACH_OFF) + 2 * (e->batches.size() - 1);
     return PB_OK;
 }
 
@@ -247,10 +253,10 @@ static int compute(pb_engine* e, bool time_pileup) {
     CK(e->ev.ensure((size_t)cap * sizeof(Event) + 16, false, s));
     CK(e->perm.ensure((size_t)cap * 4 + 16, false, s));
     CK(e->groups.ensure((size_t)cap * sizeof(Group) + 16, false, s));
-    CK(e->cand.ensure((size_t)cap * sizeof(int2) + 16, false, s));
+    CK(e->cand.ensure((size_t)cap * sizeof(int4) + 16, false, s));
     R.ev_key = e->ev_key.as<EventKey>(); R.ev = e->ev.as<Event>(); R.ev_cap = cap;
     R.groups = e->groups.as<Group>(); R.groups_cap = cap;
-    R.cand = e->cand.as<int2>(); R.cand_cap = cap;
+    R.cand = e->cand.as<int4>(); R.cand_cap = cap;
     R.str_pool = e->str_pool.as<uint8_t>(); R.str_cap = e->str_pool.cap;
     std::vector<DevBatch> img(nb);
     for (int i = 0; i < nb; i++) img[i] = e->batches[i].d;
@@ -258,11 +264,10 @@ static int compute(pb_engine* e, bool time_pileup) {
     if (nb) CK(cudaMemcpyAsync(e->d_batches.p, img.data(), sizeof(DevBatch) * nb, cudaMemcpyHostToDevice, s));
     const DevBatch* dB = e->d_batches.as<DevBatch>();
     e->dirty = true;
-    CK(cudaMemsetAsync(e->scalars.p, 0, sizeof(Scalars), s));
+    CK(cudaMemsetAsync(e->scalars.p, 0, SC_BYTES, s));
 
     for (int i = 0; i < nb; i++) {
         const DevBatch& d = e->batches[i].d;
-        CK(cudaMemsetAsync(d.reach, 0, 8, s));
         CK(cudaMemsetAsync(d.win_first, 0, ((size_t)R.n_win + 2) * 4, s));
         if (d.n_reads == 0) continue;
         k_prep<<<(unsigned)((d.n_reads + 127) / 128), 128, 0, s>>>(R, d, (uint32_t)i);
@@ -270,7 +275,7 @@ static int compute(pb_engine* e, bool time_pileup) {
         e->launches += 2;
     }
     k_scalars<<<1, 1, 0, s>>>(R); e->launches++;
-    CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, SC_REACH_OFF + 8 * (size_t)nb, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(e->ev_sc, s));
     // physCov scan does not depend on the events: keeps the GPU busy while the host waits for n_events
     const int nblocks = (int)((R.size + SCAN_TILE - 1) / SCAN_TILE);
@@ -283,6 +288,12 @@ static int compute(pb_engine* e, bool time_pileup) {
     if (e->h_sc->error & 8) return fail(PB_ERR_CUDA, "pipeline barrier timed out (internal protocol error)");
     if (e->h_sc->error) return fail(PB_ERR_CUDA, "internal capacity error in k_prep");
     const uint32_t n_ev = e->h_sc->n_events;
+    R.read_count = e->h_sc->read_count; R.min_depth = e->h_sc->min_depth;
+    {   // hand the per-batch reach to the pileup kernel by value
+        const int32_t* hr = reinterpret_cast<const int32_t*>(reinterpret_cast<const uint8_t*>(e->h_sc) + SC_REACH_OFF);
+        for (int i = 0; i < nb; i++) { img[i].fwd = hr[2 * i]; img[i].back = hr[2 * i + 1]; }
+        if (nb) CK(cudaMemcpyAsync(e->d_batches.p, img.data(), sizeof(DevBatch) * nb, cudaMemcpyHostToDevice, s));
+    }
     if (n_ev) {
         k_iota<<<(n_ev + 255) / 256, 256, 0, s>>>(e->perm.as<uint32_t>(), n_ev); e->launches++;
         size_t tmp = 0;
@@ -310,8 +321,8 @@ static int compute(pb_engine* e, bool time_pileup) {
     if (time_pileup) CK(cudaEventRecord(e->evp1, s));
     // deletion spill: candidates are bounded by the number of deletion groups
     uint32_t p2 = 1; while (p2 < n_ev) p2 <<= 1;
-    CK(e->spill_scratch.ensure((size_t)p2 * sizeof(int2) + 16, false, s));
-    if (n_ev) { k_spill<<<1, 1024, 4096 * sizeof(int2), s>>>(R, e->spill_scratch.as<int2>(), p2); e->launches++; }
+    CK(e->spill_scratch.ensure((size_t)p2 * sizeof(int4) + 16, false, s));
+    if (n_ev) { k_spill<<<1, 1024, 2048 * sizeof(int4), s>>>(R, e->spill_scratch.as<int4>(), p2); e->launches++; }
     CK(cudaGetLastError());
     return PB_OK;
 }

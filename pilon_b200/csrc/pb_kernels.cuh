@@ -218,18 +218,20 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
         fwd = max(fwd, __shfl_xor_sync(FULL, fwd, o)); back = max(back, __shfl_xor_sync(FULL, back, o));
     }
     if ((threadIdx.x & 31) == 0) {
-        if (bc) atomicAdd(&R.sc->base_count, bc);
-        if (aligned) atomicAdd(&R.sc->aligned_bases, aligned);
-        if (rc) atomicAdd(&R.sc->read_count, rc);
-        if (unk) atomicAdd(&R.sc->unknown_ops, unk);
-        if (drop) atomicAdd(&R.sc->dropped_oob, drop);
-        if (fwd) atomicMax(&B.reach[0], fwd);
-        if (back) atomicMax(&B.reach[1], back);
+        ScalarSlot* sl = &R.slots[(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (SC_SLOTS - 1)];
+        if (bc) atomicAdd(&sl->base_count, bc);
+        if (aligned) atomicAdd(&sl->aligned_bases, aligned);
+        if (rc) atomicAdd(&sl->read_count, rc);
+        if (unk) atomicAdd(&sl->unknown_ops, unk);
+        if (drop) atomicAdd(&sl->dropped_oob, drop);
+        // reach only ever grows: a plain read filters almost every atomicMax away
+        if (fwd > *(volatile int32_t*)&B.reach[0]) atomicMax(&B.reach[0], fwd);
+        if (back > *(volatile int32_t*)&B.reach[1]) atomicMax(&B.reach[1], back);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_index: win_first[k] = #reads of the batch with (pos - start) < 32*k, k = 0..n_win
+// k_index: win_first[k] = segment slot (cigar offset) of the first read with (pos - start) >= 32*k, k = 0..n_win
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int64_t kmin_of(const RegionDev& R, int32_t pos) {
     const int64_t d = (int64_t)pos - R.start;
@@ -243,13 +245,19 @@ __global__ void __launch_bounds__(256) k_index(RegionDev R, DevBatch B) {
     if (r >= B.n_reads) return;
     const int64_t k1 = kmin_of(R, B.pos[r]);
     const int64_t k0 = r == 0 ? 0 : kmin_of(R, B.pos[r - 1]);
-    for (int64_t k = k0; k < k1; k++) B.win_first[k] = (uint32_t)r;
-    if (r == B.n_reads - 1) for (int64_t k = k1; k <= R.n_win; k++) B.win_first[k] = (uint32_t)B.n_reads;
+    const uint32_t so = B.cigar_off[r];
+    for (int64_t k = k0; k < k1; k++) B.win_first[k] = so;
+    if (r == B.n_reads - 1) for (int64_t k = k1; k <= R.n_win; k++) B.win_first[k] = (uint32_t)B.n_cigar;
 }
 
 // region coverage and minDepth (PileUpRegion.scala:36; GenomeRegion.scala:221-224)
 __global__ void k_scalars(RegionDev R) {
     Scalars* sc = R.sc;
+    for (int i = 0; i < SC_SLOTS; i++) {
+        const ScalarSlot& sl = R.slots[i];
+        sc->base_count += sl.base_count; sc->aligned_bases += sl.aligned_bases; sc->read_count += sl.read_count;
+        sc->unknown_ops += sl.unknown_ops; sc->dropped_oob += sl.dropped_oob;
+    }
     const long long cov = roundDivL((long long)sc->base_count, R.size);
     sc->coverage = cov;
     int md;
@@ -479,9 +487,8 @@ __global__ void __launch_bounds__(PILEUP_WARPS * 32) k_pileup(RegionDev R, const
         // candidate reads: (pos - start) in (w0 - fwd, w0 + 32 + back)
         const int64_t x = (int64_t)w0 - fwd + 1;
         int64_t khi = (((int64_t)w0 + 32 + back) + 31) >> 5; if (khi > R.n_win) khi = R.n_win;
-        const uint32_t rlo = x <= 0 ? 0u : B.win_first[x >> 5];    // x <= 0: reads left of the region count too
-        const uint32_t rhi = (((int64_t)w0 + 32 + back) > ((int64_t)R.n_win << 5)) ? (uint32_t)B.n_reads : B.win_first[khi];
-        const uint32_t slo = B.cigar_off[rlo], shi = B.cigar_off[rhi];
+        const uint32_t slo = x <= 0 ? 0u : B.win_first[x >> 5];    // x <= 0: reads left of the region count too
+        const uint32_t shi = (((int64_t)w0 + 32 + back) > ((int64_t)R.n_win << 5)) ? (uint32_t)B.n_cigar : B.win_first[khi];
         const uint8_t* __restrict__ quals = B.quals;
         const uint8_t* __restrict__ bases2 = B.bases2;
         for (uint32_t sb = slo; sb < shi; sb += 32) {
@@ -546,8 +553,8 @@ __global__ void __launch_bounds__(PILEUP_WARPS * 32) k_pileup(RegionDev R, const
         const int64_t depth = n + r_del;
         const int64_t qtot = in.q[0] + in.q[1] + in.q[2] + in.q[3];
         uint32_t fl = 0;
-        if (R.sc->read_count != 0)                                       // GenomeRegion.scala:229-231
-            fl = classify(call, depth, R.sc->min_depth, ref_class(ref_at(R, (int64_t)R.start + loc)), R.cfg.fix_amb);
+        if (R.read_count != 0)                                           // GenomeRegion.scala:229-231
+            fl = classify(call, depth, R.min_depth, ref_class(ref_at(R, (int64_t)R.start + loc)), R.cfg.fix_amb);
         reinterpret_cast<int4*>(R.o_cnt)[loc] = make_int4((int)c0, (int)c1, (int)c2, (int)c3);
         reinterpret_cast<longlong2*>(R.o_qs)[2 * (int64_t)loc] = make_longlong2((long long)q0, (long long)q1);
         reinterpret_cast<longlong2*>(R.o_qs)[2 * (int64_t)loc + 1] = make_longlong2((long long)q2, (long long)q3);
@@ -561,9 +568,9 @@ __global__ void __launch_bounds__(PILEUP_WARPS * 32) k_pileup(RegionDev R, const
         R.o_flags[loc] = (uint8_t)fl;
         R.o_call[loc] = call;
         if ((fl & PB_FL_CHANGED) && ((fl >> PB_FL_KIND_SHIFT) & 3) == PB_KIND_DEL) {
-            cand = 1; R.cand_len[loc] = ilen;
+            cand = 1;
             const uint32_t ci = atomicAdd(&R.sc->n_cand, 1u);
-            if (ci < R.cand_cap) R.cand[ci] = make_int2(loc, r_del); else atomicOr(&R.sc->error, 2);
+            if (ci < R.cand_cap) R.cand[ci] = make_int4(loc, r_del, ilen, 0); else atomicOr(&R.sc->error, 2);
         }
     }
     (void)cand;
@@ -576,13 +583,13 @@ __global__ void __launch_bounds__(PILEUP_WARPS * 32) k_pileup(RegionDev R, const
 // by locus, accepted/rejected with a sequential watermark, then applied in parallel.
 // Single CTA; the candidate list is tiny (one entry per homozygous deletion call).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bitonic_sort_by_x(int2* a, uint32_t npow2) {
+__device__ __forceinline__ void bitonic_sort_by_x(int4* a, uint32_t npow2) {
     for (uint32_t k = 2; k <= npow2; k <<= 1)
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
             for (uint32_t t = threadIdx.x; t < npow2; t += blockDim.x) {
                 const uint32_t ixj = t ^ j;
                 if (ixj > t) {
-                    const int2 A = a[t], Bv = a[ixj];
+                    const int4 A = a[t], Bv = a[ixj];
                     const bool up = (t & k) == 0;
                     if ((A.x > Bv.x) == up) { a[t] = Bv; a[ixj] = A; }
                 }
@@ -591,32 +598,32 @@ __device__ __forceinline__ void bitonic_sort_by_x(int2* a, uint32_t npow2) {
         }
 }
 
-__global__ void __launch_bounds__(1024) k_spill(RegionDev R, int2* scratch, uint32_t scratch_cap) {
-    extern __shared__ int2 sm[];
+__global__ void __launch_bounds__(1024) k_spill(RegionDev R, int4* scratch, uint32_t scratch_cap) {
+    extern __shared__ int4 sm4[];
     const uint32_t n = min(R.sc->n_cand, R.cand_cap);
     if (n == 0) return;
     uint32_t p2 = 1; while (p2 < n) p2 <<= 1;
-    int2* a = (p2 <= 4096) ? sm : scratch;            // 32 KB of shared memory, else the global scratch
+    int4* a = (p2 <= 2048) ? sm4 : scratch;           // 32 KB of shared memory, else the global scratch
     if (p2 > scratch_cap && a == scratch) { if (threadIdx.x == 0) atomicOr(&R.sc->error, 2); return; }
-    for (uint32_t t = threadIdx.x; t < p2; t += blockDim.x) a[t] = t < n ? R.cand[t] : make_int2(0x7fffffff, 0);
+    for (uint32_t t = threadIdx.x; t < p2; t += blockDim.x) a[t] = t < n ? R.cand[t] : make_int4(0x7fffffff, 0, 0, 0);
     __syncthreads();
     bitonic_sort_by_x(a, p2);
-    // sequential watermark: y < 0 marks a rejected candidate
+    // sequential watermark over (locus, deletions, length): w = 1 marks a rejected candidate
     if (threadIdx.x == 0) {
         int64_t deleted_until = -1;
         for (uint32_t t = 0; t < n; t++) {
-            const int32_t loc = a[t].x;
-            if (loc <= deleted_until) { a[t].y = -1 - a[t].y; continue; }    // it is deleted: makes no call
-            const int64_t end = (int64_t)loc + R.cand_len[loc] - 1;
+            const int4 c = a[t];
+            if (c.x <= deleted_until) { a[t].w = 1; continue; }             // it is deleted: makes no call
+            const int64_t end = (int64_t)c.x + c.z - 1;
             if (end > deleted_until) deleted_until = end;
         }
     }
     __syncthreads();
     // apply: every deleted locus belongs to exactly one accepted deletion
     for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
-        const int32_t loc = a[t].x, d = a[t].y;
-        if (d < 0) continue;
-        const int32_t L = R.cand_len[loc];
+        const int4 cd = a[t];
+        if (cd.w) continue;
+        const int32_t loc = cd.x, d = cd.y, L = cd.z;
         for (int32_t j = 1; j < L; j++) {
             const int64_t i = (int64_t)loc + j;
             const int32_t nd = wrap32((int64_t)R.o_del[i] + d);                                  // :263

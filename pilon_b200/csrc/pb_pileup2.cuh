@@ -62,9 +62,9 @@ __device__ __forceinline__ int64_t udiv_fast(uint64_t n, uint64_t d) {      // d
 
 __device__ __forceinline__ void finish_locus(const RegionDev& R, int64_t w, int lane, int32_t loc,
                                              const uint32_t c[4], const uint64_t q[4],
-                                             uint32_t mqS, uint32_t qS, uint32_t bp, uint32_t fragN) {
+                                             uint32_t mqS, uint32_t qS, uint32_t bp, uint32_t fragN,
+                                             uint32_t rb, uint8_t refb) {
     const bool inr = loc < R.size;
-    const uint32_t rb = R.rare_bits[w];
     int32_t r_ins = 0, r_insq = 0, r_del = 0, r_delq = 0, r_q = 0, r_mq = 0, r_clips = 0, r_delfrag = 0;
     uint32_t gi = 0, gd = 0;
     if (inr && ((rb >> lane) & 1)) {
@@ -115,8 +115,8 @@ __device__ __forceinline__ void finish_locus(const RegionDev& R, int64_t w, int 
         call = compute_call(R.cfg, in, &ilen);
     }
     uint32_t fl = 0;
-    if (R.sc->read_count != 0)                                                              // GenomeRegion.scala:229-231
-        fl = classify(call, depth, R.sc->min_depth, ref_class(ref_at(R, (int64_t)R.start + loc)), R.cfg.fix_amb);
+    if (R.read_count != 0)                                                                  // GenomeRegion.scala:229-231
+        fl = classify(call, depth, R.min_depth, ref_class(refb), R.cfg.fix_amb);
     reinterpret_cast<int4*>(R.o_cnt)[loc] = make_int4((int)c[0], (int)c[1], (int)c[2], (int)c[3]);
     reinterpret_cast<longlong2*>(R.o_qs)[2 * (int64_t)loc] = make_longlong2((long long)q[0], (long long)q[1]);
     reinterpret_cast<longlong2*>(R.o_qs)[2 * (int64_t)loc + 1] = make_longlong2((long long)q[2], (long long)q[3]);
@@ -130,9 +130,8 @@ __device__ __forceinline__ void finish_locus(const RegionDev& R, int64_t w, int 
     R.o_flags[loc] = (uint8_t)fl;
     R.o_call[loc] = call;
     if ((fl & PB_FL_CHANGED) && ((fl >> PB_FL_KIND_SHIFT) & 3) == PB_KIND_DEL) {
-        R.cand_len[loc] = ilen;
         const uint32_t ci = atomicAdd(&R.sc->n_cand, 1u);
-        if (ci < R.cand_cap) R.cand[ci] = make_int2(loc, r_del); else atomicOr(&R.sc->error, 2);
+        if (ci < R.cand_cap) R.cand[ci] = make_int4(loc, r_del, ilen, 0); else atomicOr(&R.sc->error, 2);
     }
 }
 
@@ -194,9 +193,8 @@ __global__ void __launch_bounds__(P2_WARPS * 32) k_pileup2(RegionDev R, const De
         const int32_t fwd = B.reach[0], back = B.reach[1];
         const int64_t x = (int64_t)w0 - fwd + 1;
         int64_t khi = (((int64_t)w0 + 32 + back) + 31) >> 5; if (khi > R.n_win) khi = R.n_win;
-        const uint32_t rlo = x <= 0 ? 0u : B.win_first[x >> 5];
-        const uint32_t rhi = (((int64_t)w0 + 32 + back) > ((int64_t)R.n_win << 5)) ? (uint32_t)B.n_reads : B.win_first[khi];
-        const uint32_t slo = B.cigar_off[rlo], shi = B.cigar_off[rhi];
+        const uint32_t slo = x <= 0 ? 0u : B.win_first[x >> 5];
+        const uint32_t shi = (((int64_t)w0 + 32 + back) > ((int64_t)R.n_win << 5)) ? (uint32_t)B.n_cigar : B.win_first[khi];
         const uint8_t* __restrict__ quals = B.quals;
         const uint8_t* __restrict__ bases2 = B.bases2;
         const int nchunks = (int)((shi - slo + 31) >> 5);
@@ -332,7 +330,8 @@ __global__ void __launch_bounds__(P2_WARPS * 32) k_pileup2(RegionDev R, const De
     uint32_t c[4]; uint64_t q[4];
 #pragma unroll
     for (int b = 0; b < 4; b++) { c[b] = S.tcnt[lane][b]; q[b] = S.tqs[lane][b]; }
-    finish_locus(R, w, lane, w0 + lane, c, q, S.tmq[lane], S.tq[lane], S.tbp[lane], fragN);
+    finish_locus(R, w, lane, w0 + lane, c, q, S.tmq[lane], S.tq[lane], S.tbp[lane], fragN, R.rare_bits[w],
+                 (int64_t)w0 + lane < R.size ? ref_at(R, (int64_t)R.start + w0 + lane) : (uint8_t)'N');
 }
 
 }  // namespace pb

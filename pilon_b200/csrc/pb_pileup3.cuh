@@ -2,9 +2,11 @@
 //
 // A CTA owns a tile of 7 windows x 32 loci.  Warp 0 is the PRODUCER: it walks the tile's candidate
 // segment descriptors once, 32 per chunk (lane <-> descriptor), and for every segment that overlaps
-// the tile issues two TMA bulk copies (cp.async.bulk, SASS UBLKCP): the 16-byte-aligned run of
-// quality bytes and of 2-bit codes the tile needs, into a 4-deep ring of shared-memory chunks guarded
-// by full/empty mbarriers.  Warps 1..7 are CONSUMERS, one per window: for every chunk they pick the
+// the tile copies the 16-byte-aligned run of quality bytes and of 2-bit codes the tile needs with
+// per-lane cp.async (SASS LDGSTS; cp.async.bulk/UBLKCP takes warp-uniform operands, so 32 different
+// rows per chunk would serialise -- measured, see profiles/) into a 4-deep ring of shared-memory
+// chunks guarded by full/empty mbarriers; copy completion is signalled to the full barrier with
+// cp.async.mbarrier.arrive.  Warps 1..7 are CONSUMERS, one per window: for every chunk they pick the
 // rows that overlap their window and accumulate them with the byte-SIMD scheme of k_pileup2
 // (lane = (row group, column quad); packed 8-bit counts / 16-bit quality sums for bases that equal
 // the locus' primary letter and carry the chunk's dominant mapping quality).  Everything else stays
@@ -77,9 +79,10 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long* b, uint32_t parity
     atomicOr(err, 8);
     return false;
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+// every cp.async issued so far by this thread arrives on `b` when it lands; the barrier's expected
+// count already includes this arrival (.noinc)
+__device__ __forceinline__ void cp_async_arrive_noinc(unsigned long long* b) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__((P3_CW + 1) * 32) k_pileup3(RegionDev R, const
     int* err = &R.sc->error;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P3_NS; s++) { mbar_init(&S.full[s], 32); mbar_init(&S.empty[s], P3_CW); }
+        for (int s = 0; s < P3_NS; s++) { mbar_init(&S.full[s], 64); mbar_init(&S.empty[s], P3_CW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -106,71 +109,92 @@ __global__ void __launch_bounds__((P3_CW + 1) * 32) k_pileup3(RegionDev R, const
             return true;
         };
         bool alive = true;
-        for (int b = 0; b < n_batches && alive; b++) {
-            const DevBatch& B = batches[b];
-            if (B.n_reads == 0) continue;
-            const int32_t fwd = B.reach[0], back = B.reach[1];
-            const int64_t x = (int64_t)t0 - fwd + 1;
-            const int64_t y = (int64_t)t0 + P3_TILE + back;
-            int64_t khi = (y + 31) >> 5; if (khi > R.n_win) khi = R.n_win;
-            const uint32_t rlo = x <= 0 ? 0u : B.win_first[x >> 5 > R.n_win ? R.n_win : x >> 5];
-            const uint32_t rhi = (y > ((int64_t)R.n_win << 5)) ? (uint32_t)B.n_reads : B.win_first[khi];
-            const uint32_t slo = B.cigar_off[rlo], shi = B.cigar_off[rhi];
-            for (uint32_t sb = slo; sb < shi && alive; sb += 32, n++) {
-                const uint32_t slot = n % P3_NS;
-                alive = acquire(slot);
-                if (!alive) break;
-                Seg mine; mine.loc0 = 0; mine.len = 0; mine.src = 0; mine.w = 0;
-                if (sb + lane < shi) mine = B.seg[sb + lane];
-                const bool ov = mine.len > 0 && mine.loc0 < t0 + P3_TILE && mine.loc0 + mine.len > t0;
-                const bool valid = mine.w & SEG_VALID, hasq = mine.w & SEG_HASQ;
-                const uint32_t mq1 = mine.w & 0xFFFF;
-                const bool elig = ov && valid && hasq;
-                // dominant (adjMq + 1) of the chunk: the value most eligible rows carry; keep the previous one on ties
-                const unsigned peers = __match_any_sync(FULL, elig ? mq1 : (0x10000u + lane));
-                const uint32_t votes = elig ? (((uint32_t)__popc(peers) << 17) | ((mq1 == dom) ? 0x10000u : 0u) | mq1) : 0u;
-                const uint32_t best = __reduce_max_sync(FULL, votes);
-                if (best) dom = best & 0xFFFF;
-                Row3 h; h.c01 = 0; h.q = 0; h.k = ROW_NONE; h.pad = 0;
-                uint32_t bytes = 0;
-                if (ov) {
-                    const int a = mine.loc0 > t0 ? mine.loc0 : t0;
-                    const int e = mine.loc0 + mine.len < t0 + P3_TILE ? mine.loc0 + mine.len : t0 + P3_TILE;
-                    const uint32_t c0 = (uint32_t)(a - t0), c1 = (uint32_t)(e - t0);
-                    h.c01 = c0 | (c1 << 16);
-                    if (!valid) h.k = ROW_INVALID;
-                    else {
-                        const uint32_t i0 = mine.src + (uint32_t)(a - mine.loc0), nb = c1 - c0;
-                        const uint32_t ga = i0 & ~15u, qbytes = (((i0 + nb - 1) | 15u) + 1) - ga;
-                        const uint32_t b0 = i0 >> 2, gb = b0 & ~15u, cbytes = ((((i0 + nb - 1) >> 2) | 15u) + 1) - gb;
-                        uint8_t* row = S.rows[slot][lane];
-                        bulk_g2s(row, B.quals + ga, qbytes, &S.full[slot]);
-                        bulk_g2s(row + P3_QB, B.bases2 + gb, cbytes, &S.full[slot]);
-                        bytes = qbytes + cbytes;
-                        h.q = (i0 - ga) | (mq1 << 16);
-                        const uint32_t cbit = 8 * (b0 - gb) + 2 * (i0 & 3);
-                        h.k = ((hasq && mq1 == dom) ? ROW_FAST : ROW_SCALAR) | ((hasq ? 1u : 0u) << 8) | (cbit << 16);
-                    }
+        for (int bb = 0; bb < n_batches && alive; bb += 32) {
+            // candidate segment range of up to 32 batches at once (lane <-> batch): one load latency for all
+            uint32_t my_slo = 0, my_shi = 0;
+            if (bb + lane < n_batches) {
+                const DevBatch& Bl = batches[bb + lane];
+                if (Bl.n_reads) {
+                    const int64_t x = (int64_t)t0 - Bl.fwd + 1;
+                    const int64_t y = (int64_t)t0 + P3_TILE + Bl.back;
+                    int64_t khi = (y + 31) >> 5; if (khi > R.n_win) khi = R.n_win;
+                    my_slo = x <= 0 ? 0u : Bl.win_first[x >> 5];
+                    my_shi = (y > ((int64_t)R.n_win << 5)) ? (uint32_t)Bl.n_cigar : Bl.win_first[khi];
                 }
-                S.hdr[slot][lane] = h;
-                if (lane == 0) { Chunk3 ch; ch.type = CH_DATA; ch.dom = dom; ch.frag = 0; ch.pad = 0; S.chunk[slot] = ch; }
-                mbar_arrive_tx(&S.full[slot], bytes);
             }
-            if (!alive) break;
-            {   // end of batch: consumers flush and take the fragCoverage snapshot (GenomeRegion.scala:290-298)
-                const uint32_t slot = n % P3_NS;
-                alive = acquire(slot);
+            const int nbb = n_batches - bb < 32 ? n_batches - bb : 32;
+            for (int bi = 0; bi < nbb && alive; bi++) {
+                // registers, not the struct in global memory: the asm memory clobbers below would reload every field per chunk
+                const Seg* __restrict__ segs = batches[bb + bi].seg;
+                const uint8_t* __restrict__ gquals = batches[bb + bi].quals;
+                const uint8_t* __restrict__ gbases = batches[bb + bi].bases2;
+                const uint32_t bfrag = (uint32_t)batches[bb + bi].frag;
+                const bool bempty = batches[bb + bi].n_reads == 0;
+                const uint32_t slo = __shfl_sync(FULL, my_slo, bi), shi = __shfl_sync(FULL, my_shi, bi);
+                if (bempty) continue;
+                const Seg none = {0, 0, 0, 0};
+                Seg next = none;
+                if (slo + lane < shi) next = segs[slo + lane];
+                for (uint32_t sb = slo; sb < shi && alive; sb += 32, n++) {
+                    const Seg mine = next;
+                    next = none;
+                    if (sb + 32 + lane < shi) next = segs[sb + 32 + lane];      // prefetch the next chunk's descriptors
+                    const uint32_t slot = n % P3_NS;
+                    alive = acquire(slot);
+                    if (!alive) break;
+                    const bool ov = mine.len > 0 && mine.loc0 < t0 + P3_TILE && mine.loc0 + mine.len > t0;
+                    const bool valid = mine.w & SEG_VALID, hasq = mine.w & SEG_HASQ;
+                    const uint32_t mq1 = mine.w & 0xFFFF;
+                    const bool elig = ov && valid && hasq;
+                    // dominant (adjMq + 1) of the chunk: the value most eligible rows carry; keep the previous one on ties
+                    const unsigned peers = __match_any_sync(FULL, elig ? mq1 : (0x10000u + lane));
+                    const uint32_t votes = elig ? (((uint32_t)__popc(peers) << 17) | ((mq1 == dom) ? 0x10000u : 0u) | mq1) : 0u;
+                    const uint32_t best = __reduce_max_sync(FULL, votes);
+                    if (best) dom = best & 0xFFFF;
+                    Row3 h; h.c01 = 0; h.q = 0; h.k = ROW_NONE; h.pad = 0;
+                    if (ov) {
+                        const int a = mine.loc0 > t0 ? mine.loc0 : t0;
+                        const int e = mine.loc0 + mine.len < t0 + P3_TILE ? mine.loc0 + mine.len : t0 + P3_TILE;
+                        const uint32_t c0 = (uint32_t)(a - t0), c1 = (uint32_t)(e - t0);
+                        h.c01 = c0 | (c1 << 16);
+                        if (!valid) h.k = ROW_INVALID;
+                        else {
+                            const uint32_t i0 = mine.src + (uint32_t)(a - mine.loc0), nb = c1 - c0;
+                            const uint32_t ga = i0 & ~15u, qblk = (((i0 + nb - 1) >> 4) - (i0 >> 4)) + 1;
+                            const uint32_t b0 = i0 >> 2, gb = b0 & ~15u, cblk = ((((i0 + nb - 1) >> 2) >> 4) - (b0 >> 4)) + 1;
+                            uint8_t* row = S.rows[slot][lane];
+                            const uint8_t* qs = gquals + ga;
+                            for (uint32_t t = 0; t < qblk; t++) cp_async16(row + 16 * t, qs + 16 * t);
+                            const uint8_t* cs = gbases + gb;
+                            for (uint32_t t = 0; t < cblk; t++) cp_async16(row + P3_QB + 16 * t, cs + 16 * t);
+                            h.q = (i0 - ga) | (mq1 << 16);
+                            const uint32_t cbit = 8 * (b0 - gb) + 2 * (i0 & 3);
+                            h.k = ((hasq && mq1 == dom) ? ROW_FAST : ROW_SCALAR) | ((hasq ? 1u : 0u) << 8) | (cbit << 16);
+                        }
+                    }
+                    cp_async_arrive_noinc(&S.full[slot]);
+                    S.hdr[slot][lane] = h;
+                    if (lane == 0) { Chunk3 ch; ch.type = CH_DATA; ch.dom = dom; ch.frag = 0; ch.pad = 0; S.chunk[slot] = ch; }
+                    mbar_arrive(&S.full[slot]);
+                }
                 if (!alive) break;
-                if (lane == 0) { Chunk3 ch; ch.type = CH_EOB; ch.dom = dom; ch.frag = (uint32_t)B.frag; ch.pad = 0; S.chunk[slot] = ch; }
-                mbar_arrive_tx(&S.full[slot], 0);
-                n++;
+                {   // end of batch: consumers flush and take the fragCoverage snapshot (GenomeRegion.scala:290-298)
+                    const uint32_t slot = n % P3_NS;
+                    alive = acquire(slot);
+                    if (!alive) break;
+                    if (lane == 0) { Chunk3 ch; ch.type = CH_EOB; ch.dom = dom; ch.frag = bfrag; ch.pad = 0; S.chunk[slot] = ch; }
+                    cp_async_arrive_noinc(&S.full[slot]);
+                    mbar_arrive(&S.full[slot]);
+                    n++;
+                }
             }
         }
         if (alive) {
             const uint32_t slot = n % P3_NS;
             if (acquire(slot)) {
                 if (lane == 0) { Chunk3 ch; ch.type = CH_EOT; ch.dom = 0; ch.frag = 0; ch.pad = 0; S.chunk[slot] = ch; }
-                mbar_arrive_tx(&S.full[slot], 0);
+                cp_async_arrive_noinc(&S.full[slot]);
+                mbar_arrive(&S.full[slot]);
             }
         }
         return;
@@ -191,6 +215,9 @@ __global__ void __launch_bounds__((P3_CW + 1) * 32) k_pileup3(RegionDev R, const
 #pragma unroll
     for (int b = 0; b < 4; b++) { W.tqs[lane][b] = 0; W.tcnt[lane][b] = 0; }
     W.tmq[lane] = 0; W.tq[lane] = 0; W.tbp[lane] = 0;
+    // epilogue inputs, fetched now so that their latency hides behind the accumulation
+    const uint32_t pre_rb = active ? R.rare_bits[w] : 0u;
+    const uint8_t pre_ref = (active && (int64_t)w0 + lane < R.size) ? ref_at(R, (int64_t)R.start + w0 + lane) : (uint8_t)'N';
     uint32_t P8 = 0;                                                // primary letters of my 4 loci = reference bases
     if (active) {
 #pragma unroll
@@ -345,7 +372,7 @@ __global__ void __launch_bounds__((P3_CW + 1) * 32) k_pileup3(RegionDev R, const
     uint32_t c[4]; uint64_t q[4];
 #pragma unroll
     for (int b = 0; b < 4; b++) { c[b] = W.tcnt[lane][b]; q[b] = W.tqs[lane][b]; }
-    finish_locus(R, w, lane, w0 + lane, c, q, W.tmq[lane], W.tq[lane], W.tbp[lane], fragN);
+    finish_locus(R, w, lane, w0 + lane, c, q, W.tmq[lane], W.tq[lane], W.tbp[lane], fragN, pre_rb, pre_ref);
 }
 
 }  // namespace pb
