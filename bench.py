@@ -151,7 +151,7 @@ def device_batch(torch, c, dev):
     keep = []
     for name, count, width in _BATCH_FIELDS:
         nb = _field_bytes(c, count, width)
-        t = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+        t = torch.empty(nb + 64, dtype=torch.uint8, device=dev)      # kernels fetch aligned 16-byte blocks
         if nb:
             host = np.ctypeslib.as_array(C.cast(getattr(c, name), C.POINTER(C.c_uint8)), shape=(nb,))
             t[:nb].copy_(torch.from_numpy(host))

@@ -58,7 +58,7 @@ struct DevBatch {
 // k_prep spreads its per-warp partial sums over SC_SLOTS slots (same-address L2 atomics serialise);
 // k_scalars folds them into the Scalars block.
 static constexpr int SC_SLOTS = 64;
-struct ScalarSlot { unsigned long long base_count, aligned_bases; int read_count, unknown_ops, dropped_oob, pad; };
+struct ScalarSlot { unsigned long long base_count, aligned_bases; int read_count, unknown_ops, dropped_oob, pad; int fwd[8], back[8]; };
 
 struct Scalars {
     unsigned long long base_count;      // PileUpRegion.baseCount

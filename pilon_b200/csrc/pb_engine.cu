@@ -13,7 +13,7 @@
 
 #include <cub/device/device_merge_sort.cuh>
 
-#include "pb_pileup3.cuh"
+#include "pb_pileup4.cuh"
 
 using namespace pb;
 
@@ -76,7 +76,7 @@ struct pb_engine {
     int64_t launches = 0;
     float last_pileup_ms = 0.f;
     bool dirty = false;              // rare planes may be non-zero after a failed run
-    int pileup_version = 3;          // PB_PILEUP=1|2 selects an earlier kernel generation (A/B runs)
+    int pileup_version = 4;          // PB_PILEUP=1|2|3 selects an earlier kernel generation (A/B runs)
 };
 
 static int free_batches(pb_engine* e) {
@@ -103,7 +103,9 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
     e->cfg.min_qual = c->min_qual; e->cfg.min_mq = c->min_mq; e->cfg.flank = c->flank;
     e->cfg.default_qual = c->default_qual; e->cfg.min_min_depth = c->min_min_depth;
     e->cfg.old_indel = c->old_indel; e->cfg.fix_amb = c->fix_amb; e->cfg.min_depth = c->min_depth;
-    if (const char* v = getenv("PB_PILEUP")) { const int pv = atoi(v); if (pv >= 1 && pv <= 3) e->pileup_version = pv; }
+    if (const char* v = getenv("PB_PILEUP")) { const int pv = atoi(v); if (pv >= 1 && pv <= 4) e->pileup_version = pv; }
+    CK(cudaFuncSetAttribute(k_pileup4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem4)));
+    CK(cudaFuncSetAttribute(k_pileup4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem4)));
     CK(cudaFuncSetAttribute(k_pileup3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem3)));
     CK(cudaFuncSetAttribute(k_pileup3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem3)));
     CK(cudaFuncSetAttribute(k_pileup2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * P2_WARPS)));
@@ -266,15 +268,20 @@ static int compute(pb_engine* e, bool time_pileup) {
     e->dirty = true;
     CK(cudaMemsetAsync(e->scalars.p, 0, SC_BYTES, s));
 
-    for (int i = 0; i < nb; i++) {
-        const DevBatch& d = e->batches[i].d;
-        CK(cudaMemsetAsync(d.win_first, 0, ((size_t)R.n_win + 2) * 4, s));
-        if (d.n_reads == 0) continue;
-        k_prep<<<(unsigned)((d.n_reads + 127) / 128), 128, 0, s>>>(R, d, (uint32_t)i);
-        k_index<<<(unsigned)((d.n_reads + 255) / 256), 256, 0, s>>>(R, d);
-        e->launches += 2;
+    int32_t* reach_base = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(e->scalars.p) + SC_REACH_OFF);
+    if (nb == 0) { k_fold<<<1, 32, 0, s>>>(R, reach_base, 0, 1); e->launches++; }
+    for (int i0 = 0; i0 < nb; i0 += 8) {     // k_prep folds its block partials into slots that carry 8 batches' reach
+        const int i1 = std::min(nb, i0 + 8);
+        for (int i = i0; i < i1; i++) {
+            const DevBatch& d = e->batches[i].d;
+            CK(cudaMemsetAsync(d.win_first, 0, ((size_t)R.n_win + 2) * 4, s));
+            if (d.n_reads == 0) continue;
+            k_prep<<<(unsigned)((d.n_reads + 127) / 128), 128, 0, s>>>(R, d, (uint32_t)i);
+            k_index<<<(unsigned)((d.n_reads + 255) / 256), 256, 0, s>>>(R, d);
+            e->launches += 2;
+        }
+        k_fold<<<1, 32, 0, s>>>(R, reach_base + 2 * i0, i1 - i0, i1 == nb); e->launches++;
     }
-    k_scalars<<<1, 1, 0, s>>>(R); e->launches++;
     CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, SC_REACH_OFF + 8 * (size_t)nb, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(e->ev_sc, s));
     // physCov scan does not depend on the events: keeps the GPU busy while the host waits for n_events
@@ -307,6 +314,10 @@ static int compute(pb_engine* e, bool time_pileup) {
         const unsigned grid = (unsigned)((R.n_win + PILEUP_WARPS - 1) / PILEUP_WARPS);
         if (e->cfg.min_qual > 0) k_pileup<true><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
         else k_pileup<false><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
+    } else if (e->pileup_version == 4) {
+        const unsigned grid = (unsigned)((R.n_win + P4_CW - 1) / P4_CW);
+        if (e->cfg.min_qual > 0) k_pileup4<true><<<grid, (P4_CW + 1) * 32, sizeof(Smem4), s>>>(R, dB, nb);
+        else k_pileup4<false><<<grid, (P4_CW + 1) * 32, sizeof(Smem4), s>>>(R, dB, nb);
     } else if (e->pileup_version == 3) {
         const unsigned grid = (unsigned)((R.n_win + P3_CW - 1) / P3_CW);
         if (e->cfg.min_qual > 0) k_pileup3<true><<<grid, (P3_CW + 1) * 32, sizeof(Smem3), s>>>(R, dB, nb);

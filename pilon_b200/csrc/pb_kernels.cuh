@@ -210,7 +210,12 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
         }
         B.insert_out[r] = ins;
     }
-    // warp-aggregate the region scalars
+    // block-aggregate the region scalars: shuffle within the warp, shared memory across warps, then one
+    // global atomic per quantity per block, spread over SC_SLOTS slots (same-address L2 atomics serialise)
+    __shared__ unsigned long long s_bc, s_al;
+    __shared__ int s_rc, s_unk, s_drop, s_fwd, s_back;
+    if (threadIdx.x == 0) { s_bc = 0; s_al = 0; s_rc = 0; s_unk = 0; s_drop = 0; s_fwd = 0; s_back = 0; }
+    __syncthreads();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         bc += __shfl_xor_sync(FULL, bc, o); aligned += __shfl_xor_sync(FULL, aligned, o);
@@ -218,15 +223,24 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
         fwd = max(fwd, __shfl_xor_sync(FULL, fwd, o)); back = max(back, __shfl_xor_sync(FULL, back, o));
     }
     if ((threadIdx.x & 31) == 0) {
-        ScalarSlot* sl = &R.slots[(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (SC_SLOTS - 1)];
-        if (bc) atomicAdd(&sl->base_count, bc);
-        if (aligned) atomicAdd(&sl->aligned_bases, aligned);
-        if (rc) atomicAdd(&sl->read_count, rc);
-        if (unk) atomicAdd(&sl->unknown_ops, unk);
-        if (drop) atomicAdd(&sl->dropped_oob, drop);
-        // reach only ever grows: a plain read filters almost every atomicMax away
-        if (fwd > *(volatile int32_t*)&B.reach[0]) atomicMax(&B.reach[0], fwd);
-        if (back > *(volatile int32_t*)&B.reach[1]) atomicMax(&B.reach[1], back);
+        if (bc) atomicAdd(&s_bc, bc);
+        if (aligned) atomicAdd(&s_al, aligned);
+        if (rc) atomicAdd(&s_rc, rc);
+        if (unk) atomicAdd(&s_unk, unk);
+        if (drop) atomicAdd(&s_drop, drop);
+        if (fwd) atomicMax(&s_fwd, fwd);
+        if (back) atomicMax(&s_back, back);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ScalarSlot* sl = &R.slots[blockIdx.x & (SC_SLOTS - 1)];
+        if (s_bc) atomicAdd(&sl->base_count, s_bc);
+        if (s_al) atomicAdd(&sl->aligned_bases, s_al);
+        if (s_rc) atomicAdd(&sl->read_count, s_rc);
+        if (s_unk) atomicAdd(&sl->unknown_ops, s_unk);
+        if (s_drop) atomicAdd(&sl->dropped_oob, s_drop);
+        if (s_fwd) atomicMax(&sl->fwd[batch_id & 7], s_fwd);     // reach is per batch: folded by k_scalars
+        if (s_back) atomicMax(&sl->back[batch_id & 7], s_back);
     }
 }
 
@@ -251,22 +265,45 @@ __global__ void __launch_bounds__(256) k_index(RegionDev R, DevBatch B) {
 }
 
 // region coverage and minDepth (PileUpRegion.scala:36; GenomeRegion.scala:221-224)
-__global__ void k_scalars(RegionDev R) {
-    Scalars* sc = R.sc;
-    for (int i = 0; i < SC_SLOTS; i++) {
-        const ScalarSlot& sl = R.slots[i];
-        sc->base_count += sl.base_count; sc->aligned_bases += sl.aligned_bases; sc->read_count += sl.read_count;
-        sc->unknown_ops += sl.unknown_ops; sc->dropped_oob += sl.dropped_oob;
+// launched once per group of <= 8 batches with 32 threads: folds the slots, then (last group only)
+// coverage and minDepth
+__global__ void k_fold(RegionDev R, int32_t* reach0, int nb, int last) {
+    const int lane = threadIdx.x;
+    unsigned long long bc = 0, al = 0; int rc = 0, unk = 0, drop = 0; int fw[8], bk[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { fw[j] = 0; bk[j] = 0; }
+    for (int i = lane; i < SC_SLOTS; i += 32) {
+        ScalarSlot& sl = R.slots[i];
+        bc += sl.base_count; al += sl.aligned_bases; rc += sl.read_count; unk += sl.unknown_ops; drop += sl.dropped_oob;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { fw[j] = max(fw[j], sl.fwd[j]); bk[j] = max(bk[j], sl.back[j]); }
+        ScalarSlot z = {}; sl = z;
     }
-    const long long cov = roundDivL((long long)sc->base_count, R.size);
-    sc->coverage = cov;
-    int md;
-    if (R.cfg.min_depth >= 1) md = (int)R.cfg.min_depth;
-    else {
-        const double v = floor(__dadd_rn(__dmul_rn(R.cfg.min_depth, (double)cov), 0.5));   // Double.round, no FMA contraction
-        md = (int)v > R.cfg.min_min_depth ? (int)v : R.cfg.min_min_depth;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bc += __shfl_xor_sync(FULL, bc, o); al += __shfl_xor_sync(FULL, al, o);
+        rc += __shfl_xor_sync(FULL, rc, o); unk += __shfl_xor_sync(FULL, unk, o); drop += __shfl_xor_sync(FULL, drop, o);
+#pragma unroll
+        for (int j = 0; j < 8; j++) { fw[j] = max(fw[j], __shfl_xor_sync(FULL, fw[j], o)); bk[j] = max(bk[j], __shfl_xor_sync(FULL, bk[j], o)); }
     }
-    sc->min_depth = md;
+    if (lane == 0) {
+        Scalars* sc = R.sc;
+        sc->base_count += bc; sc->aligned_bases += al; sc->read_count += rc; sc->unknown_ops += unk; sc->dropped_oob += drop;
+#pragma unroll
+        for (int j = 0; j < 8; j++) if (j < nb) { reach0[2 * j] = fw[j]; reach0[2 * j + 1] = bk[j]; }
+        if (last) {
+            // region coverage and minDepth (PileUpRegion.scala:36; GenomeRegion.scala:221-224)
+            const long long cov = roundDivL((long long)sc->base_count, R.size);
+            sc->coverage = cov;
+            int md;
+            if (R.cfg.min_depth >= 1) md = (int)R.cfg.min_depth;
+            else {
+                const double v = floor(__dadd_rn(__dmul_rn(R.cfg.min_depth, (double)cov), 0.5));   // Double.round, no FMA contraction
+                md = (int)v > R.cfg.min_min_depth ? (int)v : R.cfg.min_min_depth;
+            }
+            sc->min_depth = md;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
