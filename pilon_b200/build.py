@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libpilonb200.so")
 SOURCES = ["pb_engine.cu"]
-DEPS = ["pb_engine.cu", "pb_kernels.cuh", "pb_pileup2.cuh", "pb_pileup3.cuh", "pb_pileup4.cuh", "pb_device.cuh", os.path.join("..", "..", "include", "pilon_b200.h")]
+DEPS = ["pb_engine.cu", "pb_kernels.cuh", "pb_pileup2.cuh", "pb_pileup3.cuh", "pb_pileup4.cuh", "pb_pileup5.cuh", "pb_device.cuh", os.path.join("..", "..", "include", "pilon_b200.h")]
 
 
 def nvcc_path() -> str:

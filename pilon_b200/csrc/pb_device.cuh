@@ -38,6 +38,17 @@ struct __align__(8) Group {          // device image of pb_indel (+ the winning 
     int64_t str_off;
 };
 
+struct __align__(32) Rare { int32_t ins, insq, del, delq, q, mq, clips, delfrag; };
+
+// What the pileup kernel needs to know about a batch, passed BY VALUE in the kernel parameters
+// (constant bank): no dependent global load stands between a warp and its first descriptor.
+struct PileBatch {
+    const Seg* seg; const uint8_t* quals; const uint8_t* bases2; const uint32_t* win_first;
+    uint32_t n_cigar; int32_t fwd, back; uint32_t flags;      // flags: 1 = counts toward fragCoverage, 2 = has reads
+};
+static constexpr int PB_MAXB = 20;
+struct PileBatches { int32_t n; int32_t pad; PileBatch b[PB_MAXB]; };
+
 struct DevBatch {
     int64_t n_reads, n_cigar, n_seq, n_exc;
     const int32_t *pos, *tlen, *read_len;
@@ -87,9 +98,10 @@ struct RegionDev {
     Cfg cfg;
     int32_t read_count, min_depth;   // host copies of the region scalars, valid for kernels launched after k_scalars' read-back
     Scalars* sc;
-    // sparse ("rare") per-locus planes, zero between regions; written by k_prep with atomics,
-    // consumed and re-zeroed by the pileup epilogue wherever rare_bits says so
-    int32_t *r_ins, *r_insq, *r_del, *r_delq, *r_q, *r_mq, *r_clips, *r_delfrag;
+    // sparse ("rare") per-locus contributions, zero between regions; written by k_prep with atomics,
+    // consumed and re-zeroed by the pileup epilogue wherever rare_bits says so.  One 32-byte struct per
+    // locus = one DRAM sector (eight separate planes cost eight sector round trips per touched locus).
+    Rare* rare;
     uint32_t *r_gins, *r_gdel;  // group index + 1 of the locus' insertion / deletion evidence
     uint32_t* rare_bits;        // [n_win] bit l set = locus 32*w + l has any rare contribution
     int2* pc_diff;              // physCov / insertSize difference array (PileUpRegion.scala:62-88)
@@ -99,6 +111,8 @@ struct RegionDev {
     uint8_t* str_pool; uint64_t str_cap;
     int4* cand;  uint32_t cand_cap;     // unordered pass-1 DEL candidates: (locus index, deletions, length, -)
     ScalarSlot* slots;                  // [SC_SLOTS] k_prep partial sums
+    int32_t exp_flags;                  // PB_EXP timing experiments (results invalid): 1 skip epilogue, 2 skip compute, 4 skip staging copies
+    long long* dbg; int32_t dbg_tile;   // optional timeline of one tile (PB_DEBUG_TILE), 8 warps x 256 (tag, clock) pairs
     // outputs (final state)
     int32_t* o_cnt;   // [size*4]
     int64_t* o_qs;    // [size*4]

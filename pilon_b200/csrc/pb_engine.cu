@@ -13,7 +13,7 @@
 
 #include <cub/device/device_merge_sort.cuh>
 
-#include "pb_pileup4.cuh"
+#include "pb_pileup5.cuh"
 
 using namespace pb;
 
@@ -68,15 +68,15 @@ struct pb_engine {
     std::vector<HostBatch> batches;
     DBuf d_batches;                  // DevBatch[] image
     // per-locus buffers
-    DBuf ref, rare[10], rare_bits, pc_diff, block_sums, scalars;
+    DBuf ref, rare, gplane[2], rare_bits, pc_diff, block_sums, scalars;
     DBuf o_cnt, o_qs, o_i32[12], o_wq, o_wmq, o_flags, o_call;
     // event buffers
-    DBuf ev_key, ev, perm, groups, cand, spill_scratch, str_pool, cub_tmp;
+    DBuf ev_key, ev, perm, groups, cand, spill_scratch, str_pool, cub_tmp, dbg;
     Scalars* h_sc = nullptr;         // pinned
     int64_t launches = 0;
     float last_pileup_ms = 0.f;
     bool dirty = false;              // rare planes may be non-zero after a failed run
-    int pileup_version = 4;          // PB_PILEUP=1|2|3 selects an earlier kernel generation (A/B runs)
+    int pileup_version = 5;          // PB_PILEUP=1..4 selects an earlier kernel generation (A/B runs)
 };
 
 static int free_batches(pb_engine* e) {
@@ -103,7 +103,9 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
     e->cfg.min_qual = c->min_qual; e->cfg.min_mq = c->min_mq; e->cfg.flank = c->flank;
     e->cfg.default_qual = c->default_qual; e->cfg.min_min_depth = c->min_min_depth;
     e->cfg.old_indel = c->old_indel; e->cfg.fix_amb = c->fix_amb; e->cfg.min_depth = c->min_depth;
-    if (const char* v = getenv("PB_PILEUP")) { const int pv = atoi(v); if (pv >= 1 && pv <= 4) e->pileup_version = pv; }
+    if (const char* v = getenv("PB_PILEUP")) { const int pv = atoi(v); if (pv >= 1 && pv <= 5) e->pileup_version = pv; }
+    CK(cudaFuncSetAttribute(k_pileup5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Warp5) * P5_WARPS)));
+    CK(cudaFuncSetAttribute(k_pileup5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Warp5) * P5_WARPS)));
     CK(cudaFuncSetAttribute(k_pileup4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem4)));
     CK(cudaFuncSetAttribute(k_pileup4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem4)));
     CK(cudaFuncSetAttribute(k_pileup3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem3)));
@@ -133,7 +135,7 @@ extern "C" int pb_destroy(pb_engine* e) {
                    &e->o_cnt, &e->o_qs, &e->o_wq, &e->o_wmq, &e->o_flags, &e->o_call, &e->ev_key, &e->ev, &e->perm,
                    &e->groups, &e->cand, &e->spill_scratch, &e->str_pool, &e->cub_tmp};
     for (DBuf* b : all) b->release();
-    for (auto& b : e->rare) b.release();
+    e->rare.release(); for (auto& b : e->gplane) b.release();
     for (auto& b : e->o_i32) b.release();
     if (e->h_sc) cudaFreeHost(e->h_sc);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->evp0); cudaEventDestroy(e->evp1);
@@ -163,13 +165,15 @@ extern "C" int pb_region_begin(pb_engine* e, const uint8_t* contig, int64_t cont
     CK(cudaMemcpyAsync(e->ref.p, contig + (R.ref_locus0 - 1), ref_bytes, cudaMemcpyHostToDevice, s));
     R.ref = e->ref.as<uint8_t>();
     if (e->dirty) {   // a failed run may have left sparse planes populated
-        for (auto& b : e->rare) if (b.p) CK(cudaMemsetAsync(b.p, 0, b.cap, s));
+        if (e->rare.p) CK(cudaMemsetAsync(e->rare.p, 0, e->rare.cap, s));
+        for (auto& b : e->gplane) if (b.p) CK(cudaMemsetAsync(b.p, 0, b.cap, s));
         if (e->rare_bits.p) CK(cudaMemsetAsync(e->rare_bits.p, 0, e->rare_bits.cap, s));
         if (e->pc_diff.p) CK(cudaMemsetAsync(e->pc_diff.p, 0, e->pc_diff.cap, s));
         e->dirty = false;
     }
     const size_t n4 = (size_t)S * 4;
-    for (auto& b : e->rare) CK(b.ensure(n4, true, s));
+    CK(e->rare.ensure((size_t)S * sizeof(Rare), true, s));
+    for (auto& b : e->gplane) CK(b.ensure(n4, true, s));
     CK(e->rare_bits.ensure((size_t)R.n_win * 4, true, s));
     CK(e->pc_diff.ensure((size_t)S * 8, true, s));
     CK(e->scalars.ensure(SC_BYTES, false, s));
@@ -182,10 +186,8 @@ extern "C" int pb_region_begin(pb_engine* e, const uint8_t* contig, int64_t cont
     CK(e->block_sums.ensure((size_t)nblocks * 8, false, s));
     R.sc = e->scalars.as<Scalars>();
     R.slots = reinterpret_cast<ScalarSlot*>(static_cast<uint8_t*>(e->scalars.p) + sizeof(Scalars));
-    R.r_ins = e->rare[0].as<int32_t>(); R.r_insq = e->rare[1].as<int32_t>(); R.r_del = e->rare[2].as<int32_t>();
-    R.r_delq = e->rare[3].as<int32_t>(); R.r_q = e->rare[4].as<int32_t>(); R.r_mq = e->rare[5].as<int32_t>();
-    R.r_clips = e->rare[6].as<int32_t>(); R.r_delfrag = e->rare[7].as<int32_t>();
-    R.r_gins = e->rare[8].as<uint32_t>(); R.r_gdel = e->rare[9].as<uint32_t>();
+    R.rare = e->rare.as<Rare>();
+    R.r_gins = e->gplane[0].as<uint32_t>(); R.r_gdel = e->gplane[1].as<uint32_t>();
     R.rare_bits = e->rare_bits.as<uint32_t>();
     R.pc_diff = e->pc_diff.as<int2>();
     R.o_cnt = e->o_cnt.as<int32_t>(); R.o_qs = e->o_qs.as<int64_t>();
@@ -309,13 +311,31 @@ static int compute(pb_engine* e, bool time_pileup) {
         CK(cub::DeviceMergeSort::SortPairs(e->cub_tmp.p, tmp, R.ev_key, e->perm.as<uint32_t>(), (int64_t)n_ev, EventKeyLess(), s));
         k_groups<<<(n_ev + 255) / 256, 256, 0, s>>>(R, dB, R.ev_key, e->perm.as<uint32_t>(), n_ev); e->launches++;
     }
+    if (const char* xf = getenv("PB_EXP")) R.exp_flags = atoi(xf);
     if (time_pileup) CK(cudaEventRecord(e->evp0, s));
     if (e->pileup_version == 1) {
         const unsigned grid = (unsigned)((R.n_win + PILEUP_WARPS - 1) / PILEUP_WARPS);
         if (e->cfg.min_qual > 0) k_pileup<true><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
         else k_pileup<false><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
-    } else if (e->pileup_version == 4) {
+    } else if (e->pileup_version == 5 && nb <= PB_MAXB) {
+        const unsigned grid = (unsigned)((R.n_win + P5_WARPS - 1) / P5_WARPS);
+        const size_t smem = sizeof(Warp5) * P5_WARPS;
+        PileBatches PBt; memset(&PBt, 0, sizeof(PBt)); PBt.n = nb;
+        for (int i = 0; i < nb; i++) {
+            const DevBatch& d = img[i];
+            PBt.b[i].seg = d.seg; PBt.b[i].quals = d.quals; PBt.b[i].bases2 = d.bases2; PBt.b[i].win_first = d.win_first;
+            PBt.b[i].n_cigar = (uint32_t)d.n_cigar; PBt.b[i].fwd = d.fwd; PBt.b[i].back = d.back;
+            PBt.b[i].flags = (d.frag ? 1u : 0u) | (d.n_reads ? 2u : 0u);
+        }
+        if (e->cfg.min_qual > 0) k_pileup5<true><<<grid, P5_WARPS * 32, smem, s>>>(R, PBt);
+        else k_pileup5<false><<<grid, P5_WARPS * 32, smem, s>>>(R, PBt);
+    } else if (e->pileup_version >= 4) {      // (also: more batches than k_pileup5's by-value table holds)
         const unsigned grid = (unsigned)((R.n_win + P4_CW - 1) / P4_CW);
+        if (const char* dt = getenv("PB_DEBUG_TILE")) {
+            CK(e->dbg.ensure(8 * 256 * 16, false, s));
+            CK(cudaMemsetAsync(e->dbg.p, 0, 8 * 256 * 16, s));
+            R.dbg = e->dbg.as<long long>(); R.dbg_tile = atoi(dt);
+        }
         if (e->cfg.min_qual > 0) k_pileup4<true><<<grid, (P4_CW + 1) * 32, sizeof(Smem4), s>>>(R, dB, nb);
         else k_pileup4<false><<<grid, (P4_CW + 1) * 32, sizeof(Smem4), s>>>(R, dB, nb);
     } else if (e->pileup_version == 3) {
@@ -330,6 +350,19 @@ static int compute(pb_engine* e, bool time_pileup) {
     }
     e->launches++;
     if (time_pileup) CK(cudaEventRecord(e->evp1, s));
+    if (R.dbg) {
+        std::vector<long long> h(8 * 256 * 2);
+        CK(cudaStreamSynchronize(s));
+        CK(cudaMemcpy(h.data(), R.dbg, h.size() * 8, cudaMemcpyDeviceToHost));
+        long long t0c = 0;
+        for (int w = 0; w < 8; w++) for (int i = 0; i < 256; i++) { long long t = h[(w * 256 + i) * 2 + 1]; if (t && (!t0c || t < t0c)) t0c = t; }
+        for (int w = 0; w < 8; w++) {
+            printf("DBG warp %d:", w);
+            for (int i = 0; i < 256; i++) { long long tg = h[(w * 256 + i) * 2], t = h[(w * 256 + i) * 2 + 1]; if (!t) break; printf(" %lld.%lld@%lld", tg >> 32, tg & 0xffffffff, t - t0c); }
+            printf("\n");
+        }
+        R.dbg = nullptr;
+    }
     // deletion spill: candidates are bounded by the number of deletion groups
     uint32_t p2 = 1; while (p2 < n_ev) p2 <<= 1;
     CK(e->spill_scratch.ensure((size_t)p2 * sizeof(int4) + 16, false, s));

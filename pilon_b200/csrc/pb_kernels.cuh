@@ -101,8 +101,8 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
             } else if (op == 4) {                                                                // S  :194-206
                 const int64_t clipStart = readOffset == 0 ? locus - len : locus;
                 const int64_t clipEnd = clipStart + len - 1;
-                if (clipStart >= R.start && clipStart <= R.stop) { atomicAdd(&R.r_clips[clipStart - R.start], 1); mark_rare(R, clipStart - R.start); }
-                if (clipEnd >= R.start && clipEnd <= R.stop) { atomicAdd(&R.r_clips[clipEnd - R.start], 1); mark_rare(R, clipEnd - R.start); }
+                if (clipStart >= R.start && clipStart <= R.stop) { atomicAdd(&R.rare[clipStart - R.start].clips, 1); mark_rare(R, clipStart - R.start); }
+                if (clipEnd >= R.start && clipEnd <= R.stop) { atomicAdd(&R.rare[clipEnd - R.start].clips, 1); mark_rare(R, clipEnd - R.start); }
                 const int64_t l0 = clipStart > R.start ? clipStart : R.start;
                 const int64_t l1 = clipEnd < R.stop ? clipEnd : R.stop;
                 if (l1 >= l0) { sg.loc0 = (int32_t)(l0 - R.start); sg.len = (int32_t)(l1 - l0 + 1); sg.w = 0; }   // badPair++ each
@@ -122,9 +122,9 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
                         const int64_t i = iloc - R.start;
                         uint8_t b0, q0; read_base(B, src, &b0, &q0);
                         const int qual = hasq ? (int)(int8_t)q0 : (int)(int8_t)cfg.default_qual;
-                        atomicAdd(&R.r_insq[i], indelMq + 1);                 // PileUp.addInsertion, PileUp.scala:98-105
-                        atomicAdd(&R.r_q[i], qual);
-                        atomicAdd(&R.r_ins[i], 1);
+                        atomicAdd(&R.rare[i].insq, indelMq + 1);                 // PileUp.addInsertion, PileUp.scala:98-105
+                        atomicAdd(&R.rare[i].q, qual);
+                        atomicAdd(&R.rare[i].ins, 1);
                         mark_rare(R, i);
                         // identity of the rotated string: final[t] = orig[(t - rot) mod len]
                         const uint32_t rm = (uint32_t)(rot % (uint32_t)len);
@@ -170,11 +170,11 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
                         const int64_t i = dloc - R.start;
                         uint8_t b0, q0; read_base(B, seq0 + (uint32_t)readOffset, &b0, &q0);
                         const int qual = hasq ? (int)(int8_t)q0 : (int)(int8_t)cfg.default_qual;
-                        atomicAdd(&R.r_mq[i], indelMq + 1);                   // PileUp.addDeletion, PileUp.scala:107-114
-                        atomicAdd(&R.r_delq[i], indelMq + 1);
-                        atomicAdd(&R.r_q[i], qual);
-                        atomicAdd(&R.r_del[i], 1);
-                        if (B.frag) atomicAdd(&R.r_delfrag[i], 1);
+                        atomicAdd(&R.rare[i].mq, indelMq + 1);                   // PileUp.addDeletion, PileUp.scala:107-114
+                        atomicAdd(&R.rare[i].delq, indelMq + 1);
+                        atomicAdd(&R.rare[i].q, qual);
+                        atomicAdd(&R.rare[i].del, 1);
+                        if (B.frag) atomicAdd(&R.rare[i].delfrag, 1);
                         mark_rare(R, i);
                         const uint32_t ei = atomicAdd(&R.sc->n_events, 1u);
                         if (ei < R.ev_cap) {
@@ -569,11 +569,11 @@ __global__ void __launch_bounds__(PILEUP_WARPS * 32) k_pileup(RegionDev R, const
     int32_t r_ins = 0, r_insq = 0, r_del = 0, r_delq = 0, r_q = 0, r_mq = 0, r_clips = 0, r_delfrag = 0;
     uint32_t gi = 0, gd = 0;
     if (inr && ((rb >> lane) & 1)) {
-        r_ins = R.r_ins[loc]; r_insq = R.r_insq[loc]; r_del = R.r_del[loc]; r_delq = R.r_delq[loc];
-        r_q = R.r_q[loc]; r_mq = R.r_mq[loc]; r_clips = R.r_clips[loc]; r_delfrag = R.r_delfrag[loc];
+        int4* rp = reinterpret_cast<int4*>(&R.rare[loc]);
+        const int4 ra = rp[0], rb2 = rp[1];
+        r_ins = ra.x; r_insq = ra.y; r_del = ra.z; r_delq = ra.w; r_q = rb2.x; r_mq = rb2.y; r_clips = rb2.z; r_delfrag = rb2.w;
         gi = R.r_gins[loc]; gd = R.r_gdel[loc];
-        R.r_ins[loc] = 0; R.r_insq[loc] = 0; R.r_del[loc] = 0; R.r_delq[loc] = 0;
-        R.r_q[loc] = 0; R.r_mq[loc] = 0; R.r_clips[loc] = 0; R.r_delfrag[loc] = 0;
+        rp[0] = make_int4(0, 0, 0, 0); rp[1] = make_int4(0, 0, 0, 0);
     }
     if (rb && lane == 0) R.rare_bits[w] = 0;
     uint32_t cand = 0;

@@ -67,12 +67,12 @@ __device__ __forceinline__ void finish_locus(const RegionDev& R, int64_t w, int 
     const bool inr = loc < R.size;
     int32_t r_ins = 0, r_insq = 0, r_del = 0, r_delq = 0, r_q = 0, r_mq = 0, r_clips = 0, r_delfrag = 0;
     uint32_t gi = 0, gd = 0;
-    if (inr && ((rb >> lane) & 1)) {
-        r_ins = R.r_ins[loc]; r_insq = R.r_insq[loc]; r_del = R.r_del[loc]; r_delq = R.r_delq[loc];
-        r_q = R.r_q[loc]; r_mq = R.r_mq[loc]; r_clips = R.r_clips[loc]; r_delfrag = R.r_delfrag[loc];
-        gi = R.r_gins[loc]; gd = R.r_gdel[loc];
-        R.r_ins[loc] = 0; R.r_insq[loc] = 0; R.r_del[loc] = 0; R.r_delq[loc] = 0;
-        R.r_q[loc] = 0; R.r_mq[loc] = 0; R.r_clips[loc] = 0; R.r_delfrag[loc] = 0;
+    if (inr && ((rb >> lane) & 1) && !(R.exp_flags & 32)) {
+        int4* rp = reinterpret_cast<int4*>(&R.rare[loc]);
+        const int4 ra = rp[0], rb2 = rp[1];
+        r_ins = ra.x; r_insq = ra.y; r_del = ra.z; r_delq = ra.w; r_q = rb2.x; r_mq = rb2.y; r_clips = rb2.z; r_delfrag = rb2.w;
+        if (r_ins > 2 || r_del > 2) { gi = R.r_gins[loc]; gd = R.r_gdel[loc]; }     // only an indel call needs the evidence groups
+        rp[0] = make_int4(0, 0, 0, 0); rp[1] = make_int4(0, 0, 0, 0);
     }
     if (rb && lane == 0) R.rare_bits[w] = 0;
     if (!inr) return;
@@ -82,7 +82,8 @@ __device__ __forceinline__ void finish_locus(const RegionDev& R, int64_t w, int 
     const int64_t qtot = (int64_t)(q[0] + q[1] + q[2] + q[3]);
     uint64_t call;
     int32_t ilen = 0;
-    if (r_ins <= 2 && r_del <= 2) {
+    if (R.exp_flags & 16) { call = (uint64_t)(c[0] + mqSum); }
+    else if (r_ins <= 2 && r_del <= 2) {
         // no indel can be called (PileUp.scala:183-191): the plain-base BaseCall with select-based ordering
         const bool useq = qSum > 0;                                                         // :135
         const int64_t s0 = useq ? (int64_t)q[0] : c[0], s1 = useq ? (int64_t)q[1] : c[1];
@@ -117,6 +118,7 @@ __device__ __forceinline__ void finish_locus(const RegionDev& R, int64_t w, int 
     uint32_t fl = 0;
     if (R.read_count != 0)                                                                  // GenomeRegion.scala:229-231
         fl = classify(call, depth, R.min_depth, ref_class(refb), R.cfg.fix_amb);
+    if ((R.exp_flags & 8) && call != 0x1234567812345678ull) return;
     reinterpret_cast<int4*>(R.o_cnt)[loc] = make_int4((int)c[0], (int)c[1], (int)c[2], (int)c[3]);
     reinterpret_cast<longlong2*>(R.o_qs)[2 * (int64_t)loc] = make_longlong2((long long)q[0], (long long)q[1]);
     reinterpret_cast<longlong2*>(R.o_qs)[2 * (int64_t)loc + 1] = make_longlong2((long long)q[2], (long long)q[3]);

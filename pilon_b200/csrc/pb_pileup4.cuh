@@ -41,10 +41,22 @@ struct __align__(128) Slot4 {
     Chunk4 ch;
 };
 
+// Per-window accumulation table.  The running sums are 32-bit so that every update is a native,
+// fire-and-forget shared-memory atomic (64-bit shared atomics are CAS loops); a quality sum grows by
+// at most 127 * 256 per row, so it is folded into the 64-bit table every SPILL_ROWS rows.
+struct __align__(16) Warp4 {
+    unsigned long long tqs64[32][4];
+    uint32_t tqs[32][4];
+    uint32_t tcnt[32][4];
+    uint32_t tmq[32], tq[32], tbp[32];
+    unsigned long long codes[32];
+};
+static constexpr uint32_t P4_SPILL_ROWS = 120000;   // 120000 * 32512 < 2^32
+
 struct __align__(128) Smem4 {
     Slot4 slot[P4_NS];
     unsigned long long full[P4_NS], empty[P4_NS];
-    Warp3 warp[P4_CW];
+    Warp4 warp[P4_CW];
 };
 
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
@@ -59,6 +71,12 @@ __global__ void __launch_bounds__((P4_CW + 1) * 32) k_pileup4(RegionDev R, const
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int32_t t0 = (int32_t)blockIdx.x * P4_TILE;
     int* err = &R.sc->error;
+    // debug timeline (off unless PB_DEBUG_TILE selects this tile)
+    const bool dbg_on = R.dbg != nullptr && (int32_t)blockIdx.x == R.dbg_tile && lane == 0;
+    int dbg_n = 0;
+    auto mark = [&](int tag, uint32_t n) {
+        if (dbg_on && dbg_n < 255) { R.dbg[(warp * 256 + dbg_n) * 2] = ((long long)tag << 32) | n; R.dbg[(warp * 256 + dbg_n) * 2 + 1] = clock64(); dbg_n++; }
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P4_NS; s++) { mbar_init(&S.full[s], 32); mbar_init(&S.empty[s], P4_CW); }
@@ -108,12 +126,16 @@ __global__ void __launch_bounds__((P4_CW + 1) * 32) k_pileup4(RegionDev R, const
                 if (slo + lane < shi) next = segs[slo + lane];
                 uint32_t sb = slo;
                 while (sb < shi && alive) {
+                    mark(0, n);
                     Seg mine = next;
                     next = none;
                     if (sb + 32 + lane < shi) next = segs[sb + 32 + lane];       // prefetch the next chunk's descriptors
                     const uint32_t slot = n % P4_NS;
+                    if (mine.len == 0x7fffffff) mark(99, n);                    // (forces the descriptor load to complete before mark 1)
+                    mark(1, n);
                     alive = acquire(slot);
                     if (!alive) break;
+                    mark(2, n);
                     Slot4& SL = S.slot[slot];
                     // clip to the tile
                     const int a = mine.loc0 > t0 ? mine.loc0 : t0;
@@ -152,6 +174,7 @@ __global__ void __launch_bounds__((P4_CW + 1) * 32) k_pileup4(RegionDev R, const
                             mbar_arrive(&S.full[slot]);
                         }
                     } else mbar_arrive(&S.full[slot]);
+                    mark(3, n);
                     n++;
                     sb += take;
                     if (take != 32) { next = none; if (sb + lane < shi) next = segs[sb + lane]; }
@@ -170,14 +193,14 @@ __global__ void __launch_bounds__((P4_CW + 1) * 32) k_pileup4(RegionDev R, const
     const int64_t w = (int64_t)blockIdx.x * P4_CW + cw;
     const bool active = w < R.n_win;
     const int32_t w0 = t0 + wc;
-    Warp3& W = S.warp[cw];
+    Warp4& W = S.warp[cw];
     const int g = lane >> 3, k = lane & 7, kk = k << 2;
     const int min_qual = R.cfg.min_qual;
     const uint32_t defq = (uint32_t)R.cfg.default_qual;
     const uint32_t minq_add = (uint32_t)(0x80 - (min_qual > 128 ? 128 : min_qual)) * 0x01010101u;
 
 #pragma unroll
-    for (int b = 0; b < 4; b++) { W.tqs[lane][b] = 0; W.tcnt[lane][b] = 0; }
+    for (int b = 0; b < 4; b++) { W.tqs64[lane][b] = 0; W.tqs[lane][b] = 0; W.tcnt[lane][b] = 0; }
     W.tmq[lane] = 0; W.tq[lane] = 0; W.tbp[lane] = 0;
     const uint32_t pre_rb = active ? R.rare_bits[w] : 0u;
     const uint8_t pre_ref = (active && (int64_t)w0 + lane < R.size) ? ref_at(R, (int64_t)R.start + w0 + lane) : (uint8_t)'N';
@@ -191,8 +214,15 @@ __global__ void __launch_bounds__((P4_CW + 1) * 32) k_pileup4(RegionDev R, const
     }
     __syncwarp();
 
-    uint32_t cnt4 = 0, QLo = 0, QHi = 0, cur_mq = 0, nrows = 0, fragN = 0, nprev = 0;
+    uint32_t cnt4 = 0, QLo = 0, QHi = 0, cur_mq = 0, nrows = 0, fragN = 0, nprev = 0, rows_total = 0;
 
+    auto spill = [&]() {       // fold the 32-bit quality sums into the 64-bit table (lane <-> locus)
+        __syncwarp();
+#pragma unroll
+        for (int b = 0; b < 4; b++) { W.tqs64[lane][b] += W.tqs[lane][b]; W.tqs[lane][b] = 0; }
+        __syncwarp();
+        rows_total = 0;
+    };
     auto flush = [&]() {       // warp-uniform: reduce the 4 row groups with shuffles, then lane (g,k) owns locus 4k+g
         if (__any_sync(FULL, cnt4 != 0)) {
             uint32_t c02 = cnt4 & 0x00FF00FFu, c13 = (cnt4 >> 8) & 0x00FF00FFu;
@@ -209,7 +239,7 @@ __global__ void __launch_bounds__((P4_CW + 1) * 32) k_pileup4(RegionDev R, const
             if (cj) {
                 const int l = kk + g; const uint32_t letter = (P8 >> (2 * g)) & 3;
                 W.tcnt[l][letter] += cj;
-                W.tqs[l][letter] += (unsigned long long)Qj * cur_mq;
+                W.tqs[l][letter] += Qj * cur_mq;            // <= 1020 rows * 127 * 256 per flush
                 W.tmq[l] += cj * cur_mq;
                 W.tq[l] += Qj;
             }
@@ -220,7 +250,9 @@ __global__ void __launch_bounds__((P4_CW + 1) * 32) k_pileup4(RegionDev R, const
 
     for (uint32_t n = 0;; n++) {
         const uint32_t slot = n % P4_NS;
+        mark(4, n);
         if (!mbar_wait(&S.full[slot], (n / P4_NS) & 1, err)) return;
+        mark(5, n);
         Slot4& SL = S.slot[slot];
         const Chunk4 ch = SL.ch;
         if (ch.type == CH_EOT) break;
@@ -255,17 +287,22 @@ __global__ void __launch_bounds__((P4_CW + 1) * 32) k_pileup4(RegionDev R, const
                 const uint32_t sft = (uint32_t)cbw & 31;
                 W.codes[lane] = ((unsigned long long)__funnelshift_r(W1, W2, sft) << 32) | __funnelshift_r(W0, W1, sft);
             }
-            // dominant (adjMq + 1) among this window's eligible rows; keep the current one on ties
+            // dominant (adjMq + 1) among this window's eligible rows; voted only when some row disagrees
             const bool elig = ov && valid && hasq;
-            const unsigned peers = __match_any_sync(FULL, elig ? mq1 : (0x10000u + lane));
-            const uint32_t votes = elig ? (((uint32_t)__popc(peers) << 17) | ((mq1 == cur_mq) ? 0x10000u : 0u) | mq1) : 0u;
-            const uint32_t best = __reduce_max_sync(FULL, votes);
-            if (best && (best & 0xFFFF) != cur_mq) { flush(); cur_mq = best & 0xFFFF; }
+            if (__any_sync(FULL, elig && mq1 != cur_mq)) {
+                const unsigned peers = __match_any_sync(FULL, elig ? mq1 : (0x10000u + lane));
+                const uint32_t votes = elig ? (((uint32_t)__popc(peers) << 17) | ((mq1 == cur_mq) ? 0x10000u : 0u) | mq1) : 0u;
+                const uint32_t best = __reduce_max_sync(FULL, votes);
+                if (best && (best & 0xFFFF) != cur_mq) { flush(); cur_mq = best & 0xFFFF; }
+            }
             const bool fast = elig && mq1 == cur_mq;
             const unsigned fastm = __ballot_sync(FULL, fast);
             unsigned scalm = __ballot_sync(FULL, ov && !fast);
+            rows_total += 32;
+            if (rows_total > P4_SPILL_ROWS) { flush(); spill(); }
             const uint32_t cm_fast = fast ? colmask : 0u;
             __syncwarp();
+            mark(10, (uint32_t)__popc(scalm));
             // ---- odd rows: lane <-> locus ----
             while (scalm) {
                 const int j = __ffs(scalm) - 1; scalm &= scalm - 1;
@@ -273,7 +310,7 @@ __global__ void __launch_bounds__((P4_CW + 1) * 32) k_pileup4(RegionDev R, const
                 const uint32_t swj = __shfl_sync(FULL, sg.w, j);
                 const int32_t qb = __shfl_sync(FULL, qaddr, j);
                 if ((cmj >> lane) & 1) {
-                    if (!(swj & SEG_VALID)) W.tbp[lane] += 1;                     // PileUpRegion.scala:45
+                    if (!(swj & SEG_VALID)) atomicAdd(&W.tbp[lane], 1u);           // PileUpRegion.scala:45
                     else {
                         uint32_t qv;
                         asm volatile("ld.shared.u8 %0, [%1];" : "=r"(qv) : "r"((uint32_t)(qb + lane)));
@@ -282,65 +319,84 @@ __global__ void __launch_bounds__((P4_CW + 1) * 32) k_pileup4(RegionDev R, const
                             const uint32_t q = (swj & SEG_HASQ) ? qv : defq;
                             if (!MINQ || (int)q >= min_qual) {
                                 const uint32_t m1 = swj & 0xFFFF;
-                                W.tcnt[lane][code] += 1; W.tqs[lane][code] += (unsigned long long)(q * m1);
-                                W.tmq[lane] += m1; W.tq[lane] += q;
+                                atomicAdd(&W.tcnt[lane][code], 1u); atomicAdd(&W.tqs[lane][code], q * m1);
+                                atomicAdd(&W.tmq[lane], m1); atomicAdd(&W.tq[lane], q);
                             }
                         }
                     }
                 }
             }
             // ---- fast rows: 4 rows per step (one per lane group), 4 loci per lane ----
+            mark(11, (uint32_t)__popc(fastm));
             if (fastm) {
                 const int r_lo = __ffs(fastm) - 1, r_hi = 32 - __clz(fastm);
                 const int iters = (r_hi - r_lo + 3) >> 2;
+                mark(12, (uint32_t)iters);
                 if (nrows + (uint32_t)iters > 255) flush();
                 nrows += (uint32_t)iters;
-                for (int it = 0, r = r_lo + g; it < iters; it++, r += 4) {
-                    const uint32_t cm = __shfl_sync(FULL, cm_fast, r & 31);
-                    const int32_t qb = __shfl_sync(FULL, qaddr, r & 31);
-                    const uint32_t in4 = r < r_hi ? ((((cm >> kk) & 15u) * 0x00204081u) & 0x01010101u) : 0u;
-                    const uint32_t a = (uint32_t)(qb + kk);
-                    uint32_t wlo, whi;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wlo) : "r"(a & ~3u));
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(whi) : "r"((a & ~3u) + 4));
-                    const uint32_t Q4 = __funnelshift_r(wlo, whi, (a & 3) << 3);
-                    const uint32_t C8 = reinterpret_cast<const uint8_t*>(&W.codes[r & 31])[k];
-                    const uint32_t X = C8 ^ P8;
-                    const uint32_t mis4 = (((X | (X >> 1)) & 0x55u) * 0x00041041u) & 0x01010101u;
-                    uint32_t val4 = (~Q4 >> 7) & 0x01010101u;
-                    if (MINQ) val4 &= (((Q4 & 0x7F7F7F7Fu) + minq_add) >> 7);
-                    const uint32_t act4 = val4 & in4;
-                    const uint32_t mat4 = act4 & ~mis4;
-                    const uint32_t mm4 = act4 & mis4;
-                    if (mm4) {                                   // bases that differ from the primary letter: exact, direct
+                // 4 independent rows per lane per trip: all shuffles, then all loads, then the arithmetic,
+                // so that the latencies of the four chains overlap (the single chain was ~400 cycles long)
+                for (int it0 = 0; it0 < iters; it0 += 4) {
+                    uint32_t cm[4], wlo[4], whi[4], sh[4], C8[4];
+                    int32_t qb[4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            if ((mm4 >> (8 * j)) & 1) {
-                                const uint32_t q = (Q4 >> (8 * j)) & 0x7F, letter = (C8 >> (2 * j)) & 3;
-                                const int l = kk + j;
-                                atomicAdd(&W.tcnt[l][letter], 1u);
-                                atomicAdd(&W.tqs[l][letter], (unsigned long long)(q * cur_mq));
-                                atomicAdd(&W.tmq[l], cur_mq);
-                                atomicAdd(&W.tq[l], q);
-                            }
-                        }
+                    for (int u = 0; u < 4; u++) {
+                        const int r = r_lo + g + 4 * (it0 + u);
+                        cm[u] = __shfl_sync(FULL, cm_fast, r & 31);
+                        qb[u] = __shfl_sync(FULL, qaddr, r & 31);
+                        if (r >= r_hi) cm[u] = 0;
                     }
-                    const uint32_t Qm = Q4 & (mat4 * 0xFFu);
-                    cnt4 += mat4;
-                    QLo += Qm & 0x00FF00FFu;
-                    QHi += (Qm >> 8) & 0x00FF00FFu;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int r = r_lo + g + 4 * (it0 + u);
+                        const uint32_t a = (uint32_t)(qb[u] + kk);
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wlo[u]) : "r"(a & ~3u));
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(whi[u]) : "r"((a & ~3u) + 4));
+                        sh[u] = (a & 3) << 3;
+                        C8[u] = reinterpret_cast<const uint8_t*>(&W.codes[r & 31])[k];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t in4 = (((cm[u] >> kk) & 15u) * 0x00204081u) & 0x01010101u;
+                        const uint32_t Q4 = __funnelshift_r(wlo[u], whi[u], sh[u]);
+                        const uint32_t X = C8[u] ^ P8;
+                        const uint32_t mis4 = (((X | (X >> 1)) & 0x55u) * 0x00041041u) & 0x01010101u;
+                        uint32_t val4 = (~Q4 >> 7) & 0x01010101u;
+                        if (MINQ) val4 &= (((Q4 & 0x7F7F7F7Fu) + minq_add) >> 7);
+                        const uint32_t act4 = val4 & in4;
+                        const uint32_t mat4 = act4 & ~mis4;
+                        uint32_t mm4 = act4 & mis4;
+                        while (mm4) {                            // bases that differ from the primary letter: exact, direct
+                            const int j = (__ffs(mm4) - 1) >> 3; mm4 &= mm4 - 1;
+                            const uint32_t q = (Q4 >> (8 * j)) & 0x7F, letter = (C8[u] >> (2 * j)) & 3;
+                            const int l = kk + j;
+                            atomicAdd(&W.tcnt[l][letter], 1u);
+                            atomicAdd(&W.tqs[l][letter], q * cur_mq);
+                            atomicAdd(&W.tmq[l], cur_mq);
+                            atomicAdd(&W.tq[l], q);
+                        }
+                        const uint32_t Qm = Q4 & (mat4 * 0xFFu);
+                        cnt4 += mat4;
+                        QLo += Qm & 0x00FF00FFu;
+                        QHi += (Qm >> 8) & 0x00FF00FFu;
+                    }
                 }
             }
         }
         __syncwarp();
+        mark(6, n);
         if (lane == 0) mbar_arrive(&S.empty[slot]);
     }
     if (!active) return;
+    mark(7, 0);
     flush();
     uint32_t c[4]; uint64_t q[4];
 #pragma unroll
-    for (int b = 0; b < 4; b++) { c[b] = W.tcnt[lane][b]; q[b] = W.tqs[lane][b]; }
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b < 4; b++) { c[b] = W.tcnt[lane][b]; q[b] = W.tqs64[lane][b] + W.tqs[lane][b]; }
     finish_locus(R, w, lane, w0 + lane, c, q, W.tmq[lane], W.tq[lane], W.tbp[lane], fragN, pre_rb, pre_ref);
+    mark(8, 0);
 }
 
 }  // namespace pb
