@@ -277,13 +277,23 @@ def run_gpu_arm(args):
         engines.append(e)
     torch.cuda.synchronize()
 
-    def step():
+    # (a) the kernels one region at a time: per-kernel numbers for the roofline (pileup kernel timed alone)
+    def step_sequential():
         tot = pil = 0.0
         launches = 0
         for e in engines:
             a, p, n = e.compute_timed(1)
             tot += a; pil += p; launches += n
         return tot, pil, launches
+
+    # (b) the job: every region's pass launched from a small pool of host threads onto the engines' own
+    # streams, so that the short kernels of one region overlap the long kernels of another
+    streams = [torch.cuda.ExternalStream(e.stream_ptr(), device=dev) for e in engines]
+    order = sorted(range(len(engines)), key=lambda i: -regions[i].aligned)
+    pool = ThreadPoolExecutor(args.host_threads)
+
+    def step_concurrent():
+        list(pool.map(lambda i: engines[i].compute(), order))
 
     def barrier():
         torch.cuda.synchronize()
@@ -292,20 +302,33 @@ def run_gpu_arm(args):
             torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        step()
+        step_sequential()
+        step_concurrent()
+    barrier()
+    seq_ms = pil_ms = 0.0
+    launches = 0
+    for _ in range(args.steps):
+        a, p, n = step_sequential()
+        seq_ms += a; pil_ms += p; launches += n
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
     wall0 = time.perf_counter()
-    dev_ms = pil_ms = 0.0
-    launches = 0
+    ev_start = torch.cuda.Event(enable_timing=True)
+    ev_start.record(streams[0])
     for _ in range(args.steps):
-        a, p, n = step()
-        dev_ms += a; pil_ms += p; launches += n
+        step_concurrent()
+    ends = []
+    for st in streams:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(st)
+        ends.append(ev)
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - wall0)
+    dev_ms = max(ev_start.elapsed_time(ev) for ev in ends)       # device clock: first launch -> last stream done
     clocks = sampler.stop() if rank == 0 else None
+    pool.shutdown()
 
     # ---- end-to-end arm: host buffers -> C ABI -> host results -------------------------------
     for e in engines:
@@ -367,12 +390,12 @@ def run_gpu_arm(args):
         eng.close()
 
     # ---- aggregate over ranks -----------------------------------------------------------------
-    vals = torch.tensor([dev_ms / args.steps, pil_ms / args.steps, wall_ms / args.steps, e2e_s], dtype=torch.float64, device=dev)
+    vals = torch.tensor([dev_ms / args.steps, pil_ms / args.steps, wall_ms / args.steps, e2e_s, seq_ms / args.steps], dtype=torch.float64, device=dev)
     sums = torch.tensor([float(total_aligned), float(launches), float(h2d), float(d2h)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    step_ms, pileup_ms, wall_step_ms, e2e_sec = [float(x) for x in vals.tolist()]
+    step_ms, pileup_ms, wall_step_ms, e2e_sec, seq_step_ms = [float(x) for x in vals.tolist()]
     job_aligned, job_launches, job_h2d, job_d2h = [float(x) for x in sums.tolist()]
 
     if rank == 0:
@@ -395,16 +418,17 @@ def run_gpu_arm(args):
                "config": {"workload": "%s: %s" % (wl.name, wl.description), "scale": args.scale,
                           "regions_per_gpu": len(regions), "loci_per_gpu": total_loci, "reads_per_gpu": sum(r.n_reads for r in regions),
                           "aligned_bases_per_gpu": total_aligned, "mean_depth": depth, "l2": "inputs_exceed_l2 (%.1f GB per step)" % (h2d / 1e9),
-                          "timing": "sum of per-region CUDA-event intervals on the engine streams; wall_ms_per_step is the host clock around the same steps",
+                          "timing": "CUDA events: first launch of the timed steps -> last engine stream done, regions launched by %d host threads onto one stream per region; "
+                                    "sequential_ms_per_step = sum of per-region event intervals with one region at a time (the pileup kernel's launches are timed in that pass)" % args.host_threads,
                           "e2e_planes": args.planes},
-               "wall_ms_per_step": wall_step_ms,
+               "wall_ms_per_step": wall_step_ms, "sequential_ms_per_step": seq_step_ms,
                "e2e": {"value": job_aligned / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": job_h2d, "d2h_bytes_per_step": job_d2h,
                        "ms_per_step": 1e3 * e2e_sec, "streams_per_gpu": n_workers},
                "gpu_launches": int(job_launches),
                "roofline": {"bound": "hbm", "kernel": "k_pileup", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                             "algorithmic_bytes_per_base": alg / total_aligned,
-                            "pileup_ms_per_step": pileup_ms, "pileup_share_of_step": pileup_ms / step_ms},
+                            "pileup_ms_per_step": pileup_ms, "pileup_share_of_sequential_step": pileup_ms / seq_step_ms},
                "cpu_baseline": cpu, "clocks": clocks}
         print(json.dumps(out))
     if world > 1:
@@ -421,6 +445,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrinks the genome (not the depth); 1.0 = the BASELINE config")
     ap.add_argument("--planes", default="fix", choices=["fix", "vcf"], help="per-locus results copied back in the e2e arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-threads", type=int, default=4, help="host threads feeding region passes to the GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -225,6 +225,12 @@ int pb_region_finish(pb_engine* e, pb_region_result* res, int32_t* const* insert
 int pb_region_compute_timed(pb_engine* e, int iters, float* total_ms, float* pileup_ms,
                             int64_t* launches);
 
+/* Same compute pass, launched on the engine's stream without timing and without waiting for it to
+ * finish (one short internal wait for an 8 KB scalar read-back remains): lets a caller keep several
+ * engines -- one per host thread -- busy on one GPU so that the small kernels of one region overlap
+ * the large kernels of another.  Synchronise the stream (pb_stream) before reading anything. */
+int pb_region_compute(pb_engine* e);
+
 /* Raw CUDA stream handle (cudaStream_t) so callers can order their own copies against the engine. */
 int pb_stream(pb_engine* e, void** stream_out);
 

@@ -94,6 +94,7 @@ def load_library() -> C.CDLL:
     lib.pb_region_finish.argtypes = [vp, C.POINTER(pb_region_result), vp]
     lib.pb_region_compute_timed.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                             C.POINTER(i64)]
+    lib.pb_region_compute.argtypes = [vp]
     lib.pb_stream.argtypes = [vp, C.POINTER(vp)]
     lib.pb_packer_create.argtypes = [C.POINTER(vp)]
     lib.pb_packer_destroy.argtypes = [vp]
@@ -102,7 +103,7 @@ def load_library() -> C.CDLL:
     lib.pb_packer_add_many.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.pb_packer_view.argtypes = [vp, C.POINTER(pb_batch)]
     for name in ("pb_device_count", "pb_create", "pb_destroy", "pb_region_begin", "pb_region_add_batch",
-                 "pb_region_finish", "pb_region_compute_timed", "pb_stream", "pb_packer_create",
+                 "pb_region_finish", "pb_region_compute_timed", "pb_region_compute", "pb_stream", "pb_packer_create",
                  "pb_packer_destroy", "pb_packer_reset", "pb_packer_add", "pb_packer_add_many",
                  "pb_packer_view"):
         getattr(lib, name).restype = C.c_int

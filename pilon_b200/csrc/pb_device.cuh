@@ -79,7 +79,7 @@ struct Scalars {
     int read_count;
     int phys_cov_start, insert_size_start;   // PileUpRegion.scala:59-60
     int unknown_ops, dropped_oob;
-    unsigned n_events, n_groups, n_cand;
+    unsigned n_events, n_groups, n_cand, n_work;
     int error;
     int min_depth;
 };
@@ -109,6 +109,7 @@ struct RegionDev {
     EventKey* ev_key; Event* ev; uint32_t ev_cap;
     Group* groups; uint32_t groups_cap;
     uint8_t* str_pool; uint64_t str_cap;
+    int4* work;  uint32_t work_cap;     // trusted in-region I / D ops queued by k_prep for k_indel: (read, op slot, readOffset | batch << 24, locus)
     int4* cand;  uint32_t cand_cap;     // unordered pass-1 DEL candidates: (locus index, deletions, length, -)
     ScalarSlot* slots;                  // [SC_SLOTS] k_prep partial sums
     int32_t exp_flags;                  // PB_EXP timing experiments (results invalid): 1 skip epilogue, 2 skip compute, 4 skip staging copies

@@ -71,7 +71,7 @@ struct pb_engine {
     DBuf ref, rare, gplane[2], rare_bits, pc_diff, block_sums, scalars;
     DBuf o_cnt, o_qs, o_i32[12], o_wq, o_wmq, o_flags, o_call;
     // event buffers
-    DBuf ev_key, ev, perm, groups, cand, spill_scratch, str_pool, cub_tmp, dbg;
+    DBuf ev_key, ev, perm, groups, cand, work, spill_scratch, str_pool, cub_tmp, dbg;
     Scalars* h_sc = nullptr;         // pinned
     int64_t launches = 0;
     float last_pileup_ms = 0.f;
@@ -133,7 +133,7 @@ extern "C" int pb_destroy(pb_engine* e) {
     cudaStreamSynchronize(e->stream);
     DBuf* all[] = {&e->d_batches, &e->ref, &e->rare_bits, &e->pc_diff, &e->block_sums, &e->scalars,
                    &e->o_cnt, &e->o_qs, &e->o_wq, &e->o_wmq, &e->o_flags, &e->o_call, &e->ev_key, &e->ev, &e->perm,
-                   &e->groups, &e->cand, &e->spill_scratch, &e->str_pool, &e->cub_tmp};
+                   &e->groups, &e->cand, &e->work, &e->dbg, &e->spill_scratch, &e->str_pool, &e->cub_tmp};
     for (DBuf* b : all) b->release();
     e->rare.release(); for (auto& b : e->gplane) b.release();
     for (auto& b : e->o_i32) b.release();
@@ -258,9 +258,11 @@ static int compute(pb_engine* e, bool time_pileup) {
     CK(e->perm.ensure((size_t)cap * 4 + 16, false, s));
     CK(e->groups.ensure((size_t)cap * sizeof(Group) + 16, false, s));
     CK(e->cand.ensure((size_t)cap * sizeof(int4) + 16, false, s));
+    CK(e->work.ensure((size_t)cap * sizeof(int4) + 16, false, s));
     R.ev_key = e->ev_key.as<EventKey>(); R.ev = e->ev.as<Event>(); R.ev_cap = cap;
     R.groups = e->groups.as<Group>(); R.groups_cap = cap;
     R.cand = e->cand.as<int4>(); R.cand_cap = cap;
+    R.work = e->work.as<int4>(); R.work_cap = cap;
     R.str_pool = e->str_pool.as<uint8_t>(); R.str_cap = e->str_pool.cap;
     std::vector<DevBatch> img(nb);
     for (int i = 0; i < nb; i++) img[i] = e->batches[i].d;
@@ -282,6 +284,7 @@ static int compute(pb_engine* e, bool time_pileup) {
             k_index<<<(unsigned)((d.n_reads + 255) / 256), 256, 0, s>>>(R, d);
             e->launches += 2;
         }
+        if (i1 == nb) { k_indel<<<148 * 4, 128, 0, s>>>(R, dB); e->launches++; }     // queued I / D ops of every batch
         k_fold<<<1, 32, 0, s>>>(R, reach_base + 2 * i0, i1 - i0, i1 == nb); e->launches++;
     }
     CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, SC_REACH_OFF + 8 * (size_t)nb, cudaMemcpyDeviceToHost, s));
@@ -295,6 +298,7 @@ static int compute(pb_engine* e, bool time_pileup) {
     CK(cudaEventSynchronize(e->ev_sc));
     if (e->h_sc->error & 1) return fail(PB_ERR_UNSORTED, "a batch is not sorted by pos");
     if (e->h_sc->error & 8) return fail(PB_ERR_CUDA, "pipeline barrier timed out (internal protocol error)");
+    if (e->h_sc->error & 16) return fail(PB_ERR_UNSUPPORTED, "read longer than 2^24 bases or more than 256 batches in a region");
     if (e->h_sc->error) return fail(PB_ERR_CUDA, "internal capacity error in k_prep");
     const uint32_t n_ev = e->h_sc->n_events;
     R.read_count = e->h_sc->read_count; R.min_depth = e->h_sc->min_depth;
@@ -368,6 +372,17 @@ static int compute(pb_engine* e, bool time_pileup) {
     CK(e->spill_scratch.ensure((size_t)p2 * sizeof(int4) + 16, false, s));
     if (n_ev) { k_spill<<<1, 1024, 2048 * sizeof(int4), s>>>(R, e->spill_scratch.as<int4>(), p2); e->launches++; }
     CK(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_region_compute(pb_engine* e) {
+    if (!e || !e->in_region) return fail(PB_ERR_INVALID, "no region");
+    CK(cudaSetDevice(e->device));
+    int rc = compute(e, false);
+    if (rc != PB_OK) return rc;
+    // the group count is only known on the device here: clear through the whole capacity-bounded list
+    k_groups_clear_dev<<<64, 128, 0, e->stream>>>(e->R); e->launches++;
+    e->dirty = false;
     return PB_OK;
 }
 

@@ -54,7 +54,7 @@ __device__ __forceinline__ uint64_t fnv64(uint64_t h, uint8_t b) { return (h ^ b
 __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t batch_id) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long bc = 0, aligned = 0;
-    int rc = 0, unk = 0, drop = 0, fwd = 0, back = 0;
+    int rc = 0, unk = 0, fwd = 0, back = 0;
     if (r < B.n_reads) {
         const Cfg& cfg = R.cfg;
         const int32_t length = B.read_len[r];
@@ -77,7 +77,6 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
         }
         const int32_t aEnd = (fl & PB_F_UNMAPPED) ? 0 : wrap32((int64_t)aStart + reflen - 1);    // getAlignmentEnd
         const int32_t adjMq = roundDivI(wrap32((int64_t)mq * (length - clipped)), length);       // :141
-        const int32_t indelMq = adjMq;                                                           // :142 (longRead == 0)
         const uint32_t segw = (uint32_t)((adjMq + 1) & 0xFFFF) | (hasq ? SEG_HASQ : 0u);
         const int64_t tlo = flank, thi = (int64_t)length - flank;      // trusted read offsets [tlo, thi)  :118
         int64_t readOffset = 0, refOffset = 0;
@@ -106,9 +105,94 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
                 const int64_t l0 = clipStart > R.start ? clipStart : R.start;
                 const int64_t l1 = clipEnd < R.stop ? clipEnd : R.stop;
                 if (l1 >= l0) { sg.loc0 = (int32_t)(l0 - R.start); sg.len = (int32_t)(l1 - l0 + 1); sg.w = 0; }   // badPair++ each
-            } else if (op == 1) {                                                                // I  :150-162
+            } else if (op == 1 || op == 2) {                                                     // I, D  :150-183
+                // the rare, divergent part (left shift, exception look-ups, event records) runs in k_indel, one
+                // thread per op, so that it does not hold 31 idle lanes hostage here
+                const bool inr = op == 1 ? (locus >= R.start && locus <= R.stop && len > 0)
+                                         : (locus >= R.start && locus <= R.stop && locus + len - 1 >= R.start && locus + len - 1 <= R.stop);
+                if (valid && readOffset >= tlo && readOffset < thi && inr) {
+                    if (readOffset >= (1 << 24) || batch_id >= 256) atomicOr(&R.sc->error, 16);
+                    const uint32_t wi = atomicAdd(&R.sc->n_work, 1u);
+                    if (wi < R.work_cap) R.work[wi] = make_int4((int)r, (int)k, (int)(readOffset & 0xFFFFFF) | (int)(batch_id << 24), (int)locus);
+                    else atomicOr(&R.sc->error, 2);
+                }
+            } else if (op == 5 || op == 3) {                                                     // H, N  :207-210
+            } else unk++;                                                                        // :211-212
+            if (sg.len > 0) {
+                const int64_t f = (int64_t)R.start + sg.loc0 + sg.len - aStart;    // exclusive end relative to pos
+                const int64_t bk = (int64_t)aStart - (R.start + sg.loc0);
+                if (f > fwd) fwd = (int)(f > 0x3fffffff ? 0x3fffffff : f);
+                if (bk > back) back = (int)(bk > 0x3fffffff ? 0x3fffffff : bk);
+            }
+            B.seg[k] = sg;
+            if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) readOffset += len;          // :214
+            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) refOffset += len;           // :215
+        }
+        rc = 1;                                                                                  // :218
+        // physCovIncr, PileUpRegion.scala:62-88
+        int32_t ins = 0;
+        if (valid && !(paired && B.tlen[r] <= 0)) {
+            int64_t s, e;
+            if (!paired) { s = aStart < aEnd ? aStart : aEnd; e = aStart > aEnd ? aStart : aEnd; }
+            else { s = aStart; e = (int64_t)aStart + B.tlen[r]; }
+            ins = wrap32(e - s); s = wrap32(s); e = wrap32(e);
+            if (s >= R.start && s <= R.stop) { atomicAdd(&R.pc_diff[s - R.start].x, 1); atomicAdd(&R.pc_diff[s - R.start].y, ins); }
+            else if (s < R.start && !(e < R.start)) { atomicAdd(&R.sc->phys_cov_start, 1); atomicAdd(&R.sc->insert_size_start, ins); }
+            if (e >= R.start && e <= R.stop) { atomicAdd(&R.pc_diff[e - R.start].x, -1); atomicAdd(&R.pc_diff[e - R.start].y, -ins); }
+        }
+        B.insert_out[r] = ins;
+    }
+    // warp-aggregate the region scalars, then one atomic per quantity per warp into one of SC_SLOTS slots
+    // (same-address L2 atomics serialise; a block-level reduction would make every warp wait for the slowest)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bc += __shfl_xor_sync(FULL, bc, o); aligned += __shfl_xor_sync(FULL, aligned, o);
+        rc += __shfl_xor_sync(FULL, rc, o); unk += __shfl_xor_sync(FULL, unk, o);
+        fwd = max(fwd, __shfl_xor_sync(FULL, fwd, o)); back = max(back, __shfl_xor_sync(FULL, back, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        ScalarSlot* sl = &R.slots[(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (SC_SLOTS - 1)];
+        if (bc) atomicAdd(&sl->base_count, bc);
+        if (aligned) atomicAdd(&sl->aligned_bases, aligned);
+        if (rc) atomicAdd(&sl->read_count, rc);
+        if (unk) atomicAdd(&sl->unknown_ops, unk);
+        if (fwd > sl->fwd[batch_id & 7]) atomicMax(&sl->fwd[batch_id & 7], fwd);
+        if (back > sl->back[batch_id & 7]) atomicMax(&sl->back[batch_id & 7], back);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_indel: one thread per trusted, in-region insertion / deletion op recorded by k_prep
+// (PileUpRegion.scala:150-183): left shift, PileUp.addInsertion / addDeletion, the deletion's re-added
+// bases (as the segment of the D op's own slot) and the event record for the majority vote.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_indel(RegionDev R, const DevBatch* __restrict__ batches) {
+    const uint32_t n_work = min(R.sc->n_work, R.work_cap);
+    unsigned long long bc = 0; int drop = 0;
+    for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n_work; wi += gridDim.x * blockDim.x) {
+        const int4 it = R.work[wi];
+        const int64_t r = it.x; const uint32_t k = (uint32_t)it.y;
+        const uint32_t batch_id = (uint32_t)it.z >> 24;
+        const int64_t readOffset = it.z & 0xFFFFFF, locus = it.w;
+        const DevBatch& B = batches[batch_id];
+        const Cfg& cfg = R.cfg;
+        const int32_t length = B.read_len[r];
+        const int mq = B.mapq[r];
+        const bool hasq = B.flags[r] & PB_F_HAS_QUALS;
+        const int32_t aStart = B.pos[r];
+        const uint32_t c0 = B.cigar_off[r], c1 = B.cigar_off[r + 1];
+        const uint32_t seq0 = B.seq_off[r];
+        int64_t clipped = 0;
+        for (uint32_t kk = c0; kk < c1; kk++) { const uint32_t e = B.cigar[kk]; if ((e & 15) == 4) clipped += e >> 4; }
+        const int32_t adjMq = roundDivI(wrap32((int64_t)mq * (length - clipped)), length);       // :141
+        const int32_t indelMq = adjMq;                                                           // :142 (longRead == 0)
+        const uint32_t segw = (uint32_t)((adjMq + 1) & 0xFFFF) | (hasq ? SEG_HASQ : 0u);
+        const int64_t tlo = cfg.flank, thi = (int64_t)length - cfg.flank;
+        const uint32_t e = B.cigar[k]; const int op = e & 15; const int64_t len = e >> 4;
+        Seg sg; sg.loc0 = 0; sg.len = 0; sg.src = 0; sg.w = 0;
+        if (op == 1) {                                                                // I  :150-162
                 int64_t iloc = locus;
-                if (valid && readOffset >= tlo && readOffset < thi && iloc >= R.start && iloc <= R.stop && len > 0) {
+                {
                     const uint32_t src = seq0 + (uint32_t)readOffset;
                     int64_t j = len - 1; uint32_t rot = 0; bool dropped = false;
                     while (iloc > 1) {
@@ -150,8 +234,7 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
                 }
             } else if (op == 2) {                                                                // D  :163-183
                 int64_t dloc = locus, rloc = readOffset;
-                if (valid && readOffset >= tlo && readOffset < thi && dloc >= R.start && dloc <= R.stop &&
-                    dloc + len - 1 >= R.start && dloc + len - 1 <= R.stop) {
+                {
                     bool dropped = false;
                     while (dloc > 1 && rloc > 0 && ref_at(R, dloc - 1) == ref_at(R, dloc + len - 1)) {   // refBases(dloc-2) == refBases(dloc+len-2)
                         dloc -= 1; rloc -= 1;
@@ -184,64 +267,17 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
                         } else atomicOr(&R.sc->error, 2);
                     }
                 }
-            } else if (op == 5 || op == 3) {                                                     // H, N  :207-210
-            } else unk++;                                                                        // :211-212
-            if (sg.len > 0) {
-                const int64_t f = (int64_t)R.start + sg.loc0 + sg.len - aStart;    // exclusive end relative to pos
-                const int64_t bk = (int64_t)aStart - (R.start + sg.loc0);
-                if (f > fwd) fwd = (int)(f > 0x3fffffff ? 0x3fffffff : f);
-                if (bk > back) back = (int)(bk > 0x3fffffff ? 0x3fffffff : bk);
             }
+        if (sg.len > 0) {
             B.seg[k] = sg;
-            if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) readOffset += len;          // :214
-            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) refOffset += len;           // :215
+            const int64_t f = (int64_t)R.start + sg.loc0 + sg.len - aStart;
+            const int fi = (int)(f > 0x3fffffff ? 0x3fffffff : f);
+            if (fi > B.reach[0]) atomicMax(&B.reach[0], fi);     // (never beyond the read's own aligned span in practice)
         }
-        rc = 1;                                                                                  // :218
-        // physCovIncr, PileUpRegion.scala:62-88
-        int32_t ins = 0;
-        if (valid && !(paired && B.tlen[r] <= 0)) {
-            int64_t s, e;
-            if (!paired) { s = aStart < aEnd ? aStart : aEnd; e = aStart > aEnd ? aStart : aEnd; }
-            else { s = aStart; e = (int64_t)aStart + B.tlen[r]; }
-            ins = wrap32(e - s); s = wrap32(s); e = wrap32(e);
-            if (s >= R.start && s <= R.stop) { atomicAdd(&R.pc_diff[s - R.start].x, 1); atomicAdd(&R.pc_diff[s - R.start].y, ins); }
-            else if (s < R.start && !(e < R.start)) { atomicAdd(&R.sc->phys_cov_start, 1); atomicAdd(&R.sc->insert_size_start, ins); }
-            if (e >= R.start && e <= R.stop) { atomicAdd(&R.pc_diff[e - R.start].x, -1); atomicAdd(&R.pc_diff[e - R.start].y, -ins); }
-        }
-        B.insert_out[r] = ins;
     }
-    // block-aggregate the region scalars: shuffle within the warp, shared memory across warps, then one
-    // global atomic per quantity per block, spread over SC_SLOTS slots (same-address L2 atomics serialise)
-    __shared__ unsigned long long s_bc, s_al;
-    __shared__ int s_rc, s_unk, s_drop, s_fwd, s_back;
-    if (threadIdx.x == 0) { s_bc = 0; s_al = 0; s_rc = 0; s_unk = 0; s_drop = 0; s_fwd = 0; s_back = 0; }
-    __syncthreads();
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        bc += __shfl_xor_sync(FULL, bc, o); aligned += __shfl_xor_sync(FULL, aligned, o);
-        rc += __shfl_xor_sync(FULL, rc, o); unk += __shfl_xor_sync(FULL, unk, o); drop += __shfl_xor_sync(FULL, drop, o);
-        fwd = max(fwd, __shfl_xor_sync(FULL, fwd, o)); back = max(back, __shfl_xor_sync(FULL, back, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (bc) atomicAdd(&s_bc, bc);
-        if (aligned) atomicAdd(&s_al, aligned);
-        if (rc) atomicAdd(&s_rc, rc);
-        if (unk) atomicAdd(&s_unk, unk);
-        if (drop) atomicAdd(&s_drop, drop);
-        if (fwd) atomicMax(&s_fwd, fwd);
-        if (back) atomicMax(&s_back, back);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        ScalarSlot* sl = &R.slots[blockIdx.x & (SC_SLOTS - 1)];
-        if (s_bc) atomicAdd(&sl->base_count, s_bc);
-        if (s_al) atomicAdd(&sl->aligned_bases, s_al);
-        if (s_rc) atomicAdd(&sl->read_count, s_rc);
-        if (s_unk) atomicAdd(&sl->unknown_ops, s_unk);
-        if (s_drop) atomicAdd(&sl->dropped_oob, s_drop);
-        if (s_fwd) atomicMax(&sl->fwd[batch_id & 7], s_fwd);     // reach is per batch: folded by k_scalars
-        if (s_back) atomicMax(&sl->back[batch_id & 7], s_back);
-    }
+    // few threads: plain atomics into the slots that the last k_fold folds
+    if (bc) atomicAdd(&R.slots[threadIdx.x & (SC_SLOTS - 1)].base_count, bc);
+    if (drop) atomicAdd(&R.slots[threadIdx.x & (SC_SLOTS - 1)].dropped_oob, drop);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -290,7 +326,7 @@ __global__ void k_fold(RegionDev R, int32_t* reach0, int nb, int last) {
         Scalars* sc = R.sc;
         sc->base_count += bc; sc->aligned_bases += al; sc->read_count += rc; sc->unknown_ops += unk; sc->dropped_oob += drop;
 #pragma unroll
-        for (int j = 0; j < 8; j++) if (j < nb) { reach0[2 * j] = fw[j]; reach0[2 * j + 1] = bk[j]; }
+        for (int j = 0; j < 8; j++) if (j < nb) { reach0[2 * j] = max(reach0[2 * j], fw[j]); reach0[2 * j + 1] = max(reach0[2 * j + 1], bk[j]); }
         if (last) {
             // region coverage and minDepth (PileUpRegion.scala:36; GenomeRegion.scala:221-224)
             const long long cov = roundDivL((long long)sc->base_count, R.size);
@@ -392,6 +428,14 @@ __global__ void __launch_bounds__(128) k_groups_clear(RegionDev R, uint32_t n_gr
     if (gi >= n_groups) return;
     const Group g = R.groups[gi];
     (g.kind == 2 ? R.r_gdel : R.r_gins)[g.loc] = 0;
+}
+
+__global__ void __launch_bounds__(128) k_groups_clear_dev(RegionDev R) {      // same, count read on the device
+    const uint32_t n = min(R.sc->n_groups, R.groups_cap);
+    for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < n; gi += gridDim.x * blockDim.x) {
+        const Group g = R.groups[gi];
+        (g.kind == 2 ? R.r_gdel : R.r_gins)[g.loc] = 0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

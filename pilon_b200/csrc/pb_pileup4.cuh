@@ -391,7 +391,6 @@ __global__ void __launch_bounds__((P4_CW + 1) * 32) k_pileup4(RegionDev R, const
     mark(7, 0);
     flush();
     uint32_t c[4]; uint64_t q[4];
-#pragma unroll
     __syncwarp();
 #pragma unroll
     for (int b = 0; b < 4; b++) { c[b] = W.tcnt[lane][b]; q[b] = W.tqs64[lane][b] + W.tqs[lane][b]; }

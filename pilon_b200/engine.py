@@ -82,6 +82,15 @@ class Engine:
         capi.check(self.lib.pb_region_compute_timed(self._h, iters, C.byref(tot), C.byref(pil), C.byref(n)))
         return tot.value, pil.value, n.value
 
+    def compute(self):
+        """Launch the compute pass on the engine's stream without waiting for it (see pb_region_compute)."""
+        capi.check(self.lib.pb_region_compute(self._h))
+
+    def stream_ptr(self) -> int:
+        p = C.c_void_p()
+        capi.check(self.lib.pb_stream(self._h, C.byref(p)))
+        return int(p.value or 0)
+
     def run_region(self, contig: bytes, start: int, stop: int, batches: Sequence[Tuple[ReadBatch, bool]],
                    planes: Optional[Sequence[str]] = None, indels_cap: int = 1 << 16,
                    bytes_cap: int = 1 << 20, pinned: bool = False):
