@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(P5_WARPS * 32, 4) k_pileup5(const RegionDev R,
         for (int j = 0; j < 4; j++) P8 |= __shfl_sync(FULL, code, kk + j) << (2 * j);
     }
     // candidate segment range of every batch (lane <-> batch): one load latency for all of them
-    uint32_t my_slo = 0, my_shi = 0;
+    uint32_t my_slo = 0, my_nseg = 0;
     if (lane < n_batches) {
         const PileBatch& Bl = PB.b[lane];
         if (Bl.flags & 2) {
@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(P5_WARPS * 32, 4) k_pileup5(const RegionDev R,
             const int64_t y = (int64_t)w0 + 32 + Bl.back;
             int64_t khi = (y + 31) >> 5; if (khi > R.n_win) khi = R.n_win;
             my_slo = x <= 0 ? 0u : Bl.win_first[x >> 5];
-            my_shi = (y > ((int64_t)R.n_win << 5)) ? Bl.n_cigar : Bl.win_first[khi];
+            const uint32_t shi = (y > ((int64_t)R.n_win << 5)) ? Bl.n_cigar : Bl.win_first[khi];
+            my_nseg = shi > my_slo ? shi - my_slo : 0u;
         }
     }
     __syncwarp();
@@ -117,186 +118,223 @@ __global__ void __launch_bounds__(P5_WARPS * 32, 4) k_pileup5(const RegionDev R,
         spilled = true; rows_total = 0;
         __syncwarp();
     };
-
-    for (int bb = 0; bb < n_batches; bb++) {
-        const uint32_t slo = __shfl_sync(FULL, my_slo, bb), shi = __shfl_sync(FULL, my_shi, bb);
-        const Seg* __restrict__ segs = PB.b[bb].seg;
-        const uint8_t* __restrict__ gquals = PB.b[bb].quals;
-        const uint8_t* __restrict__ gbases = PB.b[bb].bases2;
-        const bool bfrag = PB.b[bb].flags & 1;
-        if (!(PB.b[bb].flags & 2)) continue;
-        const int nchunks = (int)((shi - slo + 31) >> 5);
-        const Seg none = {0, 0, 0, 0};
-        Seg next = none;
-        if (slo + lane < shi) next = segs[slo + lane];
-        uint32_t dom_stage = cur_mq;        // dominant (adjMq + 1) of the chunk being staged
-
-        // ---- stage chunk c into buffer `buf`; returns (#rows, dominant mq of the chunk) ----
-        auto stage = [&](int c, int buf, uint32_t& dom_out) -> int {
-            const Seg mine = next;
-            next = none;
-            const uint32_t nx = slo + ((uint32_t)(c + 1) << 5) + lane;
-            if (nx < shi) next = segs[nx];                                  // prefetch the next chunk's descriptors
-            const bool ov = mine.len > 0 && mine.loc0 < w0 + 32 && mine.loc0 + mine.len > w0;
-            const bool valid = mine.w & SEG_VALID, hasq = mine.w & SEG_HASQ;
-            const uint32_t mq1 = mine.w & 0xFFFF;
-            const bool elig = ov && valid && hasq;
-            if (__any_sync(FULL, elig && mq1 != dom_stage)) {               // vote only when some row disagrees
-                const unsigned peers = __match_any_sync(FULL, elig ? mq1 : (0x10000u + lane));
-                const uint32_t votes = elig ? (((uint32_t)__popc(peers) << 17) | ((mq1 == dom_stage) ? 0x10000u : 0u) | mq1) : 0u;
-                const uint32_t best = __reduce_max_sync(FULL, votes);
-                if (best) dom_stage = best & 0xFFFF;
-            }
-            dom_out = dom_stage;
-            const unsigned ovm = __ballot_sync(FULL, ov);
-            if (ov) {
-                const int row = __popc(ovm & ((1u << lane) - 1));
-                const int cA = mine.loc0 > w0 ? mine.loc0 - w0 : 0;
-                const int cB = mine.loc0 + mine.len - w0 < 32 ? mine.loc0 + mine.len - w0 : 32;
-                Geo5 ge;
-                ge.colmask = (cB == 32 ? 0xFFFFFFFFu : ((1u << cB) - 1)) & ~((1u << cA) - 1);
-                const bool fast = elig && mq1 == dom_stage;
-                ge.flags = (uint16_t)((mq1 & 0x1FF) | (valid ? 0x200u : 0u) | (hasq ? 0x400u : 0u) | (fast ? 0x800u : 0u));
-                ge.qoff = 0;
-                if (valid && !(R.exp_flags & 4)) {
-                    const uint32_t i0 = mine.src + (uint32_t)(w0 + cA - mine.loc0);      // base index of column cA
-                    uint8_t* rq = W.rows[buf][row];
-                    const uint32_t ga = i0 & ~15u;
-                    const int nblk = (int)(((i0 + (uint32_t)(cB - cA) - 1) >> 4) - (i0 >> 4)) + 1;
-                    cp_async16(rq, gquals + ga);
-                    if (nblk > 1) cp_async16(rq + 16, gquals + ga + 16);
-                    if (nblk > 2) cp_async16(rq + 32, gquals + ga + 32);
-                    const uint32_t b0 = i0 >> 2, ba = b0 & ~3u;
-                    cp_async4(rq + 48, gbases + ba); cp_async4(rq + 52, gbases + ba + 4); cp_async4(rq + 56, gbases + ba + 8);
-                    // shared offset (from rows_base, biased by 32) of window column 0's quality byte
-                    ge.qoff = (uint16_t)((buf * 32 + row) * 64 + (int)(i0 - ga) - cA + 32);
-                    // code realignment recipe (applied after landing): bit shift | cA << 8, parked in the row's spare bytes
-                    *reinterpret_cast<uint32_t*>(rq + 60) = (8 * (b0 & 3) + 2 * (i0 & 3)) | ((uint32_t)cA << 8);
-                }
-                W.geo[buf][row] = ge;
-            }
-            return __popc(ovm);
-        };
-
-        // ---- compute one staged chunk of n rows (lane <-> row for the geometry) ----
-        auto compute = [&](int buf, int n, uint32_t dom) {
-            if (dom != cur_mq) { flush(); cur_mq = dom; }
-            rows_total += 32;
-            if (rows_total > P4_SPILL_ROWS) { flush(); spill(); }
-            uint32_t gm = 0, gf = 0; int32_t gq = (int32_t)rows_base;
-            if (lane < n) {
-                const Geo5 ge = W.geo[buf][lane];
-                gm = ge.colmask; gf = ge.flags; gq = (int32_t)rows_base + (int32_t)ge.qoff - 32;
-                if (gf & 0x200u) {                                   // realign the row's 2-bit codes to window column 0
-                    const uint32_t* wc = reinterpret_cast<const uint32_t*>(W.rows[buf][lane] + 48);
-                    const uint32_t W0 = wc[0], W1 = wc[1], W2 = wc[2], rec = wc[3];
-                    const uint32_t sft = rec & 0xFF, cA = (rec >> 8) & 0xFF;
-                    const uint64_t raw = ((uint64_t)__funnelshift_r(W1, W2, sft) << 32) | __funnelshift_r(W0, W1, sft);
-                    W.codes[lane] = raw << (2 * cA);
-                }
-            }
-            const unsigned fastm = __ballot_sync(FULL, (gf & 0x800u) != 0);
-            unsigned scalm = __ballot_sync(FULL, lane < n && !(gf & 0x800u));
-            const uint32_t cm_fast = (gf & 0x800u) ? gm : 0u;
-            __syncwarp();
-            // ---- odd rows: lane <-> locus ----
-            while (scalm) {
-                const int j = __ffs(scalm) - 1; scalm &= scalm - 1;
-                const uint32_t cmj = __shfl_sync(FULL, gm, j);
-                const uint32_t fj = __shfl_sync(FULL, gf, j);
-                const int32_t qb = __shfl_sync(FULL, gq, j);
-                if ((cmj >> lane) & 1) {
-                    if (!(fj & 0x200u)) atomicAdd(&W.tbp[lane], 1u);               // PileUpRegion.scala:45
-                    else {
-                        uint32_t qv;
-                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(qv) : "r"((uint32_t)(qb + lane)));
-                        if (!(qv & 0x80)) {
-                            const uint32_t code = (uint32_t)(W.codes[j] >> (2 * lane)) & 3;
-                            const uint32_t q = (fj & 0x400u) ? qv : defq;
-                            if (!MINQ || (int)q >= min_qual) {
-                                const uint32_t m1 = fj & 0x1FF;
-                                atomicAdd(&W.tcnt[lane][code], 1u); atomicAdd(&W.tqs[lane][code], q * m1);
-                                atomicAdd(&W.tmq[lane], m1); atomicAdd(&W.tq[lane], q);
-                            }
-                        }
-                    }
-                }
-            }
-            // ---- fast rows: 4 rows per step (lane group <-> row), 4 loci per lane, 4 steps in flight ----
-            if (fastm) {
-                const int r_lo = __ffs(fastm) - 1, r_hi = 32 - __clz(fastm);
-                const int iters = (r_hi - r_lo + 3) >> 2;
-                if (nrows + (uint32_t)iters > 255) flush();
-                nrows += (uint32_t)iters;
-                for (int it0 = 0; it0 < iters; it0 += 4) {
-                    uint32_t cm[4], wlo[4], whi[4], sh[4], C8[4];
-                    int32_t qb[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int r = r_lo + g + 4 * (it0 + u);
-                        cm[u] = __shfl_sync(FULL, cm_fast, r & 31);
-                        qb[u] = __shfl_sync(FULL, gq, r & 31);
-                        if (r >= r_hi) cm[u] = 0;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int r = r_lo + g + 4 * (it0 + u);
-                        const uint32_t a = (uint32_t)(qb[u] + kk);
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wlo[u]) : "r"(a & ~3u));
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(whi[u]) : "r"((a & ~3u) + 4));
-                        sh[u] = (a & 3) << 3;
-                        C8[u] = reinterpret_cast<const uint8_t*>(&W.codes[r & 31])[k];
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const uint32_t in4 = (((cm[u] >> kk) & 15u) * 0x00204081u) & 0x01010101u;
-                        const uint32_t Q4 = __funnelshift_r(wlo[u], whi[u], sh[u]);
-                        const uint32_t X = C8[u] ^ P8;
-                        const uint32_t mis4 = (((X | (X >> 1)) & 0x55u) * 0x00041041u) & 0x01010101u;
-                        uint32_t val4 = (~Q4 >> 7) & 0x01010101u;
-                        if (MINQ) val4 &= (((Q4 & 0x7F7F7F7Fu) + minq_add) >> 7);
-                        const uint32_t act4 = val4 & in4;
-                        const uint32_t mat4 = act4 & ~mis4;
-                        uint32_t mm4 = act4 & mis4;
-                        while (mm4) {                            // bases that differ from the primary letter: exact, direct
-                            const int j = (__ffs(mm4) - 1) >> 3; mm4 &= mm4 - 1;
-                            const uint32_t q = (Q4 >> (8 * j)) & 0x7F, letter = (C8[u] >> (2 * j)) & 3;
-                            const int l = kk + j;
-                            atomicAdd(&W.tcnt[l][letter], 1u);
-                            atomicAdd(&W.tqs[l][letter], q * cur_mq);
-                            atomicAdd(&W.tmq[l], cur_mq);
-                            atomicAdd(&W.tq[l], q);
-                        }
-                        const uint32_t Qm = Q4 & (mat4 * 0xFFu);
-                        cnt4 += mat4;
-                        QLo += Qm & 0x00FF00FFu;
-                        QHi += (Qm >> 8) & 0x00FF00FFu;
-                    }
-                }
-            }
-        };
-
-        uint32_t dom_cur = cur_mq, dom_next = cur_mq;
-        int n_cur = 0;
-        if (nchunks > 0) n_cur = stage(0, 0, dom_cur);
-        cp_async_commit();
-        for (int c = 0; c < nchunks; c++) {
-            int n_next = 0;
-            if (c + 1 < nchunks) n_next = stage(c + 1, (c + 1) & 1, dom_next);
-            cp_async_commit();
-            cp_async_wait<1>();
-            __syncwarp();
-            if (!(R.exp_flags & 2)) compute(c & 1, n_cur, dom_cur);
-            __syncwarp();
-            n_cur = n_next; dom_cur = dom_next;
-        }
+    auto batch_end = [&](bool frag) {                   // fragCoverage snapshot (GenomeRegion.scala:290-298)
         flush();
-        __syncwarp();
         const uint32_t nnow = W.tcnt[lane][0] + W.tcnt[lane][1] + W.tcnt[lane][2] + W.tcnt[lane][3];
-        if (bfrag) fragN += nnow - nprev;
+        if (frag) fragN += nnow - nprev;
         nprev = nnow;
         __syncwarp();
+    };
+
+    // ---- one flat, software-pipelined sequence of (batch, chunk) pairs: stage(i+1) | wait | compute(i) ----
+    // staging cursor
+    int s_b = -1; uint32_t s_c = 0, s_nch = 0, s_slo = 0, s_nseg = 0;
+    auto advance = [&]() -> bool {                      // move the cursor to the next non-empty chunk; false at the end
+        s_c++;
+        while (s_b < 0 || s_c >= s_nch) {
+            s_b++; s_c = 0;
+            if (s_b >= n_batches) return false;
+            s_nseg = __shfl_sync(FULL, my_nseg, s_b & 31);
+            s_nch = (s_nseg + 31) >> 5;
+            s_slo = __shfl_sync(FULL, my_slo, s_b & 31);
+        }
+        return true;
+    };
+    const Seg none = {0, 0, 0, 0};
+    Seg next = none;
+    bool have_next = advance();
+    if (have_next && (s_c << 5) + lane < s_nseg) next = PB.b[s_b].seg[s_slo + (s_c << 5) + lane];
+    uint32_t dom_stage = 0;
+
+    // per staged buffer: number of rows, dominant mq, batch index (-1: nothing staged)
+    int n_b0 = 0, n_b1 = 0; uint32_t dom_b0 = 0, dom_b1 = 0; int b_b0 = -1, b_b1 = -1;     // (scalars: no local-memory arrays)
+
+    auto stage = [&](int buf) {                         // stages the chunk under the cursor, then advances it
+        const Seg mine = next;
+        const int my_b = s_b;
+        const uint8_t* __restrict__ gquals = PB.b[my_b].quals;
+        const uint8_t* __restrict__ gbases = PB.b[my_b].bases2;
+        have_next = advance();
+        next = none;
+        if (have_next && (s_c << 5) + lane < s_nseg) next = PB.b[s_b].seg[s_slo + (s_c << 5) + lane];   // prefetch
+        const bool ov = mine.len > 0 && mine.loc0 < w0 + 32 && mine.loc0 + mine.len > w0;
+        const bool valid = mine.w & SEG_VALID, hasq = mine.w & SEG_HASQ;
+        const uint32_t mq1 = mine.w & 0xFFFF;
+        const bool elig = ov && valid && hasq;
+        if (__any_sync(FULL, elig && mq1 != dom_stage)) {               // vote only when some row disagrees
+            const unsigned peers = __match_any_sync(FULL, elig ? mq1 : (0x10000u + lane));
+            const uint32_t votes = elig ? (((uint32_t)__popc(peers) << 17) | ((mq1 == dom_stage) ? 0x10000u : 0u) | mq1) : 0u;
+            const uint32_t best = __reduce_max_sync(FULL, votes);
+            if (best) dom_stage = best & 0xFFFF;
+        }
+        const unsigned ovm = __ballot_sync(FULL, ov);
+        if (ov) {
+            const int row = __popc(ovm & ((1u << lane) - 1));
+            const int cA = mine.loc0 > w0 ? mine.loc0 - w0 : 0;
+            const int cB = mine.loc0 + mine.len - w0 < 32 ? mine.loc0 + mine.len - w0 : 32;
+            Geo5 ge;
+            ge.colmask = (cB == 32 ? 0xFFFFFFFFu : ((1u << cB) - 1)) & ~((1u << cA) - 1);
+            const bool fast = elig && mq1 == dom_stage;
+            ge.flags = (uint16_t)((mq1 & 0x1FF) | (valid ? 0x200u : 0u) | (hasq ? 0x400u : 0u) | (fast ? 0x800u : 0u));
+            ge.qoff = 0;
+            if (valid && !(R.exp_flags & 4)) {
+                const uint32_t i0 = mine.src + (uint32_t)(w0 + cA - mine.loc0);      // base index of column cA
+                uint8_t* rq = W.rows[buf][row];
+                const uint32_t ga = i0 & ~15u;
+                const int nblk = (int)(((i0 + (uint32_t)(cB - cA) - 1) >> 4) - (i0 >> 4)) + 1;
+                cp_async16(rq, gquals + ga);
+                if (nblk > 1) cp_async16(rq + 16, gquals + ga + 16);
+                if (nblk > 2) cp_async16(rq + 32, gquals + ga + 32);
+                const uint32_t b0 = i0 >> 2, ba = b0 & ~3u;
+                cp_async4(rq + 48, gbases + ba); cp_async4(rq + 52, gbases + ba + 4); cp_async4(rq + 56, gbases + ba + 8);
+                // shared offset (from rows_base, biased by 32) of window column 0's quality byte
+                ge.qoff = (uint16_t)((buf * 32 + row) * 64 + (int)(i0 - ga) - cA + 32);
+                // code realignment recipe (applied after landing): bit shift | cA << 8, parked in the row's spare bytes
+                *reinterpret_cast<uint32_t*>(rq + 60) = (8 * (b0 & 3) + 2 * (i0 & 3)) | ((uint32_t)cA << 8);
+            }
+            W.geo[buf][row] = ge;
+        }
+        if (buf) { n_b1 = __popc(ovm); dom_b1 = dom_stage; b_b1 = my_b; } else { n_b0 = __popc(ovm); dom_b0 = dom_stage; b_b0 = my_b; }
+    };
+
+    // one SIMD step for row r of the buffer (lane group g), 4 loci per lane
+    auto simd_step = [&](uint32_t cm, uint32_t wlo, uint32_t whi, uint32_t sh, uint32_t C8) {
+        const uint32_t in4 = (((cm >> kk) & 15u) * 0x00204081u) & 0x01010101u;
+        const uint32_t Q4 = __funnelshift_r(wlo, whi, sh);
+        const uint32_t X = C8 ^ P8;
+        const uint32_t mis4 = (((X | (X >> 1)) & 0x55u) * 0x00041041u) & 0x01010101u;
+        uint32_t val4 = (~Q4 >> 7) & 0x01010101u;
+        if (MINQ) val4 &= (((Q4 & 0x7F7F7F7Fu) + minq_add) >> 7);
+        const uint32_t act4 = val4 & in4;
+        const uint32_t mat4 = act4 & ~mis4;
+        uint32_t mm4 = act4 & mis4;
+        while (mm4) {                            // bases that differ from the primary letter: exact, direct
+            const int j = (__ffs(mm4) - 1) >> 3; mm4 &= mm4 - 1;
+            const uint32_t q = (Q4 >> (8 * j)) & 0x7F, letter = (C8 >> (2 * j)) & 3;
+            const int l = kk + j;
+            atomicAdd(&W.tcnt[l][letter], 1u);
+            atomicAdd(&W.tqs[l][letter], q * cur_mq);
+            atomicAdd(&W.tmq[l], cur_mq);
+            atomicAdd(&W.tq[l], q);
+        }
+        const uint32_t Qm = Q4 & (mat4 * 0xFFu);
+        cnt4 += mat4;
+        QLo += Qm & 0x00FF00FFu;
+        QHi += (Qm >> 8) & 0x00FF00FFu;
+    };
+
+    int last_b = -1;
+    auto compute = [&](int buf) {
+        const int n = buf ? n_b1 : n_b0;
+        const uint32_t dom = buf ? dom_b1 : dom_b0;
+        const int bb = buf ? b_b1 : b_b0;
+        if (bb != last_b) {                             // first chunk of another batch: close the previous one
+            if (last_b >= 0) batch_end(PB.b[last_b].flags & 1);
+            last_b = bb;
+        }
+        if (n == 0) return;
+        if (dom != cur_mq) { flush(); cur_mq = dom; }
+        rows_total += 32;
+        if (rows_total > P4_SPILL_ROWS) { flush(); spill(); }
+        uint32_t gm = 0, gf = 0; int32_t gq = (int32_t)rows_base;
+        if (lane < n) {
+            const Geo5 ge = W.geo[buf][lane];
+            gm = ge.colmask; gf = ge.flags; gq = (int32_t)rows_base + (int32_t)ge.qoff - 32;
+            if (gf & 0x200u) {                                   // realign the row's 2-bit codes to window column 0
+                const uint32_t* wc = reinterpret_cast<const uint32_t*>(W.rows[buf][lane] + 48);
+                const uint32_t W0 = wc[0], W1 = wc[1], W2 = wc[2], rec = wc[3];
+                const uint32_t sft = rec & 0xFF, cA = (rec >> 8) & 0xFF;
+                const uint64_t raw = ((uint64_t)__funnelshift_r(W1, W2, sft) << 32) | __funnelshift_r(W0, W1, sft);
+                W.codes[lane] = raw << (2 * cA);
+            }
+        }
+        const unsigned fastm = __ballot_sync(FULL, (gf & 0x800u) != 0);
+        unsigned scalm = __ballot_sync(FULL, lane < n && !(gf & 0x800u));
+        const uint32_t cm_fast = (gf & 0x800u) ? gm : 0u;
+        __syncwarp();
+        // ---- odd rows: lane <-> locus ----
+        while (scalm) {
+            const int j = __ffs(scalm) - 1; scalm &= scalm - 1;
+            const uint32_t cmj = __shfl_sync(FULL, gm, j);
+            const uint32_t fj = __shfl_sync(FULL, gf, j);
+            const int32_t qb = __shfl_sync(FULL, gq, j);
+            if ((cmj >> lane) & 1) {
+                if (!(fj & 0x200u)) atomicAdd(&W.tbp[lane], 1u);               // PileUpRegion.scala:45
+                else {
+                    uint32_t qv;
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(qv) : "r"((uint32_t)(qb + lane)));
+                    if (!(qv & 0x80)) {
+                        const uint32_t code = (uint32_t)(W.codes[j] >> (2 * lane)) & 3;
+                        const uint32_t q = (fj & 0x400u) ? qv : defq;
+                        if (!MINQ || (int)q >= min_qual) {
+                            const uint32_t m1 = fj & 0x1FF;
+                            atomicAdd(&W.tcnt[lane][code], 1u); atomicAdd(&W.tqs[lane][code], q * m1);
+                            atomicAdd(&W.tmq[lane], m1); atomicAdd(&W.tq[lane], q);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- fast rows: 4 rows per step (lane group <-> row), 4 loci per lane ----
+        if (fastm) {
+            const int r_lo = __ffs(fastm) - 1, r_hi = 32 - __clz(fastm);
+            const int iters = (r_hi - r_lo + 3) >> 2;
+            if (nrows + (uint32_t)iters > 255) flush();
+            nrows += (uint32_t)iters;
+            int it0 = 0;
+            // full trips: 4 independent steps in flight (all shuffles, then all loads, then the arithmetic)
+            for (; it0 + 4 <= iters; it0 += 4) {
+                uint32_t cm[4], wlo[4], whi[4], sh[4], C8[4];
+                int32_t qb[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int r = r_lo + g + 4 * (it0 + u);
+                    cm[u] = __shfl_sync(FULL, cm_fast, r & 31);
+                    qb[u] = __shfl_sync(FULL, gq, r & 31);
+                    if (r >= r_hi) cm[u] = 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int r = r_lo + g + 4 * (it0 + u);
+                    const uint32_t a = (uint32_t)(qb[u] + kk);
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wlo[u]) : "r"(a & ~3u));
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(whi[u]) : "r"((a & ~3u) + 4));
+                    sh[u] = (a & 3) << 3;
+                    C8[u] = reinterpret_cast<const uint8_t*>(&W.codes[r & 31])[k];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) simd_step(cm[u], wlo[u], whi[u], sh[u], C8[u]);
+            }
+            // remainder: one step per trip
+            for (; it0 < iters; it0++) {
+                const int r = r_lo + g + 4 * it0;
+                uint32_t cm = __shfl_sync(FULL, cm_fast, r & 31);
+                const int32_t qb = __shfl_sync(FULL, gq, r & 31);
+                if (r >= r_hi) cm = 0;
+                const uint32_t a = (uint32_t)(qb + kk);
+                uint32_t wlo, whi;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wlo) : "r"(a & ~3u));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(whi) : "r"((a & ~3u) + 4));
+                simd_step(cm, wlo, whi, (a & 3) << 3, reinterpret_cast<const uint8_t*>(&W.codes[r & 31])[k]);
+            }
+        }
+    };
+
+    int cur = 0;
+    bool have_cur = false;
+    if (have_next) { stage(0); have_cur = true; }
+    cp_async_commit();
+    while (have_cur) {
+        bool staged = false;
+        if (have_next) { stage(cur ^ 1); staged = true; }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        if (!(R.exp_flags & 2)) compute(cur);
+        __syncwarp();
+        cur ^= 1; have_cur = staged;
     }
+    if (last_b >= 0) batch_end(PB.b[last_b].flags & 1);
     cp_async_wait<0>();
     __syncwarp();
     uint32_t c[4]; uint64_t q[4];
