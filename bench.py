@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -305,15 +305,15 @@ def run_gpu_arm(args):
         step_sequential()
         step_concurrent()
     barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()              # covers both timed passes (nvidia-smi needs ~0.1 s to produce its first sample)
     seq_ms = pil_ms = 0.0
     launches = 0
     for _ in range(args.steps):
         a, p, n = step_sequential()
         seq_ms += a; pil_ms += p; launches += n
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
     wall0 = time.perf_counter()
     ev_start = torch.cuda.Event(enable_timing=True)
     ev_start.record(streams[0])
@@ -400,12 +400,21 @@ def run_gpu_arm(args):
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
+        traffic = None
+        try:     # dram bytes of the kernel from the committed ncu capture, scaled to this run's average launch
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["algorithmic_bytes"] * (sum(r.alg_bytes for r in regions) / len(regions))
+        except Exception:
+            pass
         alg = sum(r.alg_bytes for r in regions)                 # this rank's launches
         achieved = alg / (pileup_ms * 1e-3) / 1e9               # GB/s over the pileup kernel's launches of one step
         depth = total_aligned / total_loci
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            sample = sorted(regions, key=lambda r: abs(r.size - 2_000_000))[:3]
+            sample, acc = [], 0            # ~2 G aligned bases = 10-20 s of one host core
+            for r in sorted(regions, key=lambda r: -r.size):
+                if r.size <= 6_000_000 and acc < 2.0e9:
+                    sample.append(r); acc += r.aligned
             t = time_oracle(sample, 1)
             sb = sum(r.aligned for r in sample)
             cpu = {"value": sb / t, "unit": UNIT, "cores": 1, "kind": "port",
@@ -426,7 +435,8 @@ def run_gpu_arm(args):
                        "ms_per_step": 1e3 * e2e_sec, "streams_per_gpu": n_workers},
                "gpu_launches": int(job_launches),
                "roofline": {"bound": "hbm", "kernel": "k_pileup", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": sum(r.alg_bytes for r in regions) / len(regions),
                             "algorithmic_bytes_per_base": alg / total_aligned,
                             "pileup_ms_per_step": pileup_ms, "pileup_share_of_sequential_step": pileup_ms / seq_step_ms},
                "cpu_baseline": cpu, "clocks": clocks}
@@ -438,7 +448,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])

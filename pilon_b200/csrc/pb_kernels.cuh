@@ -457,12 +457,15 @@ __device__ __forceinline__ uint2 warp_incl_scan(uint2 v, int lane) {
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan1(RegionDev R, uint2* block_sums) {
     __shared__ uint2 wsum[SCAN_THREADS / 32];
-    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    // thread t owns items [t*ITEMS, t*ITEMS + ITEMS) of the tile: four 16-byte loads, whole sectors used
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     uint2 acc = make_uint2(0, 0);
+    if (base + SCAN_ITEMS <= R.size) {
+        const int4* p = reinterpret_cast<const int4*>(R.pc_diff + base);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        const int64_t i = base + (int64_t)k * SCAN_THREADS + threadIdx.x;
-        if (i < R.size) { const int2 d = R.pc_diff[i]; acc.x += (unsigned)d.x; acc.y += (unsigned)d.y; }
+        for (int k = 0; k < SCAN_ITEMS / 2; k++) { const int4 v = p[k]; acc.x += (unsigned)v.x + (unsigned)v.z; acc.y += (unsigned)v.y + (unsigned)v.w; }
+    } else {
+        for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < R.size) { const int2 d = R.pc_diff[base + k]; acc.x += (unsigned)d.x; acc.y += (unsigned)d.y; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { acc.x += __shfl_xor_sync(FULL, acc.x, o); acc.y += __shfl_xor_sync(FULL, acc.y, o); }
@@ -503,17 +506,29 @@ __global__ void __launch_bounds__(1024) k_scan2(RegionDev R, uint2* block_sums, 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan3(RegionDev R, const uint2* block_sums) {
     __shared__ uint2 wtot[SCAN_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // blocked arrangement: thread t owns items [t*ITEMS, t*ITEMS + ITEMS) of the tile
+    // blocked arrangement: thread t owns items [t*ITEMS, t*ITEMS + ITEMS) of the tile; 16-byte loads / stores
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    const bool full = base + SCAN_ITEMS <= R.size;
     uint2 v[SCAN_ITEMS];
     uint2 run = make_uint2(0, 0);
+    if (full) {
+        int4* p = reinterpret_cast<int4*>(R.pc_diff + base);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        const int64_t i = base + k;
-        int2 d = make_int2(0, 0);
-        if (i < R.size) { d = R.pc_diff[i]; R.pc_diff[i] = make_int2(0, 0); }
-        run.x += (unsigned)d.x; run.y += (unsigned)d.y;
-        v[k] = run;
+        for (int k = 0; k < SCAN_ITEMS / 2; k++) {
+            const int4 d = p[k];
+            p[k] = make_int4(0, 0, 0, 0);
+            run.x += (unsigned)d.x; run.y += (unsigned)d.y; v[2 * k] = run;
+            run.x += (unsigned)d.z; run.y += (unsigned)d.w; v[2 * k + 1] = run;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            const int64_t i = base + k;
+            int2 d = make_int2(0, 0);
+            if (i < R.size) { d = R.pc_diff[i]; R.pc_diff[i] = make_int2(0, 0); }
+            run.x += (unsigned)d.x; run.y += (unsigned)d.y;
+            v[k] = run;
+        }
     }
     const uint2 inc = warp_incl_scan(run, lane);
     if (lane == 31) wtot[warp] = inc;
@@ -521,15 +536,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan3(RegionDev R, const uint2
     uint2 off = block_sums[blockIdx.x];
     off.x += inc.x - run.x; off.y += inc.y - run.y;
     for (int w = 0; w < warp; w++) { off.x += wtot[w].x; off.y += wtot[w].y; }
+    int32_t pc[SCAN_ITEMS], is[SCAN_ITEMS];
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-        const int64_t i = base + k;
-        if (i < R.size) {
-            const int32_t pc = (int32_t)(v[k].x + off.x);
-            int32_t is = (int32_t)(v[k].y + off.y);
-            if (pc > 0) is /= pc;                                                               // :97-99
-            R.o_pc[i] = pc; R.o_is[i] = is;
+        pc[k] = (int32_t)(v[k].x + off.x);
+        is[k] = (int32_t)(v[k].y + off.y);
+        if (pc[k] > 0) is[k] /= pc[k];                                                          // :97-99
+    }
+    if (full) {
+        int4* op = reinterpret_cast<int4*>(R.o_pc + base); int4* oi = reinterpret_cast<int4*>(R.o_is + base);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS / 4; k++) {
+            op[k] = make_int4(pc[4 * k], pc[4 * k + 1], pc[4 * k + 2], pc[4 * k + 3]);
+            oi[k] = make_int4(is[4 * k], is[4 * k + 1], is[4 * k + 2], is[4 * k + 3]);
         }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < R.size) { R.o_pc[base + k] = pc[k]; R.o_is[base + k] = is[k]; }
     }
 }
 
