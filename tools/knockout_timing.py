@@ -1,5 +1,9 @@
+"""Knock-out timing of the pileup kernel on one 2 Mb region.
+
+usage: python tools/knockout_timing.py VER:EXP [VER:EXP ...]   (PB_PILEUP version : PB_EXP flag mask)
+"""
 import sys, os
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, torch
 from pilon_b200.engine import Engine
 wl, regions = bench.build_workload("C2", 0.2, 0, 8)
