@@ -104,8 +104,8 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
     e->cfg.default_qual = c->default_qual; e->cfg.min_min_depth = c->min_min_depth;
     e->cfg.old_indel = c->old_indel; e->cfg.fix_amb = c->fix_amb; e->cfg.min_depth = c->min_depth;
     if (const char* v = getenv("PB_PILEUP")) { const int pv = atoi(v); if (pv >= 1 && pv <= 5) e->pileup_version = pv; }
-    CK(cudaFuncSetAttribute(k_pileup5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Warp5) * P5_WARPS)));
-    CK(cudaFuncSetAttribute(k_pileup5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Warp5) * P5_WARPS)));
+    CK(cudaFuncSetAttribute(k_pileup5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_pileup5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_pileup4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem4)));
     CK(cudaFuncSetAttribute(k_pileup4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem4)));
     CK(cudaFuncSetAttribute(k_pileup3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem3)));
@@ -323,7 +323,8 @@ static int compute(pb_engine* e, bool time_pileup) {
         else k_pileup<false><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
     } else if (e->pileup_version == 5 && nb <= PB_MAXB) {
         const unsigned grid = (unsigned)((R.n_win + P5_WARPS - 1) / P5_WARPS);
-        const size_t smem = sizeof(Warp5) * P5_WARPS;
+        size_t smem = sizeof(Warp5) * P5_WARPS;
+        if (const char* sp = getenv("PB_SMEM_PAD")) smem += (size_t)atoi(sp);    // occupancy experiments
         PileBatches PBt; memset(&PBt, 0, sizeof(PBt)); PBt.n = nb;
         for (int i = 0; i < nb; i++) {
             const DevBatch& d = img[i];
