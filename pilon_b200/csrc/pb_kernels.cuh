@@ -52,6 +52,8 @@ __device__ __forceinline__ uint64_t fnv64(uint64_t h, uint8_t b) { return (h ^ b
 // per-base adds, which become segments for k_pileup.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t batch_id) {
+    // CIGAR operator sets as bit masks over the BAM op code (MIDNSHP=X = 0..8)
+    constexpr uint32_t OPS_ALN = 0x181u /* M = X */, OPS_REF = 0x18Du /* M D N = X */, OPS_READ = 0x193u /* M I S = X */;
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long bc = 0, aligned = 0;
     int rc = 0, unk = 0, fwd = 0, back = 0;
@@ -64,19 +66,23 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
         const bool valid = (mq >= cfg.min_mq) && (!paired || ((fl & PB_F_PROPER) && (fl & PB_F_MATE_SAME_REF)));  // :107
         const bool hasq = fl & PB_F_HAS_QUALS;
         const int32_t aStart = B.pos[r];
-        if (r > 0 && B.pos[r - 1] > aStart) atomicOr(&R.sc->error, 1);     // batch not sorted by pos
+        const int32_t prevStart = r > 0 ? B.pos[r - 1] : aStart;
         const uint32_t c0 = B.cigar_off[r], c1 = B.cigar_off[r + 1];
         const uint32_t seq0 = B.seq_off[r];
+        const int32_t tlen = B.tlen[r];                                    // every per-read load is issued before the first use
+        if (prevStart > aStart) atomicOr(&R.sc->error, 1);                 // batch not sorted by pos
         const int32_t flank = cfg.flank;
         int64_t clipped = 0, reflen = 0;
         for (uint32_t k = c0; k < c1; k++) {
             const uint32_t e = B.cigar[k]; const int op = e & 15; const int64_t len = e >> 4;
             if (op == 4) clipped += len;                                                        // :139
-            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) reflen += len;
-            if (op == 0 || op == 7 || op == 8) aligned += len;
+            if ((OPS_REF >> op) & 1) reflen += len;
+            if ((OPS_ALN >> op) & 1) aligned += len;
         }
         const int32_t aEnd = (fl & PB_F_UNMAPPED) ? 0 : wrap32((int64_t)aStart + reflen - 1);    // getAlignmentEnd
-        const int32_t adjMq = roundDivI(wrap32((int64_t)mq * (length - clipped)), length);       // :141
+        // :141; without soft clips roundDiv(mq * length, length) == mq whenever the product cannot wrap
+        const int32_t adjMq = (clipped == 0 && length > 0 && length < (1 << 22) && mq >= 0 && mq < 256)
+                                  ? mq : roundDivI(wrap32((int64_t)mq * (length - clipped)), length);
         const uint32_t segw = (uint32_t)((adjMq + 1) & 0xFFFF) | (hasq ? SEG_HASQ : 0u);
         const int64_t tlo = flank, thi = (int64_t)length - flank;      // trusted read offsets [tlo, thi)  :118
         int64_t readOffset = 0, refOffset = 0;
@@ -84,7 +90,7 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
             const uint32_t e = B.cigar[k]; const int op = e & 15; const int64_t len = e >> 4;
             const int64_t locus = (int64_t)aStart + refOffset;                                   // :148
             Seg sg; sg.loc0 = 0; sg.len = 0; sg.src = 0; sg.w = 0;
-            if (op == 0 || op == 7 || op == 8) {                                                 // M = X  :184-193
+            if ((OPS_ALN >> op) & 1) {                                                           // M = X  :184-193
                 int64_t o0 = readOffset > tlo ? readOffset : tlo;
                 int64_t o1 = readOffset + len < thi ? readOffset + len : thi;
                 if (o1 > o0) {
@@ -125,16 +131,16 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
                 if (bk > back) back = (int)(bk > 0x3fffffff ? 0x3fffffff : bk);
             }
             B.seg[k] = sg;
-            if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) readOffset += len;          // :214
-            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) refOffset += len;           // :215
+            if ((OPS_READ >> op) & 1) readOffset += len;                                         // :214
+            if ((OPS_REF >> op) & 1) refOffset += len;                                           // :215
         }
         rc = 1;                                                                                  // :218
         // physCovIncr, PileUpRegion.scala:62-88
         int32_t ins = 0;
-        if (valid && !(paired && B.tlen[r] <= 0)) {
+        if (valid && !(paired && tlen <= 0)) {
             int64_t s, e;
             if (!paired) { s = aStart < aEnd ? aStart : aEnd; e = aStart > aEnd ? aStart : aEnd; }
-            else { s = aStart; e = (int64_t)aStart + B.tlen[r]; }
+            else { s = aStart; e = (int64_t)aStart + tlen; }
             ins = wrap32(e - s); s = wrap32(s); e = wrap32(e);
             if (s >= R.start && s <= R.stop) { atomicAdd(&R.pc_diff[s - R.start].x, 1); atomicAdd(&R.pc_diff[s - R.start].y, ins); }
             else if (s < R.start && !(e < R.start)) { atomicAdd(&R.sc->phys_cov_start, 1); atomicAdd(&R.sc->insert_size_start, ins); }
@@ -156,8 +162,8 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
         if (aligned) atomicAdd(&sl->aligned_bases, aligned);
         if (rc) atomicAdd(&sl->read_count, rc);
         if (unk) atomicAdd(&sl->unknown_ops, unk);
-        if (fwd > sl->fwd[batch_id & 7]) atomicMax(&sl->fwd[batch_id & 7], fwd);
-        if (back > sl->back[batch_id & 7]) atomicMax(&sl->back[batch_id & 7], back);
+        if (fwd) atomicMax(&sl->fwd[batch_id & 7], fwd);          // fire-and-forget: reading the slot back would wait on a hot line
+        if (back) atomicMax(&sl->back[batch_id & 7], back);
     }
 }
 
