@@ -13,7 +13,7 @@
 
 #include <cub/device/device_merge_sort.cuh>
 
-#include "pb_pileup5.cuh"
+#include "pb_pileup7.cuh"
 
 using namespace pb;
 
@@ -76,7 +76,7 @@ struct pb_engine {
     int64_t launches = 0;
     float last_pileup_ms = 0.f;
     bool dirty = false;              // rare planes may be non-zero after a failed run
-    int pileup_version = 5;          // PB_PILEUP=1..4 selects an earlier kernel generation (A/B runs)
+    int pileup_version = 7;          // PB_PILEUP=1..5 selects an earlier kernel generation (A/B runs)
 };
 
 static int free_batches(pb_engine* e) {
@@ -103,7 +103,9 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
     e->cfg.min_qual = c->min_qual; e->cfg.min_mq = c->min_mq; e->cfg.flank = c->flank;
     e->cfg.default_qual = c->default_qual; e->cfg.min_min_depth = c->min_min_depth;
     e->cfg.old_indel = c->old_indel; e->cfg.fix_amb = c->fix_amb; e->cfg.min_depth = c->min_depth;
-    if (const char* v = getenv("PB_PILEUP")) { const int pv = atoi(v); if (pv >= 1 && pv <= 5) e->pileup_version = pv; }
+    if (const char* v = getenv("PB_PILEUP")) { const int pv = atoi(v); if (pv >= 1 && pv <= 7 && pv != 6) e->pileup_version = pv; }
+    CK(cudaFuncSetAttribute(k_pileup7<false, P7_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile7<P7_TILE>)));
+    CK(cudaFuncSetAttribute(k_pileup7<true, P7_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile7<P7_TILE>)));
     CK(cudaFuncSetAttribute(k_pileup5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_pileup5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_pileup4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem4)));
@@ -321,8 +323,10 @@ static int compute(pb_engine* e, bool time_pileup) {
         const unsigned grid = (unsigned)((R.n_win + PILEUP_WARPS - 1) / PILEUP_WARPS);
         if (e->cfg.min_qual > 0) k_pileup<true><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
         else k_pileup<false><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
-    } else if (e->pileup_version == 5 && nb <= PB_MAXB) {
-        const unsigned grid = (unsigned)((R.n_win + P5_WARPS - 1) / P5_WARPS);
+    } else if (e->pileup_version >= 5 && nb <= PB_MAXB) {
+        const bool v7 = e->pileup_version == 7;
+        const unsigned grid = v7 ? (unsigned)((R.n_win * 32 + P7_TILE - 1) / P7_TILE)
+                                 : (unsigned)((R.n_win + P5_WARPS - 1) / P5_WARPS);
         size_t smem = sizeof(Warp5) * P5_WARPS;
         if (const char* sp = getenv("PB_SMEM_PAD")) smem += (size_t)atoi(sp);    // occupancy experiments
         PileBatches PBt; memset(&PBt, 0, sizeof(PBt)); PBt.n = nb;
@@ -332,7 +336,10 @@ static int compute(pb_engine* e, bool time_pileup) {
             PBt.b[i].n_cigar = (uint32_t)d.n_cigar; PBt.b[i].fwd = d.fwd; PBt.b[i].back = d.back;
             PBt.b[i].flags = (d.frag ? 1u : 0u) | (d.n_reads ? 2u : 0u);
         }
-        if (e->cfg.min_qual > 0) k_pileup5<true><<<grid, P5_WARPS * 32, smem, s>>>(R, PBt);
+        if (v7) {
+            if (e->cfg.min_qual > 0) k_pileup7<true, P7_TILE><<<grid, P7_WARPS * 32, sizeof(Tile7<P7_TILE>), s>>>(R, PBt);
+            else k_pileup7<false, P7_TILE><<<grid, P7_WARPS * 32, sizeof(Tile7<P7_TILE>), s>>>(R, PBt);
+        } else if (e->cfg.min_qual > 0) k_pileup5<true><<<grid, P5_WARPS * 32, smem, s>>>(R, PBt);
         else k_pileup5<false><<<grid, P5_WARPS * 32, smem, s>>>(R, PBt);
     } else if (e->pileup_version >= 4) {      // (also: more batches than k_pileup5's by-value table holds)
         const unsigned grid = (unsigned)((R.n_win + P4_CW - 1) / P4_CW);

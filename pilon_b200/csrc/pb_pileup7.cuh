@@ -1,0 +1,309 @@
+// pb_pileup7.cuh -- the hot kernel, seventh generation: scatter into a shared-memory tile.
+//
+// The gather kernels (k_pileup .. k_pileup5) give a 32-locus window to a warp and bring every
+// overlapping read segment to it; a 130-base segment meets five windows, and each of those meetings
+// costs descriptor handling, staging geometry and realignment -- two thirds of k_pileup5's issue slots
+// (profiles/README.md, r1p).  This kernel turns the loop around:
+//
+//   * a CTA owns a tile of T loci and keeps PileUp's hot counters for it in shared memory;
+//   * its warps take the segments that overlap the tile, 32 descriptors per grab from a shared cursor,
+//     LANE <-> HALF A SEGMENT: every per-segment computation (clipping, addresses, flags) is done once per
+//     lane for 16 segments at a time, and a lane then walks its half in aligned 16-base chunks --
+//     one 16-byte load of quality bytes, one 4-byte load of 2-bit codes -- and issues for every counted
+//     base ONE native 32-bit shared-memory reduction,
+//         A[letter][locus] += 1 << 20 | qual        (12-bit count | 20-bit quality sum).
+//     The 32 lanes of a reduction hit 32 unrelated loci (~3 wavefronts per instruction instead of 1);
+//     that is the price for paying ~8 thread instructions per base and nothing per (segment, window);
+//   * PileUp.add's other three sums (PileUp.scala:75-84) follow from that pair for every read whose
+//     (adjMq + 1) equals the tile's reference value `dom` (the first one the CTA meets):
+//         qualSum[b] = dom * sum_q[b] + Bq[b],   mqSum = dom * count + C,   qSum = sum_b sum_q[b]
+//     where Bq / C collect `qual * (mq1 - dom)` and `mq1 - dom` of the other reads (two more reductions
+//     per base for those only).  badPair and the bases outside fragCoverage share a fourth word;
+//   * the loads of a lane's next chunk are issued before the reductions of the current one;
+//   * every segment is met once per tile (T = 1024: 13 % halo instead of 5x), quality bytes go from
+//     L2 straight into registers, nothing is staged or flushed;
+//   * 12-bit counts: after 4064 descriptors the tile is folded into the 32/64-bit output planes
+//     (deep pile-ups only), then the epilogue (finish_locus) runs per locus as before.
+//
+// Integer atomics commute, so the result is bit-identical to the sequential walk of the reference.
+#pragma once
+#include "pb_pileup5.cuh"
+
+namespace pb {
+
+static constexpr int P7_WARPS = 8;
+static constexpr int P7_TILE = 1024;                // loci per CTA
+static constexpr int P7_GRAB = 16;                  // descriptors per grab from the tile's cursor (two lanes per descriptor)
+static constexpr int P7_PASS_DESC = 4064;           // descriptors per pass <= 4095 (12-bit count)
+
+__device__ __forceinline__ void red_shared_add(uint32_t saddr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_shared_add_if(uint32_t nz, uint32_t saddr, uint32_t v) {   // predicated, no branch
+    asm volatile("{\n .reg .pred pp;\n setp.ne.u32 pp, %0, 0;\n @pp red.shared.add.u32 [%1], %2;\n}" ::"r"(nz), "r"(saddr), "r"(v) : "memory");
+}
+
+template <int T>
+struct __align__(16) Tile7 {
+    uint32_t A[4][T];            // count << 20 | sum of quals, per letter
+    int32_t Bq[4][T];            // sum of qual * (mq1 - dom)
+    int32_t C[T];                // sum of (mq1 - dom)
+    uint32_t X[T];               // badPair << 16 | counted bases outside fragCoverage
+    uint32_t grab0[PB_MAXB + 1]; // first flat grab index of every batch
+    uint32_t slo[PB_MAXB], nseg[PB_MAXB];
+    uint32_t dom;                // 0 = not chosen yet ((adjMq + 1) >= 1 always)
+    uint32_t next;               // next flat grab index to hand out
+};
+
+// if (bits & mask) { A word += v;  (NF) X word += 1 }   -- one predicate for both reductions
+template <bool NF>
+__device__ __forceinline__ void red_counted(uint32_t bits, uint32_t mask, uint32_t saddr, uint32_t v, uint32_t xaddr) {
+    if (NF)
+        asm volatile("{\n .reg .pred pp;\n .reg .b32 tt;\n and.b32 tt, %0, %1;\n setp.ne.u32 pp, tt, 0;\n @pp red.shared.add.u32 [%2], %3;\n @pp red.shared.add.u32 [%4], 1;\n}"
+                     ::"r"(bits), "r"(mask), "r"(saddr), "r"(v), "r"(xaddr) : "memory");
+    else
+        asm volatile("{\n .reg .pred pp;\n .reg .b32 tt;\n and.b32 tt, %0, %1;\n setp.ne.u32 pp, tt, 0;\n @pp red.shared.add.u32 [%2], %3;\n}"
+                     ::"r"(bits), "r"(mask), "r"(saddr), "r"(v) : "memory");
+}
+
+// 16 bases of one lane's segment: Q = their quality bytes, cw = their 2-bit codes, okm = which of them are counted,
+// sa = shared byte address of A[0][locus of base 0 of the chunk].
+template <bool NF, int T>
+__device__ __forceinline__ void scatter_chunk(const uint4 Q, uint32_t cw, uint32_t okm, uint32_t sa, uint32_t qand, uint32_t qor) {
+    constexpr uint32_t OFF_X = 36u * T;                                        // byte offset of X[.] from A[0][.]
+    constexpr int LOG = T == 512 ? 11 : T == 1024 ? 12 : 13;                   // log2 of the letter stride in bytes
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+        const uint32_t Qw = b < 4 ? Q.x : b < 8 ? Q.y : b < 12 ? Q.z : Q.w;
+        const uint32_t val = (__byte_perm(Qw, 0, 0x4440 | (b & 3)) & qand) | qor;          // 1 << 20 | q
+        const uint32_t letter = (2 * b <= LOG ? (cw << (LOG - 2 * b)) : (cw >> (2 * b - LOG))) & (3u << LOG);
+        red_counted<NF>(okm, 1u << b, sa + letter + 4u * b, val, sa + 4u * b + OFF_X);
+    }
+}
+
+// The same 16 bases for a segment whose (adjMq + 1) differs from the tile's reference value by dmq: Bq / C terms.
+template <int T>
+__device__ __forceinline__ void scatter_chunk_dmq(const uint4 Q, uint32_t cw, uint32_t okm, uint32_t sa, uint32_t qand, uint32_t qor, int32_t dmq) {
+    constexpr uint32_t OFF_BQ = 16u * T, OFF_C = 32u * T;
+    constexpr int LOG = T == 512 ? 11 : T == 1024 ? 12 : 13;
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+        const uint32_t Qw = b < 4 ? Q.x : b < 8 ? Q.y : b < 12 ? Q.z : Q.w;
+        const uint32_t q = ((__byte_perm(Qw, 0, 0x4440 | (b & 3)) & qand) | qor) & 0xFFu;
+        const uint32_t letter = (2 * b <= LOG ? (cw << (LOG - 2 * b)) : (cw >> (2 * b - LOG))) & (3u << LOG);
+        asm volatile("{\n .reg .pred pp;\n .reg .b32 tt;\n and.b32 tt, %0, %1;\n setp.ne.u32 pp, tt, 0;\n @pp red.shared.add.u32 [%2], %3;\n @pp red.shared.add.u32 [%4], %5;\n}"
+                     ::"r"(okm), "r"(1u << b), "r"(sa + letter + 4u * b + OFF_BQ), "r"((uint32_t)((int32_t)q * dmq)),
+                       "r"(sa + 4u * b + OFF_C), "r"((uint32_t)dmq) : "memory");
+    }
+}
+
+template <bool MINQ, int T>
+__global__ void __launch_bounds__(P7_WARPS * 32, 4) k_pileup7(const RegionDev R, const PileBatches PB) {
+    extern __shared__ __align__(16) uint8_t smem_raw7[];
+    Tile7<T>& S = *reinterpret_cast<Tile7<T>*>(smem_raw7);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t t0 = (int32_t)blockIdx.x * T;
+    const int n_batches = PB.n;
+    const int min_qual = R.cfg.min_qual;
+    const uint32_t defq = (uint32_t)R.cfg.default_qual;
+    const uint32_t minq_add = (uint32_t)(0x80 - (min_qual > 128 ? 128 : min_qual)) * 0x01010101u;
+    constexpr uint32_t OFF_X = 36u * T;                         // byte offset of X[.] from A[0][.]
+
+    // ---- tile set-up: zero the counters, candidate descriptor range of every batch ----
+    {
+        uint32_t* z = reinterpret_cast<uint32_t*>(&S.A[0][0]);
+        for (int i = tid; i < 10 * T; i += P7_WARPS * 32) z[i] = 0;
+        if (tid == 0) { S.dom = 0; S.next = 0; }
+        if (warp == 0) {
+            uint32_t my_slo = 0, my_nseg = 0;
+            if (lane < n_batches) {
+                const PileBatch& Bl = PB.b[lane];
+                if (Bl.flags & 2) {
+                    const int64_t x = (int64_t)t0 - Bl.fwd + 1;
+                    const int64_t y = (int64_t)t0 + T + Bl.back;
+                    int64_t khi = (y + 31) >> 5; if (khi > R.n_win) khi = R.n_win;
+                    my_slo = x <= 0 ? 0u : Bl.win_first[x >> 5];
+                    const uint32_t shi = (y > ((int64_t)R.n_win << 5)) ? Bl.n_cigar : Bl.win_first[khi];
+                    my_nseg = shi > my_slo ? shi - my_slo : 0u;
+                }
+            }
+            uint32_t ng = (my_nseg + P7_GRAB - 1) / P7_GRAB, pre = ng;      // inclusive scan of the grab counts
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += v; }
+            if (lane < PB_MAXB) { S.slo[lane] = my_slo; S.nseg[lane] = my_nseg; S.grab0[lane] = pre - ng; }
+            if (lane == PB_MAXB - 1) S.grab0[PB_MAXB] = pre;
+        }
+    }
+    __syncthreads();
+    const uint32_t total_grabs = S.grab0[PB_MAXB];
+    bool folded = false;
+
+    // fold the 12/20-bit tile into the output planes (used as 32/64-bit accumulators) and clear it
+    auto fold = [&]() {
+        const uint32_t dom = S.dom;
+        for (int l = tid; l < T; l += P7_WARPS * 32) {
+            const int64_t loc = (int64_t)t0 + l;
+            const int x_ = l;
+            if (loc < R.size) {
+                uint32_t c[4], sq[4]; long long q[4];
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const uint32_t a = S.A[b][x_]; c[b] = a >> 20; sq[b] = a & 0xFFFFFu;
+                    q[b] = (long long)((uint64_t)dom * sq[b]) + (long long)S.Bq[b][x_];
+                }
+                const uint32_t n = c[0] + c[1] + c[2] + c[3];
+                const uint32_t mq = dom * n + (uint32_t)S.C[x_], qs = sq[0] + sq[1] + sq[2] + sq[3];
+                const uint32_t x = S.X[x_];
+                int4* oc = reinterpret_cast<int4*>(R.o_cnt) + loc;
+                long long* oq = reinterpret_cast<long long*>(R.o_qs) + 4 * loc;
+                if (folded) {
+                    const int4 p = *oc;
+                    *oc = make_int4(p.x + (int)c[0], p.y + (int)c[1], p.z + (int)c[2], p.w + (int)c[3]);
+#pragma unroll
+                    for (int b = 0; b < 4; b++) oq[b] += q[b];
+                    R.o_mq[loc] += (int32_t)mq; R.o_q[loc] += (int32_t)qs;
+                    R.o_bp[loc] += (int32_t)(x >> 16); R.o_frag[loc] += (int32_t)(x & 0xFFFFu);
+                } else {
+                    *oc = make_int4((int)c[0], (int)c[1], (int)c[2], (int)c[3]);
+#pragma unroll
+                    for (int b = 0; b < 4; b++) oq[b] = q[b];
+                    R.o_mq[loc] = (int32_t)mq; R.o_q[loc] = (int32_t)qs;
+                    R.o_bp[loc] = (int32_t)(x >> 16); R.o_frag[loc] = (int32_t)(x & 0xFFFFu);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < 4; b++) { S.A[b][x_] = 0; S.Bq[b][x_] = 0; }
+            S.C[x_] = 0; S.X[x_] = 0;
+        }
+        folded = true;
+    };
+
+    // ---- scatter: passes of <= 4064 descriptors; a warp takes the next 16 descriptors when it is free ----
+    const uint32_t sA = smem_u32(&S.A[0][0]);
+    uint32_t dom_r = 0;                                          // register copy of S.dom once it is known
+    static_assert(T == 512 || T == 1024 || T == 2048, "tile size");
+    constexpr uint32_t PASS_GRABS = P7_PASS_DESC / P7_GRAB;
+    for (uint32_t p0 = 0; p0 < total_grabs; p0 += PASS_GRABS) {
+        if (p0) {
+            __syncthreads(); fold();
+            if (tid == 0) S.next = p0;
+            __syncthreads();
+        }
+        const uint32_t p1 = min(p0 + PASS_GRABS, total_grabs);
+        while (!(R.exp_flags & 2)) {
+            uint32_t g = 0;
+            if (lane == 0) g = atomicAdd(&S.next, 1u);
+            g = __shfl_sync(FULL, g, 0);
+            if (g >= p1) break;
+            int b = 0;
+            while (g >= S.grab0[b + 1]) b++;                      // batch of this grab (grab0 is non-decreasing)
+            const PileBatch& Bb = PB.b[b];
+            // two lanes per descriptor: lane (d, h) walks half h of the chunks of descriptor d
+            const int h = lane & 1;
+            const uint32_t di = (g - S.grab0[b]) * P7_GRAB + (uint32_t)(lane >> 1);
+            Seg mine = {0, 0, 0, 0};
+            if (di < S.nseg[b]) mine = Bb.seg[S.slo[b] + di];
+            const uint8_t* __restrict__ gquals = Bb.quals;
+            const uint8_t* __restrict__ gbases = Bb.bases2;
+            const bool nf = !(Bb.flags & 1);                      // warp-uniform: this batch is outside fragCoverage
+            // my segment clipped to the tile: n bases from base index src, first locus = tile column col
+            const int32_t cA = mine.loc0 > t0 ? mine.loc0 : t0;
+            const int32_t cBx = mine.loc0 + mine.len < t0 + T ? mine.loc0 + mine.len : t0 + T;
+            const int32_t n = mine.len > 0 ? (cBx > cA ? cBx - cA : 0) : 0;
+            const uint32_t src = mine.src + (uint32_t)(cA - mine.loc0);
+            const int32_t col = cA - t0;
+            const bool valid = mine.w & SEG_VALID;
+            if (n > 0 && !valid) {                                // PileUpRegion.scala:45: badPair++ on every locus
+                uint32_t xa = sA + OFF_X + 4u * (uint32_t)(col + h);
+                for (int i = h; i < n; i += 2, xa += 8) red_shared_add(xa, 0x10000u);
+            }
+            const bool live = n > 0 && valid;
+            const unsigned livem = __ballot_sync(FULL, live);
+            if (livem == 0) continue;
+            const uint32_t mq1 = mine.w & 0xFFFFu;
+            if (dom_r == 0) {                                     // the tile's reference (adjMq + 1): first one met
+                const uint32_t first = __shfl_sync(FULL, mq1, __ffs(livem) - 1);
+                uint32_t old = 0;
+                if (lane == 0) old = atomicCAS(&S.dom, 0u, first);
+                old = __shfl_sync(FULL, old, 0);
+                dom_r = old ? old : first;
+            }
+            const int32_t dmq = (int32_t)mq1 - (int32_t)dom_r;
+            const bool hasq = mine.w & SEG_HASQ;
+            const uint32_t qand = hasq ? 0x7Fu : 0u, qor = (1u << 20) | (hasq ? 0u : defq);
+            const uint32_t nohq_pass = (!hasq && (int)defq >= min_qual) ? 0x01010101u : 0u;
+            if (live) {
+                // aligned 16-base chunks c0..c1 of the batch's base stream (chunk k = bases [16 k, 16 k + 16)); my half of them
+                const uint32_t last = src + (uint32_t)n - 1u;
+                const uint32_t c0 = src >> 4, c1 = last >> 4, mid = c0 + ((c1 - c0 + 2u) >> 1);
+                uint32_t k = h ? mid : c0;
+                const uint32_t k1 = h ? c1 : mid - 1u;
+                if (k <= k1) {
+                    const uint4* qp = reinterpret_cast<const uint4*>(gquals) + k;
+                    const uint32_t* cp = reinterpret_cast<const uint32_t*>(gbases) + k;
+                    uint32_t sa = sA + 4u * (uint32_t)(col + (int32_t)(16u * k - src));      // A[0][locus of base 16 k] (virtual before col)
+                    uint4 Q = *qp; uint32_t cw = *cp;
+                    for (;;) {
+                        uint4 Qn = make_uint4(0, 0, 0, 0); uint32_t cwn = 0;
+                        const bool more = k < k1;
+                        if (more) { Qn = qp[1]; cwn = cp[1]; }                           // next chunk's loads in flight
+                        // which of the 16 bases are counted: inside [src, last], quality byte without the 0x80 mark, >= minQual
+                        const uint32_t lo = k == c0 ? (src & 15u) : 0u, hi = k == c1 ? (last & 15u) + 1u : 16u;
+                        uint32_t okm = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+                        {
+                            uint32_t v0 = ~Q.x >> 7, v1 = ~Q.y >> 7, v2 = ~Q.z >> 7, v3 = ~Q.w >> 7;
+                            if (MINQ) {                                                  // reads without qualities: default_qual decides
+                                v0 &= (((Q.x & 0x7F7F7F7Fu) + minq_add) >> 7) | nohq_pass; v1 &= (((Q.y & 0x7F7F7F7Fu) + minq_add) >> 7) | nohq_pass;
+                                v2 &= (((Q.z & 0x7F7F7F7Fu) + minq_add) >> 7) | nohq_pass; v3 &= (((Q.w & 0x7F7F7F7Fu) + minq_add) >> 7) | nohq_pass;
+                            }
+                            const uint32_t m0 = ((v0 & 0x01010101u) * 0x01020408u) >> 24, m1 = ((v1 & 0x01010101u) * 0x01020408u) >> 24;
+                            const uint32_t m2 = ((v2 & 0x01010101u) * 0x01020408u) >> 24, m3 = ((v3 & 0x01010101u) * 0x01020408u) >> 24;
+                            okm &= (m0 & 15u) | ((m1 & 15u) << 4) | ((m2 & 15u) << 8) | ((m3 & 15u) << 12);
+                        }
+                        if (nf) scatter_chunk<true, T>(Q, cw, okm, sa, qand, qor);
+                        else scatter_chunk<false, T>(Q, cw, okm, sa, qand, qor);
+                        if (dmq != 0) scatter_chunk_dmq<T>(Q, cw, okm, sa, qand, qor, dmq);      // ~5 % of the reads
+                        if (!more) break;
+                        Q = Qn; cw = cwn; k++; qp++; cp++; sa += 64;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- epilogue: warp per 32-locus window of the tile ----
+    const uint32_t dom = S.dom;
+    for (int wl = warp; wl < T / 32; wl += P7_WARPS) {
+        const int64_t w = ((int64_t)t0 >> 5) + wl;
+        if (w >= R.n_win) break;
+        const int l = wl * 32 + lane, x_ = l;
+        const int64_t loc = (int64_t)t0 + l;
+        const bool inr = loc < R.size;
+        const uint32_t pre_rb = R.rare_bits[w];
+        const uint8_t pre_ref = inr ? ref_at(R, (int64_t)R.start + loc) : (uint8_t)'N';
+        uint32_t c[4], sq[4]; uint64_t q[4];
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint32_t a = S.A[b][x_]; c[b] = a >> 20; sq[b] = a & 0xFFFFFu;
+            q[b] = (uint64_t)((long long)((uint64_t)dom * sq[b]) + (long long)S.Bq[b][x_]);
+        }
+        uint32_t n = c[0] + c[1] + c[2] + c[3];
+        uint32_t mqS = dom * n + (uint32_t)S.C[x_], qS = sq[0] + sq[1] + sq[2] + sq[3];
+        const uint32_t x = S.X[x_];
+        uint32_t bp = x >> 16, nfc = x & 0xFFFFu;
+        if (folded && inr) {
+            const int4 p = reinterpret_cast<const int4*>(R.o_cnt)[loc];
+            c[0] += (uint32_t)p.x; c[1] += (uint32_t)p.y; c[2] += (uint32_t)p.z; c[3] += (uint32_t)p.w;
+#pragma unroll
+            for (int b = 0; b < 4; b++) q[b] += (uint64_t)R.o_qs[4 * loc + b];
+            mqS += (uint32_t)R.o_mq[loc]; qS += (uint32_t)R.o_q[loc];
+            bp += (uint32_t)R.o_bp[loc]; nfc += (uint32_t)R.o_frag[loc];
+            n = c[0] + c[1] + c[2] + c[3];
+        }
+        if (R.exp_flags & 1) { if (c[0] == 0xdeadbeef) R.o_mq[loc] = (int32_t)q[0]; continue; }
+        finish_locus(R, w, lane, (int32_t)loc, c, q, mqS, qS, bp, n - nfc, pre_rb, pre_ref);
+    }
+}
+
+}  // namespace pb
