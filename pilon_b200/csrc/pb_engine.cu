@@ -76,7 +76,7 @@ struct pb_engine {
     int64_t launches = 0;
     float last_pileup_ms = 0.f;
     bool dirty = false;              // rare planes may be non-zero after a failed run
-    int pileup_version = 7;          // PB_PILEUP=1..5 selects an earlier kernel generation (A/B runs)
+    int pileup_version = 0;          // 0 = choose per region (k_pileup7 scatter / k_pileup5 gather); PB_PILEUP=1..5,7 forces one (A/B runs)
 };
 
 static int free_batches(pb_engine* e) {
@@ -319,12 +319,20 @@ static int compute(pb_engine* e, bool time_pileup) {
     }
     if (const char* xf = getenv("PB_EXP")) R.exp_flags = atoi(xf);
     if (time_pileup) CK(cudaEventRecord(e->evp0, s));
-    if (e->pileup_version == 1) {
+    // The scatter kernel needs enough 2048-locus tiles to fill the GPU and shallow enough pile-ups that its 12-bit tile
+    // counters rarely fold; deep, narrow regions (amplicons, BASELINE config 5) go to the gather kernel.
+    int pv = e->pileup_version;
+    if (pv == 0) {
+        const int64_t tiles = (R.size + P7_TILE - 1) / P7_TILE;
+        const int64_t depth = R.size > 0 ? (int64_t)(e->h_sc->base_count / (unsigned long long)R.size) : 0;
+        pv = (tiles >= 256 && depth <= 1000) ? 7 : 5;
+    }
+    if (pv == 1) {
         const unsigned grid = (unsigned)((R.n_win + PILEUP_WARPS - 1) / PILEUP_WARPS);
         if (e->cfg.min_qual > 0) k_pileup<true><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
         else k_pileup<false><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
-    } else if (e->pileup_version >= 5 && nb <= PB_MAXB) {
-        const bool v7 = e->pileup_version == 7;
+    } else if (pv >= 5 && nb <= PB_MAXB) {
+        const bool v7 = pv == 7;
         const unsigned grid = v7 ? (unsigned)((R.n_win * 32 + P7_TILE - 1) / P7_TILE)
                                  : (unsigned)((R.n_win + P5_WARPS - 1) / P5_WARPS);
         size_t smem = sizeof(Warp5) * P5_WARPS;
@@ -341,7 +349,7 @@ static int compute(pb_engine* e, bool time_pileup) {
             else k_pileup7<false, P7_TILE><<<grid, P7_WARPS * 32, sizeof(Tile7<P7_TILE>), s>>>(R, PBt);
         } else if (e->cfg.min_qual > 0) k_pileup5<true><<<grid, P5_WARPS * 32, smem, s>>>(R, PBt);
         else k_pileup5<false><<<grid, P5_WARPS * 32, smem, s>>>(R, PBt);
-    } else if (e->pileup_version >= 4) {      // (also: more batches than k_pileup5's by-value table holds)
+    } else if (pv >= 4) {      // (also: more batches than k_pileup5's by-value table holds)
         const unsigned grid = (unsigned)((R.n_win + P4_CW - 1) / P4_CW);
         if (const char* dt = getenv("PB_DEBUG_TILE")) {
             CK(e->dbg.ensure(8 * 256 * 16, false, s));
@@ -350,7 +358,7 @@ static int compute(pb_engine* e, bool time_pileup) {
         }
         if (e->cfg.min_qual > 0) k_pileup4<true><<<grid, (P4_CW + 1) * 32, sizeof(Smem4), s>>>(R, dB, nb);
         else k_pileup4<false><<<grid, (P4_CW + 1) * 32, sizeof(Smem4), s>>>(R, dB, nb);
-    } else if (e->pileup_version == 3) {
+    } else if (pv == 3) {
         const unsigned grid = (unsigned)((R.n_win + P3_CW - 1) / P3_CW);
         if (e->cfg.min_qual > 0) k_pileup3<true><<<grid, (P3_CW + 1) * 32, sizeof(Smem3), s>>>(R, dB, nb);
         else k_pileup3<false><<<grid, (P3_CW + 1) * 32, sizeof(Smem3), s>>>(R, dB, nb);

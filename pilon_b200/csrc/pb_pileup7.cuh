@@ -31,8 +31,8 @@
 
 namespace pb {
 
-static constexpr int P7_WARPS = 8;
-static constexpr int P7_TILE = 1024;                // loci per CTA
+static constexpr int P7_WARPS = 16;
+static constexpr int P7_TILE = 2048;                // loci per CTA
 static constexpr int P7_GRAB = 16;                  // descriptors per grab from the tile's cursor (two lanes per descriptor)
 static constexpr int P7_PASS_DESC = 4064;           // descriptors per pass <= 4095 (12-bit count)
 
@@ -67,17 +67,23 @@ __device__ __forceinline__ void red_counted(uint32_t bits, uint32_t mask, uint32
 }
 
 // 16 bases of one lane's segment: Q = their quality bytes, cw = their 2-bit codes, okm = which of them are counted,
-// sa = shared byte address of A[0][locus of base 0 of the chunk].
-template <bool NF, int T>
+// sa = shared byte address of A[0][locus of base 0 of the chunk].  Per base: PRMT (value), LOP + IMAD (address of
+// the letter's word), LOP3 -> predicate, RED.  HQ: every lane's read has qualities (the byte goes straight into the
+// packed value 1 << 20 | q); otherwise qand / qor substitute default_qual per lane.
+template <bool NF, bool HQ, int T>
 __device__ __forceinline__ void scatter_chunk(const uint4 Q, uint32_t cw, uint32_t okm, uint32_t sa, uint32_t qand, uint32_t qor) {
     constexpr uint32_t OFF_X = 36u * T;                                        // byte offset of X[.] from A[0][.]
     constexpr int LOG = T == 512 ? 11 : T == 1024 ? 12 : 13;                   // log2 of the letter stride in bytes
+    const uint32_t cwm = cw >> 14, cwh = cw >> 28;                             // codes of bases 7.. and 14.. at bit 0
 #pragma unroll
     for (int b = 0; b < 16; b++) {
         const uint32_t Qw = b < 4 ? Q.x : b < 8 ? Q.y : b < 12 ? Q.z : Q.w;
-        const uint32_t val = (__byte_perm(Qw, 0, 0x4440 | (b & 3)) & qand) | qor;          // 1 << 20 | q
-        const uint32_t letter = (2 * b <= LOG ? (cw << (LOG - 2 * b)) : (cw >> (2 * b - LOG))) & (3u << LOG);
-        red_counted<NF>(okm, 1u << b, sa + letter + 4u * b, val, sa + 4u * b + OFF_X);
+        const uint32_t val = HQ ? __byte_perm(Qw, 0x00100000u, 0x7650 | (b & 3))
+                                : ((__byte_perm(Qw, 0, 0x4440 | (b & 3)) & qand) | qor);   // 1 << 20 | q
+        const int pos = b < 7 ? 2 * b : b < 14 ? 2 * (b - 7) : 2 * (b - 14);   // bit position of the code in its copy
+        const uint32_t code = (b < 7 ? cw : b < 14 ? cwm : cwh) & (3u << pos);
+        const uint32_t a = code * (1u << (LOG - pos)) + sa;                    // + letter * 4 T
+        red_counted<NF>(okm, 1u << b, a + 4u * b, val, sa + 4u * b + OFF_X);
     }
 }
 
@@ -98,7 +104,7 @@ __device__ __forceinline__ void scatter_chunk_dmq(const uint4 Q, uint32_t cw, ui
 }
 
 template <bool MINQ, int T>
-__global__ void __launch_bounds__(P7_WARPS * 32, 4) k_pileup7(const RegionDev R, const PileBatches PB) {
+__global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R, const PileBatches PB) {
     extern __shared__ __align__(16) uint8_t smem_raw7[];
     Tile7<T>& S = *reinterpret_cast<Tile7<T>*>(smem_raw7);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -181,7 +187,7 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 4) k_pileup7(const RegionDev R,
     // ---- scatter: passes of <= 4064 descriptors; a warp takes the next 16 descriptors when it is free ----
     const uint32_t sA = smem_u32(&S.A[0][0]);
     uint32_t dom_r = 0;                                          // register copy of S.dom once it is known
-    static_assert(T == 512 || T == 1024 || T == 2048, "tile size");
+    static_assert(T == 1024 || T == 2048, "tile size");
     constexpr uint32_t PASS_GRABS = P7_PASS_DESC / P7_GRAB;
     for (uint32_t p0 = 0; p0 < total_grabs; p0 += PASS_GRABS) {
         if (p0) {
@@ -190,19 +196,27 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 4) k_pileup7(const RegionDev R,
             __syncthreads();
         }
         const uint32_t p1 = min(p0 + PASS_GRABS, total_grabs);
-        while (!(R.exp_flags & 2)) {
+        // the next grab (cursor value, batch, my descriptor) is fetched before the current one is processed
+        uint32_t g_nx = p1; int b_nx = 0; Seg seg_nx = {0, 0, 0, 0};
+        auto fetch = [&]() {
             uint32_t g = 0;
             if (lane == 0) g = atomicAdd(&S.next, 1u);
             g = __shfl_sync(FULL, g, 0);
-            if (g >= p1) break;
+            g_nx = g; seg_nx = Seg{0, 0, 0, 0};
+            if (g >= p1) return;
             int b = 0;
             while (g >= S.grab0[b + 1]) b++;                      // batch of this grab (grab0 is non-decreasing)
-            const PileBatch& Bb = PB.b[b];
-            // two lanes per descriptor: lane (d, h) walks half h of the chunks of descriptor d
+            b_nx = b;
+            const uint32_t di = (g - S.grab0[b]) * P7_GRAB + (uint32_t)(lane >> 1);   // two lanes per descriptor
+            if (di < S.nseg[b]) seg_nx = PB.b[b].seg[S.slo[b] + di];
+        };
+        if (!(R.exp_flags & 2)) fetch();
+        while (g_nx < p1) {
+            const Seg mine = seg_nx;
+            const PileBatch& Bb = PB.b[b_nx];
+            fetch();
+            // lane (d, h) walks half h of the chunks of descriptor d
             const int h = lane & 1;
-            const uint32_t di = (g - S.grab0[b]) * P7_GRAB + (uint32_t)(lane >> 1);
-            Seg mine = {0, 0, 0, 0};
-            if (di < S.nseg[b]) mine = Bb.seg[S.slo[b] + di];
             const uint8_t* __restrict__ gquals = Bb.quals;
             const uint8_t* __restrict__ gbases = Bb.bases2;
             const bool nf = !(Bb.flags & 1);                      // warp-uniform: this batch is outside fragCoverage
@@ -213,9 +227,11 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 4) k_pileup7(const RegionDev R,
             const uint32_t src = mine.src + (uint32_t)(cA - mine.loc0);
             const int32_t col = cA - t0;
             const bool valid = mine.w & SEG_VALID;
-            if (n > 0 && !valid) {                                // PileUpRegion.scala:45: badPair++ on every locus
-                uint32_t xa = sA + OFF_X + 4u * (uint32_t)(col + h);
-                for (int i = h; i < n; i += 2, xa += 8) red_shared_add(xa, 0x10000u);
+            unsigned badm = __ballot_sync(FULL, n > 0 && !valid && h == 0);
+            while (badm) {                                        // PileUpRegion.scala:45: badPair++ on every locus, lane <-> locus
+                const int j = __ffs(badm) - 1; badm &= badm - 1;
+                const int32_t bn = __shfl_sync(FULL, n, j), bcol = __shfl_sync(FULL, col, j);
+                for (int i = lane; i < bn; i += 32) red_shared_add(sA + OFF_X + 4u * (uint32_t)(bcol + i), 0x10000u);
             }
             const bool live = n > 0 && valid;
             const unsigned livem = __ballot_sync(FULL, live);
@@ -230,6 +246,7 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 4) k_pileup7(const RegionDev R,
             }
             const int32_t dmq = (int32_t)mq1 - (int32_t)dom_r;
             const bool hasq = mine.w & SEG_HASQ;
+            const bool allhq = __all_sync(FULL, hasq || !live);
             const uint32_t qand = hasq ? 0x7Fu : 0u, qor = (1u << 20) | (hasq ? 0u : defq);
             const uint32_t nohq_pass = (!hasq && (int)defq >= min_qual) ? 0x01010101u : 0u;
             if (live) {
@@ -260,8 +277,8 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 4) k_pileup7(const RegionDev R,
                             const uint32_t m2 = ((v2 & 0x01010101u) * 0x01020408u) >> 24, m3 = ((v3 & 0x01010101u) * 0x01020408u) >> 24;
                             okm &= (m0 & 15u) | ((m1 & 15u) << 4) | ((m2 & 15u) << 8) | ((m3 & 15u) << 12);
                         }
-                        if (nf) scatter_chunk<true, T>(Q, cw, okm, sa, qand, qor);
-                        else scatter_chunk<false, T>(Q, cw, okm, sa, qand, qor);
+                        if (allhq) { if (nf) scatter_chunk<true, true, T>(Q, cw, okm, sa, qand, qor); else scatter_chunk<false, true, T>(Q, cw, okm, sa, qand, qor); }
+                        else { if (nf) scatter_chunk<true, false, T>(Q, cw, okm, sa, qand, qor); else scatter_chunk<false, false, T>(Q, cw, okm, sa, qand, qor); }
                         if (dmq != 0) scatter_chunk_dmq<T>(Q, cw, okm, sa, qand, qor, dmq);      // ~5 % of the reads
                         if (!more) break;
                         Q = Qn; cw = cwn; k++; qp++; cp++; sa += 64;

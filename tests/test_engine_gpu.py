@@ -19,8 +19,13 @@ def eng_cfg(cfg: po.Config) -> EngineConfig:
                         cfg.oldIndel, cfg.iupac, cfg.fixAmb)
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _kernel(pileup_kernel):
+    return pileup_kernel
+
+
 @pytest.fixture(scope="module")
-def engine():
+def engine(pileup_kernel):
     e = Engine(0)
     yield e
     e.close()

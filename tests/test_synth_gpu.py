@@ -11,8 +11,13 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _kernel(pileup_kernel):
+    return pileup_kernel
+
+
 @pytest.fixture(scope="module")
-def engine():
+def engine(pileup_kernel):
     e = Engine(0)
     yield e
     e.close()
