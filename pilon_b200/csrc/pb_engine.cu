@@ -274,6 +274,7 @@ static int compute(pb_engine* e, bool time_pileup) {
     e->dirty = true;
     CK(cudaMemsetAsync(e->scalars.p, 0, SC_BYTES, s));
 
+    if (const char* xf = getenv("PB_EXP")) R.exp_flags = atoi(xf);     // knock-out experiments (tools/knockout_timing.py)
     int32_t* reach_base = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(e->scalars.p) + SC_REACH_OFF);
     if (nb == 0) { k_fold<<<1, 32, 0, s>>>(R, reach_base, 0, 1); e->launches++; }
     for (int i0 = 0; i0 < nb; i0 += 8) {     // k_prep folds its block partials into slots that carry 8 batches' reach

@@ -130,14 +130,14 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
                 if (f > fwd) fwd = (int)(f > 0x3fffffff ? 0x3fffffff : f);
                 if (bk > back) back = (int)(bk > 0x3fffffff ? 0x3fffffff : bk);
             }
-            B.seg[k] = sg;
+            if (!(R.exp_flags & 128)) B.seg[k] = sg;
             if ((OPS_READ >> op) & 1) readOffset += len;                                         // :214
             if ((OPS_REF >> op) & 1) refOffset += len;                                           // :215
         }
         rc = 1;                                                                                  // :218
         // physCovIncr, PileUpRegion.scala:62-88
         int32_t ins = 0;
-        if (valid && !(paired && tlen <= 0)) {
+        if (valid && !(paired && tlen <= 0) && !(R.exp_flags & 64)) {
             int64_t s, e;
             if (!paired) { s = aStart < aEnd ? aStart : aEnd; e = aStart > aEnd ? aStart : aEnd; }
             else { s = aStart; e = (int64_t)aStart + tlen; }
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(128) k_indel(RegionDev R, const DevBatch* __re
                 }
             }
         if (sg.len > 0) {
-            B.seg[k] = sg;
+            if (!(R.exp_flags & 128)) B.seg[k] = sg;
             const int64_t f = (int64_t)R.start + sg.loc0 + sg.len - aStart;
             const int fi = (int)(f > 0x3fffffff ? 0x3fffffff : f);
             if (fi > B.reach[0]) atomicMax(&B.reach[0], fi);     // (never beyond the read's own aligned span in practice)
