@@ -35,6 +35,7 @@ static constexpr int P7_WARPS = 16;
 static constexpr int P7_TILE = 2048;                // loci per CTA
 static constexpr int P7_GRAB = 16;                  // descriptors per grab from the tile's cursor (two lanes per descriptor)
 static constexpr int P7_PASS_DESC = 4064;           // descriptors per pass <= 4095 (12-bit count)
+static constexpr int P7_SLOW_CAP = 512;             // per pass: segments with another mapping quality, handled after the scatter
 
 __device__ __forceinline__ void red_shared_add(uint32_t saddr, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
@@ -53,6 +54,8 @@ struct __align__(16) Tile7 {
     uint32_t slo[PB_MAXB], nseg[PB_MAXB];
     uint32_t dom;                // 0 = not chosen yet ((adjMq + 1) >= 1 always)
     uint32_t next;               // next flat grab index to hand out
+    uint32_t slow_n;             // entries in slow[] (may run past P7_SLOW_CAP: the overflow is handled inline)
+    uint2 slow[P7_SLOW_CAP];     // (batch, descriptor index) of segments whose (adjMq + 1) != dom
 };
 
 // if (bits & mask) { A word += v;  (NF) X word += 1 }   -- one predicate for both reductions
@@ -87,6 +90,20 @@ __device__ __forceinline__ void scatter_chunk(const uint4 Q, uint32_t cw, uint32
     }
 }
 
+// Which of the 16 bases of aligned chunk k are counted: inside [src, last], quality byte without the 0x80 mark, >= minQual.
+template <bool MINQ>
+__device__ __forceinline__ uint32_t chunk_mask(const uint4 Q, uint32_t k, uint32_t src, uint32_t last, uint32_t minq_add, uint32_t nohq_pass) {
+    const uint32_t lo = k == (src >> 4) ? (src & 15u) : 0u, hi = k == (last >> 4) ? (last & 15u) + 1u : 16u;
+    uint32_t v0 = ~Q.x >> 7, v1 = ~Q.y >> 7, v2 = ~Q.z >> 7, v3 = ~Q.w >> 7;
+    if (MINQ) {                                                  // reads without qualities: default_qual decides
+        v0 &= (((Q.x & 0x7F7F7F7Fu) + minq_add) >> 7) | nohq_pass; v1 &= (((Q.y & 0x7F7F7F7Fu) + minq_add) >> 7) | nohq_pass;
+        v2 &= (((Q.z & 0x7F7F7F7Fu) + minq_add) >> 7) | nohq_pass; v3 &= (((Q.w & 0x7F7F7F7Fu) + minq_add) >> 7) | nohq_pass;
+    }
+    const uint32_t m0 = ((v0 & 0x01010101u) * 0x01020408u) >> 24, m1 = ((v1 & 0x01010101u) * 0x01020408u) >> 24;
+    const uint32_t m2 = ((v2 & 0x01010101u) * 0x01020408u) >> 24, m3 = ((v3 & 0x01010101u) * 0x01020408u) >> 24;
+    return ((1u << hi) - 1u) & ~((1u << lo) - 1u) & ((m0 & 15u) | ((m1 & 15u) << 4) | ((m2 & 15u) << 8) | ((m3 & 15u) << 12));
+}
+
 // The same 16 bases for a segment whose (adjMq + 1) differs from the tile's reference value by dmq: Bq / C terms.
 template <int T>
 __device__ __forceinline__ void scatter_chunk_dmq(const uint4 Q, uint32_t cw, uint32_t okm, uint32_t sa, uint32_t qand, uint32_t qor, int32_t dmq) {
@@ -119,7 +136,7 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
     {
         uint32_t* z = reinterpret_cast<uint32_t*>(&S.A[0][0]);
         for (int i = tid; i < 10 * T; i += P7_WARPS * 32) z[i] = 0;
-        if (tid == 0) { S.dom = 0; S.next = 0; }
+        if (tid == 0) { S.dom = 0; S.next = 0; S.slow_n = 0; }
         if (warp == 0) {
             uint32_t my_slo = 0, my_nseg = 0;
             if (lane < n_batches) {
@@ -189,15 +206,42 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
     uint32_t dom_r = 0;                                          // register copy of S.dom once it is known
     static_assert(T == 1024 || T == 2048, "tile size");
     constexpr uint32_t PASS_GRABS = P7_PASS_DESC / P7_GRAB;
+    // queued segments: two per warp iteration, lane <-> chunk (16 lanes per segment)
+    auto drain_slow = [&]() {
+        const uint32_t ns = min(S.slow_n, (uint32_t)P7_SLOW_CAP);
+        const uint32_t dom = S.dom;
+        for (uint32_t e = 2u * warp + (uint32_t)(lane >> 4); e < ns; e += 2u * P7_WARPS) {
+            const uint2 en = S.slow[e];
+            const PileBatch& Bb = PB.b[en.x];
+            const Seg sg = Bb.seg[en.y];
+            const int32_t cA = sg.loc0 > t0 ? sg.loc0 : t0;
+            const int32_t cBx = sg.loc0 + sg.len < t0 + T ? sg.loc0 + sg.len : t0 + T;
+            const int32_t n = cBx - cA;
+            const uint32_t src = sg.src + (uint32_t)(cA - sg.loc0), last = src + (uint32_t)n - 1u;
+            const int32_t col = cA - t0;
+            const int32_t dmq = (int32_t)(sg.w & 0xFFFFu) - (int32_t)dom;
+            const bool hasq = sg.w & SEG_HASQ;
+            const uint32_t qand = hasq ? 0x7Fu : 0u, qor = hasq ? 0u : defq;
+            const uint32_t nohq_pass = (!hasq && (int)defq >= min_qual) ? 0x01010101u : 0u;
+            const uint4* qp = reinterpret_cast<const uint4*>(Bb.quals);
+            const uint32_t* cp = reinterpret_cast<const uint32_t*>(Bb.bases2);
+            for (uint32_t k = (src >> 4) + (uint32_t)(lane & 15); k <= (last >> 4); k += 16) {
+                const uint4 Q = qp[k]; const uint32_t cw = cp[k];
+                const uint32_t okm = chunk_mask<MINQ>(Q, k, src, last, minq_add, nohq_pass);
+                scatter_chunk_dmq<T>(Q, cw, okm, sA + 4u * (uint32_t)(col + (int32_t)(16u * k - src)), qand, qor, dmq);
+            }
+        }
+    };
+
     for (uint32_t p0 = 0; p0 < total_grabs; p0 += PASS_GRABS) {
         if (p0) {
-            __syncthreads(); fold();
-            if (tid == 0) S.next = p0;
+            fold();
+            if (tid == 0) { S.next = p0; S.slow_n = 0; }
             __syncthreads();
         }
         const uint32_t p1 = min(p0 + PASS_GRABS, total_grabs);
         // the next grab (cursor value, batch, my descriptor) is fetched before the current one is processed
-        uint32_t g_nx = p1; int b_nx = 0; Seg seg_nx = {0, 0, 0, 0};
+        uint32_t g_nx = p1, sidx_nx = 0; int b_nx = 0; Seg seg_nx = {0, 0, 0, 0};
         auto fetch = [&]() {
             uint32_t g = 0;
             if (lane == 0) g = atomicAdd(&S.next, 1u);
@@ -208,12 +252,14 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
             while (g >= S.grab0[b + 1]) b++;                      // batch of this grab (grab0 is non-decreasing)
             b_nx = b;
             const uint32_t di = (g - S.grab0[b]) * P7_GRAB + (uint32_t)(lane >> 1);   // two lanes per descriptor
-            if (di < S.nseg[b]) seg_nx = PB.b[b].seg[S.slo[b] + di];
+            sidx_nx = S.slo[b] + di;
+            if (di < S.nseg[b]) seg_nx = PB.b[b].seg[sidx_nx];
         };
         if (!(R.exp_flags & 2)) fetch();
         while (g_nx < p1) {
             const Seg mine = seg_nx;
-            const PileBatch& Bb = PB.b[b_nx];
+            const int b_cur = b_nx; const uint32_t sidx = sidx_nx;
+            const PileBatch& Bb = PB.b[b_cur];
             fetch();
             // lane (d, h) walks half h of the chunks of descriptor d
             const int h = lane & 1;
@@ -245,6 +291,14 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
                 dom_r = old ? old : first;
             }
             const int32_t dmq = (int32_t)mq1 - (int32_t)dom_r;
+            // a segment with another mapping quality (~5 % of the reads) is queued: its Bq / C terms are added after the
+            // scatter, lane <-> chunk, instead of dragging the whole warp through a second reduction block here
+            int inl = 0;
+            if (live && dmq != 0 && h == 0) {
+                const uint32_t e = atomicAdd(&S.slow_n, 1u);
+                if (e < P7_SLOW_CAP) S.slow[e] = make_uint2((uint32_t)b_cur, sidx); else inl = 1;
+            }
+            inl = __shfl_sync(FULL, inl, lane & ~1);
             const bool hasq = mine.w & SEG_HASQ;
             const bool allhq = __all_sync(FULL, hasq || !live);
             const uint32_t qand = hasq ? 0x7Fu : 0u, qor = (1u << 20) | (hasq ? 0u : defq);
@@ -264,30 +318,20 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
                         uint4 Qn = make_uint4(0, 0, 0, 0); uint32_t cwn = 0;
                         const bool more = k < k1;
                         if (more) { Qn = qp[1]; cwn = cp[1]; }                           // next chunk's loads in flight
-                        // which of the 16 bases are counted: inside [src, last], quality byte without the 0x80 mark, >= minQual
-                        const uint32_t lo = k == c0 ? (src & 15u) : 0u, hi = k == c1 ? (last & 15u) + 1u : 16u;
-                        uint32_t okm = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-                        {
-                            uint32_t v0 = ~Q.x >> 7, v1 = ~Q.y >> 7, v2 = ~Q.z >> 7, v3 = ~Q.w >> 7;
-                            if (MINQ) {                                                  // reads without qualities: default_qual decides
-                                v0 &= (((Q.x & 0x7F7F7F7Fu) + minq_add) >> 7) | nohq_pass; v1 &= (((Q.y & 0x7F7F7F7Fu) + minq_add) >> 7) | nohq_pass;
-                                v2 &= (((Q.z & 0x7F7F7F7Fu) + minq_add) >> 7) | nohq_pass; v3 &= (((Q.w & 0x7F7F7F7Fu) + minq_add) >> 7) | nohq_pass;
-                            }
-                            const uint32_t m0 = ((v0 & 0x01010101u) * 0x01020408u) >> 24, m1 = ((v1 & 0x01010101u) * 0x01020408u) >> 24;
-                            const uint32_t m2 = ((v2 & 0x01010101u) * 0x01020408u) >> 24, m3 = ((v3 & 0x01010101u) * 0x01020408u) >> 24;
-                            okm &= (m0 & 15u) | ((m1 & 15u) << 4) | ((m2 & 15u) << 8) | ((m3 & 15u) << 12);
-                        }
+                        const uint32_t okm = chunk_mask<MINQ>(Q, k, src, last, minq_add, nohq_pass);
                         if (allhq) { if (nf) scatter_chunk<true, true, T>(Q, cw, okm, sa, qand, qor); else scatter_chunk<false, true, T>(Q, cw, okm, sa, qand, qor); }
                         else { if (nf) scatter_chunk<true, false, T>(Q, cw, okm, sa, qand, qor); else scatter_chunk<false, false, T>(Q, cw, okm, sa, qand, qor); }
-                        if (dmq != 0) scatter_chunk_dmq<T>(Q, cw, okm, sa, qand, qor, dmq);      // ~5 % of the reads
+                        if (inl) scatter_chunk_dmq<T>(Q, cw, okm, sa, qand, qor, dmq);           // slow list full (deep pile-ups)
                         if (!more) break;
                         Q = Qn; cw = cwn; k++; qp++; cp++; sa += 64;
                     }
                 }
             }
         }
+        __syncthreads();
+        drain_slow();
+        __syncthreads();
     }
-    __syncthreads();
 
     // ---- epilogue: warp per 32-locus window of the tile ----
     const uint32_t dom = S.dom;
