@@ -273,13 +273,24 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
             const uint32_t src = mine.src + (uint32_t)(cA - mine.loc0);
             const int32_t col = cA - t0;
             const bool valid = mine.w & SEG_VALID;
+            const bool live = n > 0 && valid;
+            // aligned 16-base chunks c0..c1 of the batch's base stream (chunk k = bases [16 k, 16 k + 16)); my half of them.
+            // The first chunk's loads are issued now, the rest of the per-grab set-up runs under their latency.
+            const uint32_t last = src + (uint32_t)n - 1u;
+            const uint32_t c0 = src >> 4, c1 = last >> 4, mid = c0 + ((c1 - c0 + 2u) >> 1);
+            uint32_t k = h ? mid : c0;
+            const uint32_t k1 = h ? c1 : mid - 1u;
+            const bool work = live && k <= k1;
+            const uint4* qp = reinterpret_cast<const uint4*>(gquals) + k;
+            const uint32_t* cp = reinterpret_cast<const uint32_t*>(gbases) + k;
+            uint4 Q = make_uint4(0, 0, 0, 0); uint32_t cw = 0;
+            if (work) { Q = *qp; cw = *cp; }
             unsigned badm = __ballot_sync(FULL, n > 0 && !valid && h == 0);
             while (badm) {                                        // PileUpRegion.scala:45: badPair++ on every locus, lane <-> locus
                 const int j = __ffs(badm) - 1; badm &= badm - 1;
                 const int32_t bn = __shfl_sync(FULL, n, j), bcol = __shfl_sync(FULL, col, j);
                 for (int i = lane; i < bn; i += 32) red_shared_add(sA + OFF_X + 4u * (uint32_t)(bcol + i), 0x10000u);
             }
-            const bool live = n > 0 && valid;
             const unsigned livem = __ballot_sync(FULL, live);
             if (livem == 0) continue;
             const uint32_t mq1 = mine.w & 0xFFFFu;
@@ -303,17 +314,9 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
             const bool allhq = __all_sync(FULL, hasq || !live);
             const uint32_t qand = hasq ? 0x7Fu : 0u, qor = (1u << 20) | (hasq ? 0u : defq);
             const uint32_t nohq_pass = (!hasq && (int)defq >= min_qual) ? 0x01010101u : 0u;
-            if (live) {
-                // aligned 16-base chunks c0..c1 of the batch's base stream (chunk k = bases [16 k, 16 k + 16)); my half of them
-                const uint32_t last = src + (uint32_t)n - 1u;
-                const uint32_t c0 = src >> 4, c1 = last >> 4, mid = c0 + ((c1 - c0 + 2u) >> 1);
-                uint32_t k = h ? mid : c0;
-                const uint32_t k1 = h ? c1 : mid - 1u;
-                if (k <= k1) {
-                    const uint4* qp = reinterpret_cast<const uint4*>(gquals) + k;
-                    const uint32_t* cp = reinterpret_cast<const uint32_t*>(gbases) + k;
+            if (work) {
+                {
                     uint32_t sa = sA + 4u * (uint32_t)(col + (int32_t)(16u * k - src));      // A[0][locus of base 16 k] (virtual before col)
-                    uint4 Q = *qp; uint32_t cw = *cp;
                     for (;;) {
                         uint4 Qn = make_uint4(0, 0, 0, 0); uint32_t cwn = 0;
                         const bool more = k < k1;
