@@ -162,11 +162,15 @@ def device_batch(torch, c, dev):
 
 
 def pin_batch(torch, c):
-    """cudaHostRegister every array of a host batch so that H2D copies are true async DMA."""
+    """cudaHostRegister every array of a host batch that the engine uploads, so that H2D copies are true async
+    DMA; returns the bytes uploaded per pass (4-bit quality codes replace the quality bytes when the batch has them)."""
     rt = torch.cuda.cudart()
     n = 0
     for name, count, width in _BATCH_FIELDS:
         nb = _field_bytes(c, count, width)
+        if name == "quals" and c.quals4:
+            nb = int(c.n_seq) // 2
+            name = "quals4"
         if nb:
             rt.cudaHostRegister(getattr(c, name), nb, 0)
             n += nb
@@ -335,6 +339,11 @@ def run_gpu_arm(args):
         e.close()
     engines, keep = [], []
     torch.cuda.empty_cache()
+    if args.quals8:
+        for r in regions:
+            for b in r.batches:
+                b.c.quals4 = None
+    q4 = all(bool(b.c.quals4) for r in regions for b in r.batches)
     h2d = sum(pin_batch(torch, b.c) for r in regions for b in r.batches) + sum(r.size + 1 for r in regions)
     planes = FIX_PLANES if args.planes == "fix" else None
     n_workers = 3
@@ -429,7 +438,9 @@ def run_gpu_arm(args):
                           "aligned_bases_per_gpu": total_aligned, "mean_depth": depth, "l2": "inputs_exceed_l2 (%.1f GB per step)" % (h2d / 1e9),
                           "timing": "CUDA events: first launch of the timed steps -> last engine stream done, regions launched by %d host threads onto one stream per region; "
                                     "sequential_ms_per_step = sum of per-region event intervals with one region at a time (the pileup kernel's launches are timed in that pass)" % args.host_threads,
-                          "e2e_planes": args.planes},
+                          "e2e_planes": args.planes,
+                          "e2e_quals": ("4-bit codes + 16-entry table (the workload has <= 16 distinct quality bytes), expanded on the device"
+                                        if q4 else "1 byte per base")},
                "wall_ms_per_step": wall_step_ms, "sequential_ms_per_step": seq_step_ms,
                "e2e": {"value": job_aligned / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": job_h2d, "d2h_bytes_per_step": job_d2h,
                        "ms_per_step": 1e3 * e2e_sec, "streams_per_gpu": n_workers},
@@ -455,6 +466,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrinks the genome (not the depth); 1.0 = the BASELINE config")
     ap.add_argument("--planes", default="fix", choices=["fix", "vcf"], help="per-locus results copied back in the e2e arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quals8", action="store_true", help="e2e arm: upload one quality byte per base even when the batch "
+                    "offers the 4-bit transport (pb_batch.quals4)")
     ap.add_argument("--host-threads", type=int, default=4, help="host threads feeding region passes to the GPU")
     args = ap.parse_args()
     if args.impl == "reference":

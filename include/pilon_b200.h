@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB_ABI_VERSION 1
+#define PB_ABI_VERSION 2
 
 /* ---- status codes ---------------------------------------------------------------------- */
 #define PB_OK                 0
@@ -99,6 +99,13 @@ typedef struct pb_batch {
     const uint8_t*  exc_qual;   /* [n_exc] original quality byte                              */
     int32_t mem;                /* PB_MEM_HOST | PB_MEM_DEVICE                                */
     int32_t reserved;
+    /* Optional compact transport of `quals` for PB_MEM_HOST batches (the end-to-end path is PCIe-bound):
+     * when quals4 is non-NULL the engine uploads these n_seq / 2 bytes instead of `quals` and expands
+     * them on the device, quals[i] = qual_lut[(quals4[i >> 1] >> (4 * (i & 1))) & 15].  Possible whenever
+     * a batch uses at most 16 distinct quality bytes (binned instrument qualities); pb_packer_view fills
+     * it in automatically, else leaves it NULL.  `quals` may then be NULL for the engine. */
+    const uint8_t*  quals4;     /* [n_seq / 2] or NULL                                        */
+    uint8_t qual_lut[16];       /* code -> quality byte (0..127, or 0x80)                     */
 } pb_batch;
 
 /* ---- per-locus call record (PileUp.BaseCall, PileUp.scala:132-167) -----------------------

@@ -215,6 +215,21 @@ static int stage(pb_engine* e, HostBatch& hb, const T* src, size_t n, int mem, c
     return PB_OK;
 }
 
+// 4-bit quality codes -> quality bytes (pb_batch.quals4).  A thread expands 16 bases: the low / high half of an input
+// word is directly a PRMT selector (one code per nibble); codes 0..7 and 8..15 come from two 8-byte pools, bit 3 picks.
+__global__ void __launch_bounds__(256) k_unpack_quals4(const uint2* __restrict__ in, uint4* __restrict__ out, size_t groups,
+                                                       uint32_t l0, uint32_t l1, uint32_t l2, uint32_t l3) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= groups) return;
+    const uint2 w = in[i];
+    auto four = [&](uint32_t sel16) {
+        const uint32_t lo = __byte_perm(l0, l1, sel16 & 0x7777u), hi = __byte_perm(l2, l3, sel16 & 0x7777u);
+        const uint32_t m = __byte_perm(0x0000FF00u, 0u, (sel16 >> 3) & 0x1111u);          // 0xFF where the code is >= 8
+        return (hi & m) | (lo & ~m);
+    };
+    out[i] = make_uint4(four(w.x & 0xFFFFu), four(w.x >> 16), four(w.y & 0xFFFFu), four(w.y >> 16));
+}
+
 extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, int long_read_type) {
     if (!e || !b) return fail(PB_ERR_INVALID, "null argument");
     if (!e->in_region) return fail(PB_ERR_INVALID, "pb_region_begin has not been called");
@@ -231,7 +246,23 @@ extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, in
     int rc;
 #define ST(field, count) if ((rc = stage(e, hb, b->field, (size_t)(count), b->mem, &d.field)) != PB_OK) return rc
     ST(pos, n); ST(tlen, n); ST(read_len, n); ST(mapq, n); ST(flags, n); ST(cigar_off, n + 1);
-    ST(cigar, b->n_cigar); ST(seq_off, n); ST(quals, b->n_seq); ST(bases2, b->n_seq / 4);
+    ST(cigar, b->n_cigar); ST(seq_off, n); ST(bases2, b->n_seq / 4);
+    if (b->mem == PB_MEM_HOST && b->quals4) {          // compact transport: upload 4-bit codes, expand on the device
+        const size_t groups = ((size_t)b->n_seq + 15) / 16;
+        void *pin = nullptr, *pout = nullptr;
+        CK(cudaMallocAsync(&pin, groups * 8 + 64, e->stream)); hb.owned.push_back(pin);
+        CK(cudaMallocAsync(&pout, groups * 16 + 64, e->stream)); hb.owned.push_back(pout);
+        if (b->n_seq) {
+            CK(cudaMemcpyAsync(pin, b->quals4, (size_t)b->n_seq / 2, cudaMemcpyHostToDevice, e->stream));
+            uint32_t l[4]; memcpy(l, b->qual_lut, 16);
+            k_unpack_quals4<<<(unsigned)((groups + 255) / 256), 256, 0, e->stream>>>((const uint2*)pin, (uint4*)pout, groups, l[0], l[1], l[2], l[3]);
+            e->launches++;
+        }
+        d.quals = (const uint8_t*)pout;
+    } else {
+        if (!b->quals && b->n_seq) return fail(PB_ERR_INVALID, "batch has neither quals nor quals4");
+        ST(quals, b->n_seq);
+    }
     ST(exc_idx, b->n_exc); ST(exc_base, b->n_exc); ST(exc_qual, b->n_exc);
 #undef ST
     void* p = nullptr;
@@ -505,8 +536,16 @@ extern "C" int pb_region_finish(pb_engine* e, pb_region_result* res, int32_t* co
 // ---------------------------------------------------------------------------------------------
 struct pb_packer {
     std::vector<int32_t> pos, tlen, read_len;
-    std::vector<uint8_t> mapq, flags, quals, bases2, exc_base, exc_qual;
+    std::vector<uint8_t> mapq, flags, quals, bases2, exc_base, exc_qual, quals4;
     std::vector<uint32_t> cigar_off{0}, cigar, seq_off, exc_idx;
+    // alphabet of the stored quality bytes: at most 16 distinct values -> the 4-bit transport is possible
+    uint8_t code_of[256]; uint8_t lut[16]; int n_codes = 0; bool q4_ok = true;
+    pb_packer() { memset(code_of, 0xFF, sizeof(code_of)); memset(lut, 0, sizeof(lut)); note(0); }
+    void note(uint8_t v) {
+        if (code_of[v] != 0xFF || !q4_ok) return;
+        if (n_codes == 16) { q4_ok = false; return; }
+        code_of[v] = (uint8_t)n_codes; lut[n_codes++] = v;
+    }
 };
 
 extern "C" int pb_packer_create(pb_packer** out) { if (!out) return fail(PB_ERR_INVALID, "null"); *out = new pb_packer(); return PB_OK; }
@@ -515,7 +554,8 @@ extern "C" int pb_packer_reset(pb_packer* p) {
     if (!p) return fail(PB_ERR_INVALID, "null");
     p->pos.clear(); p->tlen.clear(); p->read_len.clear(); p->mapq.clear(); p->flags.clear(); p->quals.clear();
     p->bases2.clear(); p->exc_base.clear(); p->exc_qual.clear(); p->cigar_off.assign(1, 0); p->cigar.clear();
-    p->seq_off.clear(); p->exc_idx.clear();
+    p->seq_off.clear(); p->exc_idx.clear(); p->quals4.clear();
+    memset(p->code_of, 0xFF, sizeof(p->code_of)); memset(p->lut, 0, sizeof(p->lut)); p->n_codes = 0; p->q4_ok = true; p->note(0);
     return PB_OK;
 }
 
@@ -544,6 +584,7 @@ extern "C" int pb_packer_add(pb_packer* p, int32_t pos, int32_t tlen, int32_t ma
             p->quals[i] = 0x80;
             p->exc_idx.push_back((uint32_t)i); p->exc_base.push_back(c); p->exc_qual.push_back(q);
         } else p->quals[i] = q;
+        p->note(p->quals[i]);
         if (code > 0) p->bases2[i >> 2] |= (uint8_t)(code << (2 * (i & 3)));
     }
     return PB_OK;
@@ -572,5 +613,11 @@ extern "C" int pb_packer_view(pb_packer* p, pb_batch* b) {
     b->cigar = p->cigar.data(); b->seq_off = p->seq_off.data(); b->quals = p->quals.data();
     b->bases2 = p->bases2.data(); b->exc_idx = p->exc_idx.data(); b->exc_base = p->exc_base.data();
     b->exc_qual = p->exc_qual.data(); b->mem = PB_MEM_HOST;
+    if (p->q4_ok) {                                     // binned qualities: offer the 4-bit transport as well
+        const size_t ns = p->quals.size();
+        p->quals4.assign(ns / 2 + 16, 0);
+        for (size_t i = 0; i < ns; i++) p->quals4[i >> 1] |= (uint8_t)(p->code_of[p->quals[i]] << (4 * (i & 1)));
+        b->quals4 = p->quals4.data(); memcpy(b->qual_lut, p->lut, 16);
+    }
     return PB_OK;
 }

@@ -153,6 +153,8 @@ struct Gen {
     std::vector<int32_t> pos, tlen, read_len;
     std::vector<uint8_t> mapq, flags, quals, bases2, exc_base, exc_qual;
     std::vector<uint32_t> cigar_off, cigar, seq_off, exc_idx;
+    std::vector<uint8_t> quals4;            // 4-bit transport of quals (pb_batch.quals4) when <= 16 distinct bytes occur
+    uint8_t lut[16] = {0}; bool q4_ok = false;
     int64_t aligned = 0;
 };
 
@@ -319,6 +321,27 @@ void* ps_generate(const ps_params* Pp, int64_t lo, int64_t hi) {
         g->exc_qual.insert(g->exc_qual.end(), tq[t].begin(), tq[t].end());
         g->aligned += al[t];
     }
+    {   // the same alphabet rule as pb_packer_view: at most 16 distinct stored quality bytes -> 4-bit codes
+        bool seen[256] = {false};
+        const int64_t ns = (int64_t)g->quals.size();
+#pragma omp parallel
+        {
+            bool mine[256] = {false};
+#pragma omp for schedule(static)
+            for (int64_t i = 0; i < ns; i++) mine[g->quals[i]] = true;
+#pragma omp critical
+            for (int v = 0; v < 256; v++) seen[v] = seen[v] || mine[v];
+        }
+        uint8_t code_of[256]; int n_codes = 0; seen[0] = true;
+        for (int v = 0; v < 256; v++) if (seen[v]) { if (n_codes < 16) { code_of[v] = (uint8_t)n_codes; g->lut[n_codes] = (uint8_t)v; } n_codes++; }
+        g->q4_ok = n_codes <= 16;
+        if (g->q4_ok) {
+            g->quals4.assign((size_t)ns / 2 + 16, 0);
+#pragma omp parallel for schedule(static)
+            for (int64_t j = 0; j < ns / 2; j++)
+                g->quals4[j] = (uint8_t)(code_of[g->quals[2 * j]] | (code_of[g->quals[2 * j + 1]] << 4));
+        }
+    }
     return g;
 }
 
@@ -332,6 +355,7 @@ void ps_view(void* h, pb_batch* b, int64_t* aligned) {
     b->cigar = g->cigar.data(); b->seq_off = g->seq_off.data(); b->quals = g->quals.data();
     b->bases2 = g->bases2.data(); b->exc_idx = g->exc_idx.data(); b->exc_base = g->exc_base.data();
     b->exc_qual = g->exc_qual.data(); b->mem = PB_MEM_HOST;
+    if (g->q4_ok) { b->quals4 = g->quals4.data(); memcpy(b->qual_lut, g->lut, 16); }
     if (aligned) *aligned = g->aligned;
 }
 

@@ -10,6 +10,7 @@ getAlignmentStart is 1-based.
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
 from dataclasses import dataclass
 from typing import Iterable, List, Optional, Sequence
 
@@ -39,6 +40,8 @@ class ReadBatch:
     exc_idx: np.ndarray
     exc_base: np.ndarray
     exc_qual: np.ndarray
+    quals4: Optional[np.ndarray] = None        # pb_batch.quals4: 4-bit codes, two bases per byte (compact H2D transport)
+    qual_lut: Optional[np.ndarray] = None      # pb_batch.qual_lut: code -> quality byte
 
     @property
     def n_reads(self) -> int:
@@ -58,9 +61,29 @@ class ReadBatch:
             arr = getattr(self, name)
             assert arr.flags["C_CONTIGUOUS"]
             setattr(b, name, arr.ctypes.data)
+        if self.quals4 is not None:
+            assert self.quals4.flags["C_CONTIGUOUS"] and self.quals4.shape[0] >= self.quals.shape[0] // 2
+            b.quals4 = self.quals4.ctypes.data
+            for i in range(16):
+                b.qual_lut[i] = int(self.qual_lut[i])
         b.mem = capi.PB_MEM_HOST
         b._keepalive = self
         return b
+
+    def with_quals4(self) -> "ReadBatch":
+        """Adds the 4-bit quality transport when the batch uses at most 16 distinct quality bytes
+        (what pb_packer_view does natively); returns self unchanged otherwise."""
+        vals = np.unique(np.concatenate([self.quals, np.zeros(1, np.uint8)]))
+        if vals.shape[0] > 16:
+            return self
+        lut = np.zeros(16, np.uint8)
+        lut[:vals.shape[0]] = vals
+        code = np.zeros(256, np.uint8)
+        code[vals] = np.arange(vals.shape[0], dtype=np.uint8)
+        c = code[self.quals]
+        q4 = np.zeros(self.quals.shape[0] // 2 + 16, np.uint8)
+        q4[:self.quals.shape[0] // 2] = c[0::2] | (c[1::2] << 4)
+        return dataclasses.replace(self, quals4=q4, qual_lut=lut)
 
     def slice_reads(self, lo: int, hi: int) -> "ReadBatch":
         """Sub-batch of reads [lo, hi) (re-based offsets); used to split a region's reads."""

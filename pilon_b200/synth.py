@@ -38,7 +38,8 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(SRC):
+    hdr = os.path.join(os.path.dirname(HERE), "include", "pilon_b200.h")      # pb_batch's layout lives there
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
         subprocess.check_call(["g++", "-O3", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-o", LIB, SRC])
     return LIB
 
