@@ -35,7 +35,7 @@ static constexpr int P7_WARPS = 16;
 static constexpr int P7_TILE = 2048;                // loci per CTA
 static constexpr int P7_GRAB = 16;                  // descriptors per grab from the tile's cursor (two lanes per descriptor)
 static constexpr int P7_PASS_DESC = 4064;           // descriptors per pass <= 4095 (12-bit count)
-static constexpr int P7_SLOW_CAP = 512;             // per pass: segments with another mapping quality, handled after the scatter
+static constexpr int P7_SLOW_CAP = 32;              // per warp and pass: queued segments with another mapping quality
 
 __device__ __forceinline__ void red_shared_add(uint32_t saddr, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
@@ -54,8 +54,7 @@ struct __align__(16) Tile7 {
     uint32_t slo[PB_MAXB], nseg[PB_MAXB];
     uint32_t dom;                // 0 = not chosen yet ((adjMq + 1) >= 1 always)
     uint32_t next;               // next flat grab index to hand out
-    uint32_t slow_n;             // entries in slow[] (may run past P7_SLOW_CAP: the overflow is handled inline)
-    uint2 slow[P7_SLOW_CAP];     // (batch, descriptor index) of segments whose (adjMq + 1) != dom
+    uint2 slow[P7_WARPS][P7_SLOW_CAP];   // per warp: (batch, descriptor index) of segments whose (adjMq + 1) != dom
 };
 
 // if (bits & mask) { A word += v;  (NF) X word += 1 }   -- one predicate for both reductions
@@ -136,7 +135,7 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
     {
         uint32_t* z = reinterpret_cast<uint32_t*>(&S.A[0][0]);
         for (int i = tid; i < 10 * T; i += P7_WARPS * 32) z[i] = 0;
-        if (tid == 0) { S.dom = 0; S.next = 0; S.slow_n = 0; }
+        if (tid == 0) { S.dom = 0; S.next = 0; }
         if (warp == 0) {
             uint32_t my_slo = 0, my_nseg = 0;
             if (lane < n_batches) {
@@ -206,12 +205,14 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
     uint32_t dom_r = 0;                                          // register copy of S.dom once it is known
     static_assert(T == 1024 || T == 2048, "tile size");
     constexpr uint32_t PASS_GRABS = P7_PASS_DESC / P7_GRAB;
-    // queued segments: two per warp iteration, lane <-> chunk (16 lanes per segment)
+    // A warp drains its own queue right after its last grab of a pass (no barrier needed: the reductions commute):
+    // two queued segments per iteration, lane <-> chunk (16 lanes per segment)
+    uint32_t slow_n = 0;                                         // warp-uniform: entries in S.slow[warp]
     auto drain_slow = [&]() {
-        const uint32_t ns = min(S.slow_n, (uint32_t)P7_SLOW_CAP);
-        const uint32_t dom = S.dom;
-        for (uint32_t e = 2u * warp + (uint32_t)(lane >> 4); e < ns; e += 2u * P7_WARPS) {
-            const uint2 en = S.slow[e];
+        __syncwarp();
+        const uint32_t dom = dom_r;
+        for (uint32_t e = (uint32_t)(lane >> 4); e < slow_n; e += 2u) {
+            const uint2 en = S.slow[warp][e];
             const PileBatch& Bb = PB.b[en.x];
             const Seg sg = Bb.seg[en.y];
             const int32_t cA = sg.loc0 > t0 ? sg.loc0 : t0;
@@ -231,12 +232,14 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
                 scatter_chunk_dmq<T>(Q, cw, okm, sA + 4u * (uint32_t)(col + (int32_t)(16u * k - src)), qand, qor, dmq);
             }
         }
+        slow_n = 0;
+        __syncwarp();
     };
 
     for (uint32_t p0 = 0; p0 < total_grabs; p0 += PASS_GRABS) {
         if (p0) {
             fold();
-            if (tid == 0) { S.next = p0; S.slow_n = 0; }
+            if (tid == 0) S.next = p0;
             __syncthreads();
         }
         const uint32_t p1 = min(p0 + PASS_GRABS, total_grabs);
@@ -305,9 +308,13 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
             // a segment with another mapping quality (~5 % of the reads) is queued: its Bq / C terms are added after the
             // scatter, lane <-> chunk, instead of dragging the whole warp through a second reduction block here
             int inl = 0;
-            if (live && dmq != 0 && h == 0) {
-                const uint32_t e = atomicAdd(&S.slow_n, 1u);
-                if (e < P7_SLOW_CAP) S.slow[e] = make_uint2((uint32_t)b_cur, sidx); else inl = 1;
+            {
+                const unsigned qm = __ballot_sync(FULL, live && dmq != 0 && h == 0);
+                if (qm) {
+                    const uint32_t e = slow_n + (uint32_t)__popc(qm & ((1u << lane) - 1u));
+                    if ((qm >> lane) & 1u) { if (e < P7_SLOW_CAP) S.slow[warp][e] = make_uint2((uint32_t)b_cur, sidx); else inl = 1; }
+                    slow_n = min(slow_n + (uint32_t)__popc(qm), (uint32_t)P7_SLOW_CAP);
+                }
             }
             inl = __shfl_sync(FULL, inl, lane & ~1);
             const bool hasq = mine.w & SEG_HASQ;
@@ -331,7 +338,6 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
                 }
             }
         }
-        __syncthreads();
         drain_slow();
         __syncthreads();
     }
