@@ -253,3 +253,46 @@ def test_4bit_quality_transport_matches_byte_transport(engine):
     engine.finish(res4, ins4)
     H.assert_results_equal(res4, ref, "4-bit transport vs C oracle")
     assert np.array_equal(ins4[0], ins_ref[0])
+
+
+def test_more_batches_than_the_by_value_table_holds(engine):
+    """More than 20 BAMs in one region (the kernels' by-value batch table holds 20): the engine falls back to the
+    kernel generation that walks a device-side batch list; results stay bit-identical."""
+    contig, start, stop, reads = H.clean_case(21, n=9000, start=301, stop=7000, depth=40, n_sites=12)
+    rng = random.Random(21)
+    k = 27
+    groups = [[] for _ in range(k)]
+    for r in reads:
+        groups[rng.randrange(k)].append(r)
+    run_both(engine, contig, start, stop, [(g, i % 3 != 0) for i, g in enumerate(groups)])
+
+
+def test_device_resident_batches_match_host_batches(engine):
+    """PB_MEM_DEVICE: arrays already on the GPU are used in place (the bench's HBM-resident arm)."""
+    import ctypes as C
+    import torch
+    contig, start, stop, reads = H.clean_case(22, n=9000, start=301, stop=7000, depth=30, n_sites=10)
+    packed = pack_records(reads)
+    ref, ins_ref = H.run_c_oracle(contig, start, stop, [(packed, True)])
+    host = packed.to_c()
+    dev = capi.pb_batch()
+    dev.n_reads, dev.n_cigar, dev.n_seq, dev.n_exc = host.n_reads, host.n_cigar, host.n_seq, host.n_exc
+    keep = []
+    for name in ("pos", "tlen", "read_len", "mapq", "flags", "cigar_off", "cigar", "seq_off", "quals", "bases2",
+                 "exc_idx", "exc_base", "exc_qual"):
+        a = getattr(packed, name)
+        t = torch.zeros(a.nbytes + 64, dtype=torch.uint8, device="cuda:0")      # readable 16 bytes past the end
+        if a.nbytes:
+            t[:a.nbytes].copy_(torch.from_numpy(a.view(np.uint8).reshape(-1)))
+        keep.append(t)
+        setattr(dev, name, t.data_ptr())
+    dev.mem = capi.PB_MEM_DEVICE
+    torch.cuda.synchronize()
+    from pilon_b200.packing import ResultBuffers
+    engine.region_begin(contig, start, stop)
+    engine.add_batch(dev, True)
+    res = ResultBuffers(stop + 1 - start, None, 1 << 16, 1 << 20)
+    ins = [np.zeros(packed.n_reads, np.int32)]
+    engine.finish(res, ins)
+    H.assert_results_equal(res, ref, "device-resident batch vs C oracle")
+    assert np.array_equal(ins[0], ins_ref[0])
