@@ -11,7 +11,7 @@
 #include <string>
 #include <vector>
 
-#include <cub/device/device_merge_sort.cuh>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "pb_pileup7.cuh"
 
@@ -71,7 +71,7 @@ struct pb_engine {
     DBuf ref, rare, gplane[2], rare_bits, pc_diff, block_sums, scalars;
     DBuf o_cnt, o_qs, o_i32[12], o_wq, o_wmq, o_flags, o_call;
     // event buffers
-    DBuf ev_key, ev, perm, groups, cand, work, spill_scratch, str_pool, cub_tmp, dbg;
+    DBuf ev_key, ev, perm, sort_buf, groups, cand, work, spill_scratch, str_pool, cub_tmp, dbg;
     Scalars* h_sc = nullptr;         // pinned
     int64_t launches = 0;
     float last_pileup_ms = 0.f;
@@ -277,7 +277,6 @@ extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, in
 // ---------------------------------------------------------------------------------------------
 // the compute pipeline (no host<->device data copies except one 80-byte scalar read-back)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_iota(uint32_t* p, uint32_t n) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; }
 
 static int compute(pb_engine* e, bool time_pileup) {
     cudaStream_t s = e->stream;
@@ -289,6 +288,7 @@ static int compute(pb_engine* e, bool time_pileup) {
     CK(e->ev_key.ensure((size_t)cap * sizeof(EventKey) + 16, false, s));
     CK(e->ev.ensure((size_t)cap * sizeof(Event) + 16, false, s));
     CK(e->perm.ensure((size_t)cap * 4 + 16, false, s));
+    CK(e->sort_buf.ensure((size_t)cap * 12 + 64, false, s));       // radix sort: keys in, keys out, indices out
     CK(e->groups.ensure((size_t)cap * sizeof(Group) + 16, false, s));
     CK(e->cand.ensure((size_t)cap * sizeof(int4) + 16, false, s));
     CK(e->work.ensure((size_t)cap * sizeof(int4) + 16, false, s));
@@ -342,12 +342,19 @@ static int compute(pb_engine* e, bool time_pileup) {
         if (nb) CK(cudaMemcpyAsync(e->d_batches.p, img.data(), sizeof(DevBatch) * nb, cudaMemcpyHostToDevice, s));
     }
     if (n_ev) {
-        k_iota<<<(n_ev + 255) / 256, 256, 0, s>>>(e->perm.as<uint32_t>(), n_ev); e->launches++;
+        // events -> (locus, kind) groups: radix sort of 32-bit keys (only the bits a locus index can have), then k_groups
+        uint32_t* keys_in = e->sort_buf.as<uint32_t>();
+        uint32_t* keys_out = keys_in + cap + 4;
+        uint32_t* idx_out = keys_out + cap + 4;
+        uint32_t* idx_in = e->perm.as<uint32_t>();
+        k_event_keys<<<(n_ev + 255) / 256, 256, 0, s>>>(R.ev_key, keys_in, idx_in, n_ev); e->launches++;
+        int end_bit = 1;
+        while (end_bit < 32 && (((uint64_t)R.size << 1) >> end_bit)) end_bit++;
         size_t tmp = 0;
-        CK(cub::DeviceMergeSort::SortPairs(nullptr, tmp, R.ev_key, e->perm.as<uint32_t>(), (int64_t)n_ev, EventKeyLess(), s));
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys_in, keys_out, idx_in, idx_out, (int64_t)n_ev, 0, end_bit, s));
         CK(e->cub_tmp.ensure(tmp + 16, false, s));
-        CK(cub::DeviceMergeSort::SortPairs(e->cub_tmp.p, tmp, R.ev_key, e->perm.as<uint32_t>(), (int64_t)n_ev, EventKeyLess(), s));
-        k_groups<<<(n_ev + 255) / 256, 256, 0, s>>>(R, dB, R.ev_key, e->perm.as<uint32_t>(), n_ev); e->launches++;
+        CK(cub::DeviceRadixSort::SortPairs(e->cub_tmp.p, tmp, keys_in, keys_out, idx_in, idx_out, (int64_t)n_ev, 0, end_bit, s));
+        k_groups<<<(n_ev + 255) / 256, 256, 0, s>>>(R, dB, keys_out, idx_out, n_ev); e->launches++;
     }
     if (const char* xf = getenv("PB_EXP")) R.exp_flags = atoi(xf);
     if (time_pileup) CK(cudaEventRecord(e->evp0, s));
@@ -359,7 +366,8 @@ static int compute(pb_engine* e, bool time_pileup) {
         const int64_t depth = R.size > 0 ? (int64_t)(e->h_sc->base_count / (unsigned long long)R.size) : 0;
         pv = (tiles >= 256 && depth <= 1000) ? 7 : 5;
     }
-    if (pv == 1) {
+    if (R.exp_flags & 256) {               // knock-out: everything but the pileup kernel (what the rest of the pass costs)
+    } else if (pv == 1) {
         const unsigned grid = (unsigned)((R.n_win + PILEUP_WARPS - 1) / PILEUP_WARPS);
         if (e->cfg.min_qual > 0) k_pileup<true><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
         else k_pileup<false><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);

@@ -4,7 +4,7 @@
 //   k_prep      thread per read: CIGAR walk -> segments, sparse updates, indel events, physCov diffs
 //   k_index     per batch: window -> first candidate read table
 //   k_scalars   region coverage / minDepth
-//   (cub merge sort of the indel events) -> k_groups -> k_indel_strings
+//   (cub radix sort of the indel event keys) -> k_groups -> k_indel_strings
 //   k_scan1/2/3 physCov prefix sums (PileUpRegion.computePhysCov)
 //   k_pileup    THE hot kernel: warp per 32-locus window gathers every overlapping segment,
 //               accumulates in registers, then runs BaseCall + pass-1 classification and flushes
@@ -349,20 +349,13 @@ __global__ void k_fold(RegionDev R, int32_t* reach0, int nb, int last) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// indel evidence: sorted events -> one Group per (locus, kind)
+// indel evidence: events -> one Group per (locus, kind).  The events are radix-sorted by (locus, kind) only;
+// inside a group the strict-majority string (PileUp.scala:219-220, the only one hetIndelCall can accept) is
+// found with a Boyer-Moore vote over the 64-bit string identities -- no ordering of the strings is needed.
 // ---------------------------------------------------------------------------------------------
-struct EventKeyLess {
-    __host__ __device__ bool operator()(const EventKey& a, const EventKey& b) const {
-        return a.lk < b.lk || (a.lk == b.lk && a.h < b.h);
-    }
-};
-
-__device__ __forceinline__ bool key_lt(const EventKey& a, uint64_t lk, uint64_t h) { return a.lk < lk || (a.lk == lk && a.h < h); }
-
-// first index in [lo, hi) whose key is >= (lk, h)
-__device__ __forceinline__ uint32_t key_lower(const EventKey* k, uint32_t lo, uint32_t hi, uint64_t lk, uint64_t h) {
-    while (lo < hi) { uint32_t m = lo + ((hi - lo) >> 1); if (key_lt(k[m], lk, h)) lo = m + 1; else hi = m; }
-    return lo;
+__global__ void __launch_bounds__(256) k_event_keys(const EventKey* __restrict__ ev_key, uint32_t* keys, uint32_t* idx, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { keys[i] = (uint32_t)ev_key[i].lk; idx[i] = i; }      // lk = locus index << 1 | kind  < 2^32
 }
 
 // byte t of the string of event e (insertion: rotated read bases; deletion: raw reference bytes)
@@ -373,26 +366,32 @@ __device__ __forceinline__ uint8_t event_byte(const RegionDev& R, const DevBatch
     return b;
 }
 
-// `keys` sorted, `perm[i]` = original event index of sorted position i
-__global__ void __launch_bounds__(256) k_groups(RegionDev R, const DevBatch* batches, const EventKey* keys,
+// `keys` = (locus << 1 | kind) sorted, `perm[i]` = original event index of sorted position i
+__global__ void __launch_bounds__(256) k_groups(RegionDev R, const DevBatch* batches, const uint32_t* keys,
                                                 const uint32_t* perm, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint64_t lk = keys[i].lk;
-    if (i > 0 && keys[i - 1].lk == lk) return;                       // not a group start
-    const uint32_t ge = key_lower(keys, i, n, lk + 1, 0);            // group = [i, ge)
+    const uint32_t key = keys[i];
+    if (i > 0 && keys[i - 1] == key) return;                         // not a group start
+    const uint64_t lk = key;
+    // Boyer-Moore vote over the group [i, ge): a strict majority, if there is one, survives as the candidate
+    uint64_t h = 0; uint32_t votes = 0, ge = i;
+    for (; ge < n && keys[ge] == key; ge++) {
+        const uint64_t hj = R.ev_key[perm[ge]].h;
+        if (votes == 0) { h = hj; votes = 1; } else if (hj == h) votes++; else votes--;
+    }
     const uint32_t len = ge - i;
-    // a strict-majority string (PileUp.scala:219-220) must own the median of the sorted group
-    const uint32_t mid = i + (len >> 1);
-    const uint64_t h = keys[mid].h;
-    const uint32_t rs = key_lower(keys, i, ge, lk, h);
-    const uint32_t re = (h == ~0ull) ? ge : key_lower(keys, rs, ge, lk, h + 1);
-    uint32_t cnt = re - rs;
-    const Event wev = R.ev[perm[rs]];
-    // hashed identities (long / non-ACGT insertions): make sure the run really is one string
+    uint32_t cnt = 0, rep = 0xFFFFFFFFu;                             // occurrences of the candidate; its lowest event index
+    for (uint32_t j = i; j < ge; j++) {
+        const uint32_t ej = perm[j];
+        if (R.ev_key[ej].h == h) { cnt++; rep = min(rep, ej); }
+    }
+    const Event wev = R.ev[rep];
+    // hashed identities (long / non-ACGT insertions): make sure the candidate's events really are one string
     if ((h >> 63) && !(lk & 1)) {
         uint32_t same = 0;
-        for (uint32_t j = rs; j < re; j++) {
+        for (uint32_t j = i; j < ge; j++) {
+            if (R.ev_key[perm[j]].h != h) continue;
             const Event e2 = R.ev[perm[j]];
             bool eq = e2.len == wev.len;
             for (uint32_t t = 0; eq && t < wev.len; t++) eq = event_byte(R, batches, lk, e2, t) == event_byte(R, batches, lk, wev, t);
@@ -405,7 +404,7 @@ __global__ void __launch_bounds__(256) k_groups(RegionDev R, const DevBatch* bat
     const bool majority = cnt >= 2 && cnt > len / 2;
     g.win_count = majority ? (int32_t)cnt : 0;                       // only a strict majority is ever consumed
     g.win_len = majority ? (int32_t)wev.len : 0;
-    g.win_ev = perm[rs]; g.pad = 0; g.str_off = 0;
+    g.win_ev = rep; g.pad = 0; g.str_off = 0;
     int has_n = 0;
     if (majority) for (uint32_t t = 0; t < wev.len; t++) has_n |= event_byte(R, batches, lk, wev, t) == 'N';   // PileUp.scala:222
     g.win_has_n = has_n;
