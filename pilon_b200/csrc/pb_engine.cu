@@ -385,8 +385,8 @@ static int compute(pb_engine* e, bool time_pileup) {
             PBt.b[i].flags = (d.frag ? 1u : 0u) | (d.n_reads ? 2u : 0u);
         }
         if (v7) {
-            if (e->cfg.min_qual > 0) k_pileup7<true, P7_TILE><<<grid, P7_WARPS * 32, sizeof(Tile7<P7_TILE>), s>>>(R, PBt, nullptr);
-            else k_pileup7<false, P7_TILE><<<grid, P7_WARPS * 32, sizeof(Tile7<P7_TILE>), s>>>(R, PBt, nullptr);
+            if (e->cfg.min_qual > 0) k_pileup7<true, P7_TILE><<<grid, P7_WARPS * 32, sizeof(Tile7<P7_TILE>), s>>>(R, PBt);
+            else k_pileup7<false, P7_TILE><<<grid, P7_WARPS * 32, sizeof(Tile7<P7_TILE>), s>>>(R, PBt);
         } else if (e->cfg.min_qual > 0) k_pileup5<true><<<grid, P5_WARPS * 32, smem, s>>>(R, PBt);
         else k_pileup5<false><<<grid, P5_WARPS * 32, smem, s>>>(R, PBt);
     } else if (pv >= 4) {      // (also: more batches than k_pileup5's by-value table holds)

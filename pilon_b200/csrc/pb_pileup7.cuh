@@ -44,6 +44,19 @@ __device__ __forceinline__ void red_shared_add_if(uint32_t nz, uint32_t saddr, u
     asm volatile("{\n .reg .pred pp;\n setp.ne.u32 pp, %0, 0;\n @pp red.shared.add.u32 [%1], %2;\n}" ::"r"(nz), "r"(saddr), "r"(v) : "memory");
 }
 
+template <int T>
+struct __align__(16) Tile7 {
+    uint32_t A[4][T];            // count << 20 | sum of quals, per letter
+    int32_t Bq[4][T];            // sum of qual * (mq1 - dom)
+    int32_t C[T];                // sum of (mq1 - dom)
+    uint32_t X[T];               // badPair << 16 | counted bases outside fragCoverage
+    uint32_t grab0[PB_MAXB + 1]; // first flat grab index of every batch
+    uint32_t slo[PB_MAXB], nseg[PB_MAXB];
+    uint32_t dom;                // 0 = not chosen yet ((adjMq + 1) >= 1 always)
+    uint32_t next;               // next flat grab index to hand out
+    uint2 slow[P7_WARPS][P7_SLOW_CAP];   // per warp: (batch, descriptor index) of segments whose (adjMq + 1) != dom
+};
+
 // if (bits & mask) { A word += v;  (NF) X word += 1 }   -- one predicate for both reductions
 template <bool NF>
 __device__ __forceinline__ void red_counted(uint32_t bits, uint32_t mask, uint32_t saddr, uint32_t v, uint32_t xaddr) {
@@ -106,252 +119,42 @@ __device__ __forceinline__ void scatter_chunk_dmq(const uint4 Q, uint32_t cw, ui
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// building blocks shared by k_pileup7 (one tile per CTA, CTA barriers) and k_pileup8 (persistent
-// CTAs, two tile buffers, no barrier in the steady state)
-// ---------------------------------------------------------------------------------------------
-template <int T>
-struct __align__(16) Tables7 {
-    uint32_t A[4][T];            // count << 20 | sum of quals, per letter
-    int32_t Bq[4][T];            // sum of qual * (mq1 - dom)
-    int32_t C[T];                // sum of (mq1 - dom)
-    uint32_t X[T];               // badPair << 16 | counted bases outside fragCoverage
-};
-
-// where a tile's descriptors come from and where its state lives (all pointers into shared memory)
-struct TileCtx {
-    const uint32_t* grab0;       // [PB_MAXB + 1] first flat grab index of every batch
-    const uint32_t* slo;         // [PB_MAXB] first candidate descriptor of every batch
-    const uint32_t* nseg;        // [PB_MAXB] candidate descriptors of every batch
-    uint32_t* dom;               // the tile's reference (adjMq + 1); 0 = not chosen yet
-    uint32_t* next;              // next flat grab index to hand out
-    uint2* slow;                 // this warp's queue of segments with another (adjMq + 1)
-    uint32_t sA;                 // shared byte address of A[0][0]
-    int32_t t0;                  // first locus of the tile
-};
-
-// candidate descriptor range of every batch for the tile starting at t0 (one warp, lane <-> batch)
-template <int T>
-__device__ __forceinline__ void tile_ranges(const RegionDev& R, const PileBatches& PB, int lane, int32_t t0,
-                                            uint32_t* grab0, uint32_t* slo, uint32_t* nseg) {
-    uint32_t my_slo = 0, my_nseg = 0;
-    if (lane < PB.n) {
-        const PileBatch& Bl = PB.b[lane];
-        if (Bl.flags & 2) {
-            const int64_t x = (int64_t)t0 - Bl.fwd + 1;
-            const int64_t y = (int64_t)t0 + T + Bl.back;
-            int64_t khi = (y + 31) >> 5; if (khi > R.n_win) khi = R.n_win;
-            my_slo = x <= 0 ? 0u : Bl.win_first[x >> 5];
-            const uint32_t shi = (y > ((int64_t)R.n_win << 5)) ? Bl.n_cigar : Bl.win_first[khi];
-            my_nseg = shi > my_slo ? shi - my_slo : 0u;
-        }
-    }
-    uint32_t ng = (my_nseg + P7_GRAB - 1) / P7_GRAB, pre = ng;      // inclusive scan of the grab counts
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += v; }
-    if (lane < PB_MAXB) { slo[lane] = my_slo; nseg[lane] = my_nseg; grab0[lane] = pre - ng; }
-    if (lane == PB_MAXB - 1) grab0[PB_MAXB] = pre;
-}
-
-// One warp: take grabs from the tile's cursor until it reaches p1; scatter them into the tile's tables.
 template <bool MINQ, int T>
-__device__ __forceinline__ void scatter_grabs(const RegionDev& R, const PileBatches& PB, const TileCtx& X, int lane,
-                                              uint32_t p1, uint32_t& dom_r, uint32_t& slow_n) {
-    constexpr uint32_t OFF_X = 36u * T;                         // byte offset of X[.] from A[0][.]
-    const int min_qual = R.cfg.min_qual;
-    const uint32_t defq = (uint32_t)R.cfg.default_qual;
-    const uint32_t minq_add = (uint32_t)(0x80 - (min_qual > 128 ? 128 : min_qual)) * 0x01010101u;
-    const uint32_t sA = X.sA;
-    const int32_t t0 = X.t0;
-    // the next grab (cursor value, batch, my descriptor) is fetched before the current one is processed
-    uint32_t g_nx = p1, sidx_nx = 0; int b_nx = 0; Seg seg_nx = {0, 0, 0, 0};
-    auto fetch = [&]() {
-        uint32_t g = 0;
-        if (lane == 0) g = atomicAdd(X.next, 1u);
-        g = __shfl_sync(FULL, g, 0);
-        g_nx = g; seg_nx = Seg{0, 0, 0, 0};
-        if (g >= p1) return;
-        int b = 0;
-        while (g >= X.grab0[b + 1]) b++;                      // batch of this grab (grab0 is non-decreasing)
-        b_nx = b;
-        const uint32_t di = (g - X.grab0[b]) * P7_GRAB + (uint32_t)(lane >> 1);   // two lanes per descriptor
-        sidx_nx = X.slo[b] + di;
-        if (di < X.nseg[b]) seg_nx = PB.b[b].seg[sidx_nx];
-    };
-    if (!(R.exp_flags & 2)) fetch();
-    while (g_nx < p1) {
-        const Seg mine = seg_nx;
-        const int b_cur = b_nx; const uint32_t sidx = sidx_nx;
-        const PileBatch& Bb = PB.b[b_cur];
-        fetch();
-        // lane (d, h) walks half h of the chunks of descriptor d
-        const int h = lane & 1;
-        const uint8_t* __restrict__ gquals = Bb.quals;
-        const uint8_t* __restrict__ gbases = Bb.bases2;
-        const bool nf = !(Bb.flags & 1);                      // warp-uniform: this batch is outside fragCoverage
-        // my segment clipped to the tile: n bases from base index src, first locus = tile column col
-        const int32_t cA = mine.loc0 > t0 ? mine.loc0 : t0;
-        const int32_t cBx = mine.loc0 + mine.len < t0 + T ? mine.loc0 + mine.len : t0 + T;
-        const int32_t n = mine.len > 0 ? (cBx > cA ? cBx - cA : 0) : 0;
-        const uint32_t src = mine.src + (uint32_t)(cA - mine.loc0);
-        const int32_t col = cA - t0;
-        const bool valid = mine.w & SEG_VALID;
-        const bool live = n > 0 && valid;
-        // aligned 16-base chunks c0..c1 of the batch's base stream (chunk k = bases [16 k, 16 k + 16)); my half of them.
-        // The first chunk's loads are issued now, the rest of the per-grab set-up runs under their latency.
-        const uint32_t last = src + (uint32_t)n - 1u;
-        const uint32_t c0 = src >> 4, c1 = last >> 4, mid = c0 + ((c1 - c0 + 2u) >> 1);
-        uint32_t k = h ? mid : c0;
-        const uint32_t k1 = h ? c1 : mid - 1u;
-        const bool work = live && k <= k1;
-        const uint4* qp = reinterpret_cast<const uint4*>(gquals) + k;
-        const uint32_t* cp = reinterpret_cast<const uint32_t*>(gbases) + k;
-        uint4 Q = make_uint4(0, 0, 0, 0); uint32_t cw = 0;
-        if (work) { Q = *qp; cw = *cp; }
-        unsigned badm = __ballot_sync(FULL, n > 0 && !valid && h == 0);
-        while (badm) {                                        // PileUpRegion.scala:45: badPair++ on every locus, lane <-> locus
-            const int j = __ffs(badm) - 1; badm &= badm - 1;
-            const int32_t bn = __shfl_sync(FULL, n, j), bcol = __shfl_sync(FULL, col, j);
-            for (int i = lane; i < bn; i += 32) red_shared_add(sA + OFF_X + 4u * (uint32_t)(bcol + i), 0x10000u);
-        }
-        const unsigned livem = __ballot_sync(FULL, live);
-        if (livem == 0) continue;
-        const uint32_t mq1 = mine.w & 0xFFFFu;
-        if (dom_r == 0) {                                     // the tile's reference (adjMq + 1): first one met
-            const uint32_t first = __shfl_sync(FULL, mq1, __ffs(livem) - 1);
-            uint32_t old = 0;
-            if (lane == 0) old = atomicCAS(X.dom, 0u, first);
-            old = __shfl_sync(FULL, old, 0);
-            dom_r = old ? old : first;
-        }
-        const int32_t dmq = (int32_t)mq1 - (int32_t)dom_r;
-        // a segment with another mapping quality (~5 % of the reads) is queued: its Bq / C terms are added by
-        // drain_queue, lane <-> chunk, instead of dragging the whole warp through a second reduction block here
-        int inl = 0;
-        {
-            const unsigned qm = __ballot_sync(FULL, live && dmq != 0 && h == 0);
-            if (qm) {
-                const uint32_t e = slow_n + (uint32_t)__popc(qm & ((1u << lane) - 1u));
-                if ((qm >> lane) & 1u) { if (e < P7_SLOW_CAP) X.slow[e] = make_uint2((uint32_t)b_cur, sidx); else inl = 1; }
-                slow_n = min(slow_n + (uint32_t)__popc(qm), (uint32_t)P7_SLOW_CAP);
-            }
-        }
-        inl = __shfl_sync(FULL, inl, lane & ~1);
-        const bool hasq = mine.w & SEG_HASQ;
-        const bool allhq = __all_sync(FULL, hasq || !live);
-        const uint32_t qand = hasq ? 0x7Fu : 0u, qor = (1u << 20) | (hasq ? 0u : defq);
-        const uint32_t nohq_pass = (!hasq && (int)defq >= min_qual) ? 0x01010101u : 0u;
-        if (work) {
-            uint32_t sa = sA + 4u * (uint32_t)(col + (int32_t)(16u * k - src));      // A[0][locus of base 16 k] (virtual before col)
-            for (;;) {
-                uint4 Qn = make_uint4(0, 0, 0, 0); uint32_t cwn = 0;
-                const bool more = k < k1;
-                if (more) { Qn = qp[1]; cwn = cp[1]; }                           // next chunk's loads in flight
-                const uint32_t okm = chunk_mask<MINQ>(Q, k, src, last, minq_add, nohq_pass);
-                if (allhq) { if (nf) scatter_chunk<true, true, T>(Q, cw, okm, sa, qand, qor); else scatter_chunk<false, true, T>(Q, cw, okm, sa, qand, qor); }
-                else { if (nf) scatter_chunk<true, false, T>(Q, cw, okm, sa, qand, qor); else scatter_chunk<false, false, T>(Q, cw, okm, sa, qand, qor); }
-                if (inl) scatter_chunk_dmq<T>(Q, cw, okm, sa, qand, qor, dmq);           // queue full (deep pile-ups)
-                if (!more) break;
-                Q = Qn; cw = cwn; k++; qp++; cp++; sa += 64;
-            }
-        }
-    }
-}
-
-// A warp drains its own queue right after its last grab of a pass (no barrier needed: the reductions commute):
-// two queued segments per iteration, lane <-> chunk (16 lanes per segment)
-template <bool MINQ, int T>
-__device__ __forceinline__ void drain_queue(const RegionDev& R, const PileBatches& PB, const TileCtx& X, int lane,
-                                            uint32_t dom, uint32_t& slow_n) {
-    const int min_qual = R.cfg.min_qual;
-    const uint32_t defq = (uint32_t)R.cfg.default_qual;
-    const uint32_t minq_add = (uint32_t)(0x80 - (min_qual > 128 ? 128 : min_qual)) * 0x01010101u;
-    const int32_t t0 = X.t0;
-    __syncwarp();
-    for (uint32_t e = (uint32_t)(lane >> 4); e < slow_n; e += 2u) {
-        const uint2 en = X.slow[e];
-        const PileBatch& Bb = PB.b[en.x];
-        const Seg sg = Bb.seg[en.y];
-        const int32_t cA = sg.loc0 > t0 ? sg.loc0 : t0;
-        const int32_t cBx = sg.loc0 + sg.len < t0 + T ? sg.loc0 + sg.len : t0 + T;
-        const int32_t n = cBx - cA;
-        const uint32_t src = sg.src + (uint32_t)(cA - sg.loc0), last = src + (uint32_t)n - 1u;
-        const int32_t col = cA - t0;
-        const int32_t dmq = (int32_t)(sg.w & 0xFFFFu) - (int32_t)dom;
-        const bool hasq = sg.w & SEG_HASQ;
-        const uint32_t qand = hasq ? 0x7Fu : 0u, qor = hasq ? 0u : defq;
-        const uint32_t nohq_pass = (!hasq && (int)defq >= min_qual) ? 0x01010101u : 0u;
-        const uint4* qp = reinterpret_cast<const uint4*>(Bb.quals);
-        const uint32_t* cp = reinterpret_cast<const uint32_t*>(Bb.bases2);
-        for (uint32_t k = (src >> 4) + (uint32_t)(lane & 15); k <= (last >> 4); k += 16) {
-            const uint4 Q = qp[k]; const uint32_t cw = cp[k];
-            const uint32_t okm = chunk_mask<MINQ>(Q, k, src, last, minq_add, nohq_pass);
-            scatter_chunk_dmq<T>(Q, cw, okm, X.sA + 4u * (uint32_t)(col + (int32_t)(16u * k - src)), qand, qor, dmq);
-        }
-    }
-    slow_n = 0;
-    __syncwarp();
-}
-
-// epilogue of window wl (32 loci) of a tile: decode the tables, add what earlier passes folded away, finish_locus
-template <int T>
-__device__ __forceinline__ void epilogue_window(const RegionDev& R, const Tables7<T>& S, int32_t t0, int wl, int lane,
-                                                uint32_t dom, bool folded) {
-    const int64_t w = ((int64_t)t0 >> 5) + wl;
-    if (w >= R.n_win) return;
-    const int l = wl * 32 + lane;
-    const int64_t loc = (int64_t)t0 + l;
-    const bool inr = loc < R.size;
-    const uint32_t pre_rb = R.rare_bits[w];
-    const uint8_t pre_ref = inr ? ref_at(R, (int64_t)R.start + loc) : (uint8_t)'N';
-    uint32_t c[4], sq[4]; uint64_t q[4];
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-        const uint32_t a = S.A[b][l]; c[b] = a >> 20; sq[b] = a & 0xFFFFFu;
-        q[b] = (uint64_t)((long long)((uint64_t)dom * sq[b]) + (long long)S.Bq[b][l]);
-    }
-    uint32_t n = c[0] + c[1] + c[2] + c[3];
-    uint32_t mqS = dom * n + (uint32_t)S.C[l], qS = sq[0] + sq[1] + sq[2] + sq[3];
-    const uint32_t x = S.X[l];
-    uint32_t bp = x >> 16, nfc = x & 0xFFFFu;
-    if (folded && inr) {
-        const int4 p = reinterpret_cast<const int4*>(R.o_cnt)[loc];
-        c[0] += (uint32_t)p.x; c[1] += (uint32_t)p.y; c[2] += (uint32_t)p.z; c[3] += (uint32_t)p.w;
-#pragma unroll
-        for (int b = 0; b < 4; b++) q[b] += (uint64_t)R.o_qs[4 * loc + b];
-        mqS += (uint32_t)R.o_mq[loc]; qS += (uint32_t)R.o_q[loc];
-        bp += (uint32_t)R.o_bp[loc]; nfc += (uint32_t)R.o_frag[loc];
-        n = c[0] + c[1] + c[2] + c[3];
-    }
-    if (R.exp_flags & 1) { if (c[0] == 0xdeadbeef) R.o_mq[loc] = (int32_t)q[0]; return; }
-    finish_locus(R, w, lane, (int32_t)loc, c, q, mqS, qS, bp, n - nfc, pre_rb, pre_ref);
-}
-
-template <int T>
-struct __align__(16) Tile7 {
-    Tables7<T> tab;
-    uint32_t grab0[PB_MAXB + 1]; // first flat grab index of every batch
-    uint32_t slo[PB_MAXB], nseg[PB_MAXB];
-    uint32_t dom;                // 0 = not chosen yet ((adjMq + 1) >= 1 always)
-    uint32_t next;               // next flat grab index to hand out
-    uint2 slow[P7_WARPS][P7_SLOW_CAP];   // per warp: (batch, descriptor index) of segments whose (adjMq + 1) != dom
-};
-
-// `only_if_deep`: when non-null the kernel runs only if the flag it points to is set (k_pileup8 took the other case)
-template <bool MINQ, int T>
-__global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R, const PileBatches PB, const uint32_t* only_if_deep) {
-    if (only_if_deep && !*only_if_deep) return;
+__global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R, const PileBatches PB) {
     extern __shared__ __align__(16) uint8_t smem_raw7[];
     Tile7<T>& S = *reinterpret_cast<Tile7<T>*>(smem_raw7);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int32_t t0 = (int32_t)blockIdx.x * T;
+    const int n_batches = PB.n;
+    const int min_qual = R.cfg.min_qual;
+    const uint32_t defq = (uint32_t)R.cfg.default_qual;
+    const uint32_t minq_add = (uint32_t)(0x80 - (min_qual > 128 ? 128 : min_qual)) * 0x01010101u;
+    constexpr uint32_t OFF_X = 36u * T;                         // byte offset of X[.] from A[0][.]
 
     // ---- tile set-up: zero the counters, candidate descriptor range of every batch ----
     {
-        uint32_t* z = reinterpret_cast<uint32_t*>(&S.tab);
+        uint32_t* z = reinterpret_cast<uint32_t*>(&S.A[0][0]);
         for (int i = tid; i < 10 * T; i += P7_WARPS * 32) z[i] = 0;
         if (tid == 0) { S.dom = 0; S.next = 0; }
-        if (warp == 0) tile_ranges<T>(R, PB, lane, t0, S.grab0, S.slo, S.nseg);
+        if (warp == 0) {
+            uint32_t my_slo = 0, my_nseg = 0;
+            if (lane < n_batches) {
+                const PileBatch& Bl = PB.b[lane];
+                if (Bl.flags & 2) {
+                    const int64_t x = (int64_t)t0 - Bl.fwd + 1;
+                    const int64_t y = (int64_t)t0 + T + Bl.back;
+                    int64_t khi = (y + 31) >> 5; if (khi > R.n_win) khi = R.n_win;
+                    my_slo = x <= 0 ? 0u : Bl.win_first[x >> 5];
+                    const uint32_t shi = (y > ((int64_t)R.n_win << 5)) ? Bl.n_cigar : Bl.win_first[khi];
+                    my_nseg = shi > my_slo ? shi - my_slo : 0u;
+                }
+            }
+            uint32_t ng = (my_nseg + P7_GRAB - 1) / P7_GRAB, pre = ng;      // inclusive scan of the grab counts
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += v; }
+            if (lane < PB_MAXB) { S.slo[lane] = my_slo; S.nseg[lane] = my_nseg; S.grab0[lane] = pre - ng; }
+            if (lane == PB_MAXB - 1) S.grab0[PB_MAXB] = pre;
+        }
     }
     __syncthreads();
     const uint32_t total_grabs = S.grab0[PB_MAXB];
@@ -360,19 +163,19 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
     // fold the 12/20-bit tile into the output planes (used as 32/64-bit accumulators) and clear it
     auto fold = [&]() {
         const uint32_t dom = S.dom;
-        Tables7<T>& Tb = S.tab;
         for (int l = tid; l < T; l += P7_WARPS * 32) {
             const int64_t loc = (int64_t)t0 + l;
+            const int x_ = l;
             if (loc < R.size) {
                 uint32_t c[4], sq[4]; long long q[4];
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
-                    const uint32_t a = Tb.A[b][l]; c[b] = a >> 20; sq[b] = a & 0xFFFFFu;
-                    q[b] = (long long)((uint64_t)dom * sq[b]) + (long long)Tb.Bq[b][l];
+                    const uint32_t a = S.A[b][x_]; c[b] = a >> 20; sq[b] = a & 0xFFFFFu;
+                    q[b] = (long long)((uint64_t)dom * sq[b]) + (long long)S.Bq[b][x_];
                 }
                 const uint32_t n = c[0] + c[1] + c[2] + c[3];
-                const uint32_t mq = dom * n + (uint32_t)Tb.C[l], qs = sq[0] + sq[1] + sq[2] + sq[3];
-                const uint32_t x = Tb.X[l];
+                const uint32_t mq = dom * n + (uint32_t)S.C[x_], qs = sq[0] + sq[1] + sq[2] + sq[3];
+                const uint32_t x = S.X[x_];
                 int4* oc = reinterpret_cast<int4*>(R.o_cnt) + loc;
                 long long* oq = reinterpret_cast<long long*>(R.o_qs) + 4 * loc;
                 if (folded) {
@@ -391,33 +194,186 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
                 }
             }
 #pragma unroll
-            for (int b = 0; b < 4; b++) { Tb.A[b][l] = 0; Tb.Bq[b][l] = 0; }
-            Tb.C[l] = 0; Tb.X[l] = 0;
+            for (int b = 0; b < 4; b++) { S.A[b][x_] = 0; S.Bq[b][x_] = 0; }
+            S.C[x_] = 0; S.X[x_] = 0;
         }
         folded = true;
     };
 
     // ---- scatter: passes of <= 4064 descriptors; a warp takes the next 16 descriptors when it is free ----
-    TileCtx X;
-    X.grab0 = S.grab0; X.slo = S.slo; X.nseg = S.nseg; X.dom = &S.dom; X.next = &S.next; X.slow = S.slow[warp];
-    X.sA = smem_u32(&S.tab.A[0][0]); X.t0 = t0;
+    const uint32_t sA = smem_u32(&S.A[0][0]);
     uint32_t dom_r = 0;                                          // register copy of S.dom once it is known
-    uint32_t slow_n = 0;                                         // warp-uniform: entries in my queue
+    static_assert(T == 1024 || T == 2048, "tile size");
     constexpr uint32_t PASS_GRABS = P7_PASS_DESC / P7_GRAB;
+    // A warp drains its own queue right after its last grab of a pass (no barrier needed: the reductions commute):
+    // two queued segments per iteration, lane <-> chunk (16 lanes per segment)
+    uint32_t slow_n = 0;                                         // warp-uniform: entries in S.slow[warp]
+    auto drain_slow = [&]() {
+        __syncwarp();
+        const uint32_t dom = dom_r;
+        for (uint32_t e = (uint32_t)(lane >> 4); e < slow_n; e += 2u) {
+            const uint2 en = S.slow[warp][e];
+            const PileBatch& Bb = PB.b[en.x];
+            const Seg sg = Bb.seg[en.y];
+            const int32_t cA = sg.loc0 > t0 ? sg.loc0 : t0;
+            const int32_t cBx = sg.loc0 + sg.len < t0 + T ? sg.loc0 + sg.len : t0 + T;
+            const int32_t n = cBx - cA;
+            const uint32_t src = sg.src + (uint32_t)(cA - sg.loc0), last = src + (uint32_t)n - 1u;
+            const int32_t col = cA - t0;
+            const int32_t dmq = (int32_t)(sg.w & 0xFFFFu) - (int32_t)dom;
+            const bool hasq = sg.w & SEG_HASQ;
+            const uint32_t qand = hasq ? 0x7Fu : 0u, qor = hasq ? 0u : defq;
+            const uint32_t nohq_pass = (!hasq && (int)defq >= min_qual) ? 0x01010101u : 0u;
+            const uint4* qp = reinterpret_cast<const uint4*>(Bb.quals);
+            const uint32_t* cp = reinterpret_cast<const uint32_t*>(Bb.bases2);
+            for (uint32_t k = (src >> 4) + (uint32_t)(lane & 15); k <= (last >> 4); k += 16) {
+                const uint4 Q = qp[k]; const uint32_t cw = cp[k];
+                const uint32_t okm = chunk_mask<MINQ>(Q, k, src, last, minq_add, nohq_pass);
+                scatter_chunk_dmq<T>(Q, cw, okm, sA + 4u * (uint32_t)(col + (int32_t)(16u * k - src)), qand, qor, dmq);
+            }
+        }
+        slow_n = 0;
+        __syncwarp();
+    };
+
     for (uint32_t p0 = 0; p0 < total_grabs; p0 += PASS_GRABS) {
         if (p0) {
             fold();
             if (tid == 0) S.next = p0;
             __syncthreads();
         }
-        scatter_grabs<MINQ, T>(R, PB, X, lane, min(p0 + PASS_GRABS, total_grabs), dom_r, slow_n);
-        drain_queue<MINQ, T>(R, PB, X, lane, dom_r, slow_n);
+        const uint32_t p1 = min(p0 + PASS_GRABS, total_grabs);
+        // the next grab (cursor value, batch, my descriptor) is fetched before the current one is processed
+        uint32_t g_nx = p1, sidx_nx = 0; int b_nx = 0; Seg seg_nx = {0, 0, 0, 0};
+        auto fetch = [&]() {
+            uint32_t g = 0;
+            if (lane == 0) g = atomicAdd(&S.next, 1u);
+            g = __shfl_sync(FULL, g, 0);
+            g_nx = g; seg_nx = Seg{0, 0, 0, 0};
+            if (g >= p1) return;
+            int b = 0;
+            while (g >= S.grab0[b + 1]) b++;                      // batch of this grab (grab0 is non-decreasing)
+            b_nx = b;
+            const uint32_t di = (g - S.grab0[b]) * P7_GRAB + (uint32_t)(lane >> 1);   // two lanes per descriptor
+            sidx_nx = S.slo[b] + di;
+            if (di < S.nseg[b]) seg_nx = PB.b[b].seg[sidx_nx];
+        };
+        if (!(R.exp_flags & 2)) fetch();
+        while (g_nx < p1) {
+            const Seg mine = seg_nx;
+            const int b_cur = b_nx; const uint32_t sidx = sidx_nx;
+            const PileBatch& Bb = PB.b[b_cur];
+            fetch();
+            // lane (d, h) walks half h of the chunks of descriptor d
+            const int h = lane & 1;
+            const uint8_t* __restrict__ gquals = Bb.quals;
+            const uint8_t* __restrict__ gbases = Bb.bases2;
+            const bool nf = !(Bb.flags & 1);                      // warp-uniform: this batch is outside fragCoverage
+            // my segment clipped to the tile: n bases from base index src, first locus = tile column col
+            const int32_t cA = mine.loc0 > t0 ? mine.loc0 : t0;
+            const int32_t cBx = mine.loc0 + mine.len < t0 + T ? mine.loc0 + mine.len : t0 + T;
+            const int32_t n = mine.len > 0 ? (cBx > cA ? cBx - cA : 0) : 0;
+            const uint32_t src = mine.src + (uint32_t)(cA - mine.loc0);
+            const int32_t col = cA - t0;
+            const bool valid = mine.w & SEG_VALID;
+            const bool live = n > 0 && valid;
+            // aligned 16-base chunks c0..c1 of the batch's base stream (chunk k = bases [16 k, 16 k + 16)); my half of them.
+            // The first chunk's loads are issued now, the rest of the per-grab set-up runs under their latency.
+            const uint32_t last = src + (uint32_t)n - 1u;
+            const uint32_t c0 = src >> 4, c1 = last >> 4, mid = c0 + ((c1 - c0 + 2u) >> 1);
+            uint32_t k = h ? mid : c0;
+            const uint32_t k1 = h ? c1 : mid - 1u;
+            const bool work = live && k <= k1;
+            const uint4* qp = reinterpret_cast<const uint4*>(gquals) + k;
+            const uint32_t* cp = reinterpret_cast<const uint32_t*>(gbases) + k;
+            uint4 Q = make_uint4(0, 0, 0, 0); uint32_t cw = 0;
+            if (work) { Q = *qp; cw = *cp; }
+            unsigned badm = __ballot_sync(FULL, n > 0 && !valid && h == 0);
+            while (badm) {                                        // PileUpRegion.scala:45: badPair++ on every locus, lane <-> locus
+                const int j = __ffs(badm) - 1; badm &= badm - 1;
+                const int32_t bn = __shfl_sync(FULL, n, j), bcol = __shfl_sync(FULL, col, j);
+                for (int i = lane; i < bn; i += 32) red_shared_add(sA + OFF_X + 4u * (uint32_t)(bcol + i), 0x10000u);
+            }
+            const unsigned livem = __ballot_sync(FULL, live);
+            if (livem == 0) continue;
+            const uint32_t mq1 = mine.w & 0xFFFFu;
+            if (dom_r == 0) {                                     // the tile's reference (adjMq + 1): first one met
+                const uint32_t first = __shfl_sync(FULL, mq1, __ffs(livem) - 1);
+                uint32_t old = 0;
+                if (lane == 0) old = atomicCAS(&S.dom, 0u, first);
+                old = __shfl_sync(FULL, old, 0);
+                dom_r = old ? old : first;
+            }
+            const int32_t dmq = (int32_t)mq1 - (int32_t)dom_r;
+            // a segment with another mapping quality (~5 % of the reads) is queued: its Bq / C terms are added after the
+            // scatter, lane <-> chunk, instead of dragging the whole warp through a second reduction block here
+            int inl = 0;
+            {
+                const unsigned qm = __ballot_sync(FULL, live && dmq != 0 && h == 0);
+                if (qm) {
+                    const uint32_t e = slow_n + (uint32_t)__popc(qm & ((1u << lane) - 1u));
+                    if ((qm >> lane) & 1u) { if (e < P7_SLOW_CAP) S.slow[warp][e] = make_uint2((uint32_t)b_cur, sidx); else inl = 1; }
+                    slow_n = min(slow_n + (uint32_t)__popc(qm), (uint32_t)P7_SLOW_CAP);
+                }
+            }
+            inl = __shfl_sync(FULL, inl, lane & ~1);
+            const bool hasq = mine.w & SEG_HASQ;
+            const bool allhq = __all_sync(FULL, hasq || !live);
+            const uint32_t qand = hasq ? 0x7Fu : 0u, qor = (1u << 20) | (hasq ? 0u : defq);
+            const uint32_t nohq_pass = (!hasq && (int)defq >= min_qual) ? 0x01010101u : 0u;
+            if (work) {
+                {
+                    uint32_t sa = sA + 4u * (uint32_t)(col + (int32_t)(16u * k - src));      // A[0][locus of base 16 k] (virtual before col)
+                    for (;;) {
+                        uint4 Qn = make_uint4(0, 0, 0, 0); uint32_t cwn = 0;
+                        const bool more = k < k1;
+                        if (more) { Qn = qp[1]; cwn = cp[1]; }                           // next chunk's loads in flight
+                        const uint32_t okm = chunk_mask<MINQ>(Q, k, src, last, minq_add, nohq_pass);
+                        if (allhq) { if (nf) scatter_chunk<true, true, T>(Q, cw, okm, sa, qand, qor); else scatter_chunk<false, true, T>(Q, cw, okm, sa, qand, qor); }
+                        else { if (nf) scatter_chunk<true, false, T>(Q, cw, okm, sa, qand, qor); else scatter_chunk<false, false, T>(Q, cw, okm, sa, qand, qor); }
+                        if (inl) scatter_chunk_dmq<T>(Q, cw, okm, sa, qand, qor, dmq);           // slow list full (deep pile-ups)
+                        if (!more) break;
+                        Q = Qn; cw = cwn; k++; qp++; cp++; sa += 64;
+                    }
+                }
+            }
+        }
+        drain_slow();
         __syncthreads();
     }
 
     // ---- epilogue: warp per 32-locus window of the tile ----
     const uint32_t dom = S.dom;
-    for (int wl = warp; wl < T / 32; wl += P7_WARPS) epilogue_window<T>(R, S.tab, t0, wl, lane, dom, folded);
+    for (int wl = warp; wl < T / 32; wl += P7_WARPS) {
+        const int64_t w = ((int64_t)t0 >> 5) + wl;
+        if (w >= R.n_win) break;
+        const int l = wl * 32 + lane, x_ = l;
+        const int64_t loc = (int64_t)t0 + l;
+        const bool inr = loc < R.size;
+        const uint32_t pre_rb = R.rare_bits[w];
+        const uint8_t pre_ref = inr ? ref_at(R, (int64_t)R.start + loc) : (uint8_t)'N';
+        uint32_t c[4], sq[4]; uint64_t q[4];
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint32_t a = S.A[b][x_]; c[b] = a >> 20; sq[b] = a & 0xFFFFFu;
+            q[b] = (uint64_t)((long long)((uint64_t)dom * sq[b]) + (long long)S.Bq[b][x_]);
+        }
+        uint32_t n = c[0] + c[1] + c[2] + c[3];
+        uint32_t mqS = dom * n + (uint32_t)S.C[x_], qS = sq[0] + sq[1] + sq[2] + sq[3];
+        const uint32_t x = S.X[x_];
+        uint32_t bp = x >> 16, nfc = x & 0xFFFFu;
+        if (folded && inr) {
+            const int4 p = reinterpret_cast<const int4*>(R.o_cnt)[loc];
+            c[0] += (uint32_t)p.x; c[1] += (uint32_t)p.y; c[2] += (uint32_t)p.z; c[3] += (uint32_t)p.w;
+#pragma unroll
+            for (int b = 0; b < 4; b++) q[b] += (uint64_t)R.o_qs[4 * loc + b];
+            mqS += (uint32_t)R.o_mq[loc]; qS += (uint32_t)R.o_q[loc];
+            bp += (uint32_t)R.o_bp[loc]; nfc += (uint32_t)R.o_frag[loc];
+            n = c[0] + c[1] + c[2] + c[3];
+        }
+        if (R.exp_flags & 1) { if (c[0] == 0xdeadbeef) R.o_mq[loc] = (int32_t)q[0]; continue; }
+        finish_locus(R, w, lane, (int32_t)loc, c, q, mqS, qS, bp, n - nfc, pre_rb, pre_ref);
+    }
 }
 
 }  // namespace pb
