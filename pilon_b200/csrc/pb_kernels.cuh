@@ -366,53 +366,74 @@ __device__ __forceinline__ uint8_t event_byte(const RegionDev& R, const DevBatch
     return b;
 }
 
-// `keys` = (locus << 1 | kind) sorted, `perm[i]` = original event index of sorted position i
+// `keys` = (locus << 1 | kind) sorted, `perm[i]` = original event index of sorted position i.
+// Thread per event finds the group starts; every group is then worked on by the whole warp (a 5000x pile-up has
+// groups of thousands of events): each lane runs the Boyer-Moore vote over its strided share -- a strict majority of
+// the group is a strict majority of at least one share -- and the distinct surviving candidates are counted exactly.
 __global__ void __launch_bounds__(256) k_groups(RegionDev R, const DevBatch* batches, const uint32_t* keys,
                                                 const uint32_t* perm, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t key = keys[i];
-    if (i > 0 && keys[i - 1] == key) return;                         // not a group start
-    const uint64_t lk = key;
-    // Boyer-Moore vote over the group [i, ge): a strict majority, if there is one, survives as the candidate
-    uint64_t h = 0; uint32_t votes = 0, ge = i;
-    for (; ge < n && keys[ge] == key; ge++) {
-        const uint64_t hj = R.ev_key[perm[ge]].h;
-        if (votes == 0) { h = hj; votes = 1; } else if (hj == h) votes++; else votes--;
-    }
-    const uint32_t len = ge - i;
-    uint32_t cnt = 0, rep = 0xFFFFFFFFu;                             // occurrences of the candidate; its lowest event index
-    for (uint32_t j = i; j < ge; j++) {
-        const uint32_t ej = perm[j];
-        if (R.ev_key[ej].h == h) { cnt++; rep = min(rep, ej); }
-    }
-    const Event wev = R.ev[rep];
-    // hashed identities (long / non-ACGT insertions): make sure the candidate's events really are one string
-    if ((h >> 63) && !(lk & 1)) {
-        uint32_t same = 0;
-        for (uint32_t j = i; j < ge; j++) {
-            if (R.ev_key[perm[j]].h != h) continue;
-            const Event e2 = R.ev[perm[j]];
-            bool eq = e2.len == wev.len;
-            for (uint32_t t = 0; eq && t < wev.len; t++) eq = event_byte(R, batches, lk, e2, t) == event_byte(R, batches, lk, wev, t);
-            same += eq;
+    const int lane = threadIdx.x & 31;
+    const bool is_start = i < n && (i == 0 || keys[i - 1] != keys[i]);
+    unsigned starts = __ballot_sync(FULL, is_start);
+    while (starts) {
+        const int js = __ffs(starts) - 1; starts &= starts - 1;
+        const uint32_t g0 = __shfl_sync(FULL, i, js);
+        const uint32_t key = keys[g0];
+        uint32_t lo = g0 + 1, hi = n;                                    // group end: keys are sorted, equal keys contiguous
+        while (lo < hi) { const uint32_t m = lo + ((hi - lo) >> 1); if (keys[m] == key) lo = m + 1; else hi = m; }
+        const uint32_t ge = lo, len = ge - g0;
+        const uint64_t lk = key;
+        uint64_t cand = 0; uint32_t votes = 0;
+        for (uint32_t t = g0 + lane; t < ge; t += 32) {
+            const uint64_t hj = R.ev_key[perm[t]].h;
+            if (votes == 0) { cand = hj; votes = 1; } else if (hj == cand) votes++; else votes--;
         }
-        if (same != cnt) atomicOr(&R.sc->error, 4);                  // 63-bit hash collision (never observed)
+        uint64_t h = 0; uint32_t cnt = 0, rep = perm[g0];
+        unsigned todo = __ballot_sync(FULL, votes > 0);
+        while (todo) {
+            const int kc = __ffs(todo) - 1;
+            const uint64_t c = ((uint64_t)__shfl_sync(FULL, (uint32_t)(cand >> 32), kc) << 32) | __shfl_sync(FULL, (uint32_t)cand, kc);
+            todo &= ~__ballot_sync(FULL, votes > 0 && cand == c);        // every lane that voted for c is settled
+            uint32_t my = 0, myrep = 0xFFFFFFFFu;
+            for (uint32_t t = g0 + lane; t < ge; t += 32) {
+                const uint32_t ej = perm[t];
+                if (R.ev_key[ej].h == c) { my++; myrep = min(myrep, ej); }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { my += __shfl_xor_sync(FULL, my, o); myrep = min(myrep, __shfl_xor_sync(FULL, myrep, o)); }
+            if (my > cnt) { h = c; cnt = my; rep = myrep; }
+            if (my > len / 2) break;                                     // the strict majority, unique
+        }
+        if (lane != 0) continue;
+        const Event wev = R.ev[rep];
+        // hashed identities (long / non-ACGT insertions): make sure the candidate's events really are one string
+        if ((h >> 63) && !(lk & 1)) {
+            uint32_t same = 0;
+            for (uint32_t j = g0; j < ge; j++) {
+                if (R.ev_key[perm[j]].h != h) continue;
+                const Event e2 = R.ev[perm[j]];
+                bool eq = e2.len == wev.len;
+                for (uint32_t t = 0; eq && t < wev.len; t++) eq = event_byte(R, batches, lk, e2, t) == event_byte(R, batches, lk, wev, t);
+                same += eq;
+            }
+            if (same != cnt) atomicOr(&R.sc->error, 4);                  // 63-bit hash collision (never observed)
+        }
+        Group g;
+        g.loc = (int32_t)(lk >> 1); g.kind = (int32_t)(lk & 1) + 1; g.list_len = (int32_t)len;
+        const bool majority = cnt >= 2 && cnt > len / 2;
+        g.win_count = majority ? (int32_t)cnt : 0;                       // only a strict majority is ever consumed
+        g.win_len = majority ? (int32_t)wev.len : 0;
+        g.win_ev = rep; g.pad = 0; g.str_off = 0;
+        int has_n = 0;
+        if (majority) for (uint32_t t = 0; t < wev.len; t++) has_n |= event_byte(R, batches, lk, wev, t) == 'N';   // PileUp.scala:222
+        g.win_has_n = has_n;
+        const uint32_t gi = atomicAdd(&R.sc->n_groups, 1u);
+        if (gi < R.groups_cap) {
+            R.groups[gi] = g;
+            ((lk & 1) ? R.r_gdel : R.r_gins)[g.loc] = gi + 1;            // locus already has its rare bit (k_prep)
+        } else atomicOr(&R.sc->error, 2);
     }
-    Group g;
-    g.loc = (int32_t)(lk >> 1); g.kind = (int32_t)(lk & 1) + 1; g.list_len = (int32_t)len;
-    const bool majority = cnt >= 2 && cnt > len / 2;
-    g.win_count = majority ? (int32_t)cnt : 0;                       // only a strict majority is ever consumed
-    g.win_len = majority ? (int32_t)wev.len : 0;
-    g.win_ev = rep; g.pad = 0; g.str_off = 0;
-    int has_n = 0;
-    if (majority) for (uint32_t t = 0; t < wev.len; t++) has_n |= event_byte(R, batches, lk, wev, t) == 'N';   // PileUp.scala:222
-    g.win_has_n = has_n;
-    const uint32_t gi = atomicAdd(&R.sc->n_groups, 1u);
-    if (gi < R.groups_cap) {
-        R.groups[gi] = g;
-        ((lk & 1) ? R.r_gdel : R.r_gins)[g.loc] = gi + 1;            // locus already has its rare bit (k_prep)
-    } else atomicOr(&R.sc->error, 2);
 }
 
 __global__ void __launch_bounds__(128) k_indel_strings(RegionDev R, const DevBatch* batches, uint32_t n_groups) {
