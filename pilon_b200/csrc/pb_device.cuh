@@ -44,7 +44,8 @@ struct __align__(32) Rare { int32_t ins, insq, del, delq, q, mq, clips, delfrag;
 // (constant bank): no dependent global load stands between a warp and its first descriptor.
 struct PileBatch {
     const Seg* seg; const uint8_t* quals; const uint8_t* bases2; const uint32_t* win_first;
-    uint32_t n_cigar; int32_t fwd, back; uint32_t flags;      // flags: 1 = counts toward fragCoverage, 2 = has reads
+    const int32_t* reach;      // device: [0] max forward reach, [1] max backward reach of the batch's segments (k_fold)
+    uint32_t n_cigar; uint32_t flags;      // flags: 1 = counts toward fragCoverage, 2 = has reads
 };
 static constexpr int PB_MAXB = 20;
 struct PileBatches { int32_t n; int32_t pad; PileBatch b[PB_MAXB]; };

@@ -76,10 +76,21 @@ struct pb_engine {
     int64_t launches = 0;
     float last_pileup_ms = 0.f;
     bool dirty = false;              // rare planes may be non-zero after a failed run
+    // pb_region_compute replays a captured CUDA graph of the pass while the region's batches stay the same
+    int graph_state = 0;             // 0: next pass runs plainly (and grows every buffer), 1: next pass is captured, 2: replay, 3: never
+    cudaGraphExec_t graph_exec = nullptr;
+    int64_t graph_launches = 0;      // kernels inside the captured pass
+    std::vector<DevBatch> img_host;  // image of the batch table; a captured H2D copy reads it at every replay
     int pileup_version = 0;          // 0 = choose per region (k_pileup7 scatter / k_pileup5 gather); PB_PILEUP=1..5,7 forces one (A/B runs)
 };
 
+static int clean_sparse_planes(pb_engine* e);
+static void drop_graph(pb_engine* e) {
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    if (e->graph_state != 3) e->graph_state = 0;
+}
 static int free_batches(pb_engine* e) {
+    drop_graph(e);
     for (auto& hb : e->batches)
         for (void* p : hb.owned) CK(cudaFreeAsync(p, e->stream));
     e->batches.clear();
@@ -166,13 +177,7 @@ extern "C" int pb_region_begin(pb_engine* e, const uint8_t* contig, int64_t cont
     CK(e->ref.ensure(ref_bytes, false, s));
     CK(cudaMemcpyAsync(e->ref.p, contig + (R.ref_locus0 - 1), ref_bytes, cudaMemcpyHostToDevice, s));
     R.ref = e->ref.as<uint8_t>();
-    if (e->dirty) {   // a failed run may have left sparse planes populated
-        if (e->rare.p) CK(cudaMemsetAsync(e->rare.p, 0, e->rare.cap, s));
-        for (auto& b : e->gplane) if (b.p) CK(cudaMemsetAsync(b.p, 0, b.cap, s));
-        if (e->rare_bits.p) CK(cudaMemsetAsync(e->rare_bits.p, 0, e->rare_bits.cap, s));
-        if (e->pc_diff.p) CK(cudaMemsetAsync(e->pc_diff.p, 0, e->pc_diff.cap, s));
-        e->dirty = false;
-    }
+    if (e->dirty) { int rcc = clean_sparse_planes(e); if (rcc != PB_OK) return rcc; e->dirty = false; }
     const size_t n4 = (size_t)S * 4;
     CK(e->rare.ensure((size_t)S * sizeof(Rare), true, s));
     for (auto& b : e->gplane) CK(b.ensure(n4, true, s));
@@ -237,6 +242,7 @@ extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, in
     if (b->n_seq >= (1ll << 32) || (b->n_seq & 3)) return fail(PB_ERR_INVALID, "n_seq must be a multiple of 4 and < 2^32");
     if (b->n_cigar >= (1ll << 32) || b->n_reads >= (1ll << 31)) return fail(PB_ERR_INVALID, "batch too large");
     CK(cudaSetDevice(e->device));
+    drop_graph(e);                                   // the captured pass belongs to the previous batch set
     e->batches.emplace_back();
     HostBatch& hb = e->batches.back();
     DevBatch& d = hb.d;
@@ -278,13 +284,38 @@ extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, in
 // the compute pipeline (no host<->device data copies except one 80-byte scalar read-back)
 // ---------------------------------------------------------------------------------------------
 
-static int compute(pb_engine* e, bool time_pileup) {
+static int clean_sparse_planes(pb_engine* e) {   // a failed / abandoned pass may have left the sparse planes populated
+    cudaStream_t s = e->stream;
+    if (e->rare.p) CK(cudaMemsetAsync(e->rare.p, 0, e->rare.cap, s));
+    for (auto& b : e->gplane) if (b.p) CK(cudaMemsetAsync(b.p, 0, b.cap, s));
+    if (e->rare_bits.p) CK(cudaMemsetAsync(e->rare_bits.p, 0, e->rare_bits.cap, s));
+    if (e->pc_diff.p) CK(cudaMemsetAsync(e->pc_diff.p, 0, e->pc_diff.cap, s));
+    return PB_OK;
+}
+
+// error flags raised by the kernels of a pass (read back by the caller once the pass has been synchronised)
+static int pass_error(uint32_t err) {
+    if (err & 1) return fail(PB_ERR_UNSORTED, "a batch is not sorted by pos");
+    if (err & 8) return fail(PB_ERR_CUDA, "pipeline barrier timed out (internal protocol error)");
+    if (err & 16) return fail(PB_ERR_UNSUPPORTED, "read longer than 2^24 bases or more than 256 batches in a region");
+    if (err & 4) return fail(PB_ERR_HASH, "two different long insertions share a 63-bit hash");
+    if (err) return fail(PB_ERR_CUDA, "internal capacity error flag set by a kernel");
+    return PB_OK;
+}
+
+// No host round trip inside: everything the later kernels need from the earlier ones (event count, reach of the
+// segments, read count, minDepth) stays on the device, so the whole pass can be enqueued at once (and captured in a
+// CUDA graph, pb_region_compute).  The indel event list is sized on the host by an upper bound -- CIGAR operations
+// minus reads: every read has at least one operation that is not I or D -- and a read set that breaks that bound
+// (I/D-only CIGARs) raises the capacity flag, which makes the callers repeat the pass with `full_cap`.
+static int compute(pb_engine* e, bool time_pileup, bool full_cap = false) {
     cudaStream_t s = e->stream;
     RegionDev& R = e->R;
     const int nb = (int)e->batches.size();
-    size_t total_cigar = 0;
-    for (auto& hb : e->batches) total_cigar += (size_t)hb.d.n_cigar;
+    size_t total_cigar = 0, total_reads = 0, total_seq = 0;
+    for (auto& hb : e->batches) { total_cigar += (size_t)hb.d.n_cigar; total_reads += (size_t)hb.d.n_reads; total_seq += (size_t)hb.d.n_seq; }
     const uint32_t cap = (uint32_t)std::min<size_t>(total_cigar, 0xFFFFFFF0u);
+    const uint32_t evcap = full_cap ? cap : (uint32_t)std::min<size_t>((size_t)cap, total_cigar - std::min(total_cigar, total_reads) + 64);
     CK(e->ev_key.ensure((size_t)cap * sizeof(EventKey) + 16, false, s));
     CK(e->ev.ensure((size_t)cap * sizeof(Event) + 16, false, s));
     CK(e->perm.ensure((size_t)cap * 4 + 16, false, s));
@@ -292,12 +323,13 @@ static int compute(pb_engine* e, bool time_pileup) {
     CK(e->groups.ensure((size_t)cap * sizeof(Group) + 16, false, s));
     CK(e->cand.ensure((size_t)cap * sizeof(int4) + 16, false, s));
     CK(e->work.ensure((size_t)cap * sizeof(int4) + 16, false, s));
-    R.ev_key = e->ev_key.as<EventKey>(); R.ev = e->ev.as<Event>(); R.ev_cap = cap;
+    R.ev_key = e->ev_key.as<EventKey>(); R.ev = e->ev.as<Event>(); R.ev_cap = evcap;
     R.groups = e->groups.as<Group>(); R.groups_cap = cap;
     R.cand = e->cand.as<int4>(); R.cand_cap = cap;
-    R.work = e->work.as<int4>(); R.work_cap = cap;
+    R.work = e->work.as<int4>(); R.work_cap = evcap;
     R.str_pool = e->str_pool.as<uint8_t>(); R.str_cap = e->str_pool.cap;
-    std::vector<DevBatch> img(nb);
+    std::vector<DevBatch>& img = e->img_host;
+    img.resize(nb);
     for (int i = 0; i < nb; i++) img[i] = e->batches[i].d;
     CK(e->d_batches.ensure(sizeof(DevBatch) * (size_t)std::max(nb, 1), false, s));
     if (nb) CK(cudaMemcpyAsync(e->d_batches.p, img.data(), sizeof(DevBatch) * nb, cudaMemcpyHostToDevice, s));
@@ -314,47 +346,32 @@ static int compute(pb_engine* e, bool time_pileup) {
             const DevBatch& d = e->batches[i].d;
             CK(cudaMemsetAsync(d.win_first, 0, ((size_t)R.n_win + 2) * 4, s));
             if (d.n_reads == 0) continue;
-            k_prep<<<(unsigned)((d.n_reads + 127) / 128), 128, 0, s>>>(R, d, (uint32_t)i);
-            k_index<<<(unsigned)((d.n_reads + 255) / 256), 256, 0, s>>>(R, d);
-            e->launches += 2;
+            k_prep<<<(unsigned)((d.n_reads + 127) / 128), 128, 0, s>>>(R, d, (uint32_t)i);      // also builds win_first
+            e->launches += 1;
         }
         if (i1 == nb) { k_indel<<<148 * 4, 128, 0, s>>>(R, dB); e->launches++; }     // queued I / D ops of every batch
         k_fold<<<1, 32, 0, s>>>(R, reach_base + 2 * i0, i1 - i0, i1 == nb); e->launches++;
     }
-    CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, SC_REACH_OFF + 8 * (size_t)nb, cudaMemcpyDeviceToHost, s));
-    CK(cudaEventRecord(e->ev_sc, s));
-    // physCov scan does not depend on the events: keeps the GPU busy while the host waits for n_events
     const int nblocks = (int)((R.size + SCAN_TILE - 1) / SCAN_TILE);
     k_scan1<<<nblocks, SCAN_THREADS, 0, s>>>(R, e->block_sums.as<uint2>());
     k_scan2<<<1, 1024, 0, s>>>(R, e->block_sums.as<uint2>(), nblocks);
     k_scan3<<<nblocks, SCAN_THREADS, 0, s>>>(R, e->block_sums.as<uint2>());
     e->launches += 3;
-    CK(cudaEventSynchronize(e->ev_sc));
-    if (e->h_sc->error & 1) return fail(PB_ERR_UNSORTED, "a batch is not sorted by pos");
-    if (e->h_sc->error & 8) return fail(PB_ERR_CUDA, "pipeline barrier timed out (internal protocol error)");
-    if (e->h_sc->error & 16) return fail(PB_ERR_UNSUPPORTED, "read longer than 2^24 bases or more than 256 batches in a region");
-    if (e->h_sc->error) return fail(PB_ERR_CUDA, "internal capacity error in k_prep");
-    const uint32_t n_ev = e->h_sc->n_events;
-    R.read_count = e->h_sc->read_count; R.min_depth = e->h_sc->min_depth;
-    {   // hand the per-batch reach to the pileup kernel by value
-        const int32_t* hr = reinterpret_cast<const int32_t*>(reinterpret_cast<const uint8_t*>(e->h_sc) + SC_REACH_OFF);
-        for (int i = 0; i < nb; i++) { img[i].fwd = hr[2 * i]; img[i].back = hr[2 * i + 1]; }
-        if (nb) CK(cudaMemcpyAsync(e->d_batches.p, img.data(), sizeof(DevBatch) * nb, cudaMemcpyHostToDevice, s));
-    }
-    if (n_ev) {
-        // events -> (locus, kind) groups: radix sort of 32-bit keys (only the bits a locus index can have), then k_groups
+    if (evcap) {
+        // events -> (locus, kind) groups: radix sort of `evcap` 32-bit keys (the unused slots carry the largest key), k_groups
         uint32_t* keys_in = e->sort_buf.as<uint32_t>();
         uint32_t* keys_out = keys_in + cap + 4;
         uint32_t* idx_out = keys_out + cap + 4;
         uint32_t* idx_in = e->perm.as<uint32_t>();
-        k_event_keys<<<(n_ev + 255) / 256, 256, 0, s>>>(R.ev_key, keys_in, idx_in, n_ev); e->launches++;
+        k_event_keys<<<(evcap + 255) / 256, 256, 0, s>>>(R, keys_in, idx_in, evcap); e->launches++;
         int end_bit = 1;
         while (end_bit < 32 && (((uint64_t)R.size << 1) >> end_bit)) end_bit++;
+        if (end_bit < 32) end_bit++;                                     // the padding key's extra bit
         size_t tmp = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys_in, keys_out, idx_in, idx_out, (int64_t)n_ev, 0, end_bit, s));
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys_in, keys_out, idx_in, idx_out, (int64_t)evcap, 0, end_bit, s));
         CK(e->cub_tmp.ensure(tmp + 16, false, s));
-        CK(cub::DeviceRadixSort::SortPairs(e->cub_tmp.p, tmp, keys_in, keys_out, idx_in, idx_out, (int64_t)n_ev, 0, end_bit, s));
-        k_groups<<<(n_ev + 255) / 256, 256, 0, s>>>(R, dB, keys_out, idx_out, n_ev); e->launches++;
+        CK(cub::DeviceRadixSort::SortPairs(e->cub_tmp.p, tmp, keys_in, keys_out, idx_in, idx_out, (int64_t)evcap, 0, end_bit, s));
+        k_groups<<<(evcap + 255) / 256, 256, 0, s>>>(R, dB, keys_out, idx_out, evcap); e->launches++;
     }
     if (const char* xf = getenv("PB_EXP")) R.exp_flags = atoi(xf);
     if (time_pileup) CK(cudaEventRecord(e->evp0, s));
@@ -363,7 +380,7 @@ static int compute(pb_engine* e, bool time_pileup) {
     int pv = e->pileup_version;
     if (pv == 0) {
         const int64_t tiles = (R.size + P7_TILE - 1) / P7_TILE;
-        const int64_t depth = R.size > 0 ? (int64_t)(e->h_sc->base_count / (unsigned long long)R.size) : 0;
+        const int64_t depth = R.size > 0 ? (int64_t)(total_seq / (size_t)R.size) : 0;      // stored bases per locus: >= depth
         pv = (tiles >= 256 && depth <= 1000) ? 7 : 5;
     }
     if (R.exp_flags & 256) {               // knock-out: everything but the pileup kernel (what the rest of the pass costs)
@@ -381,7 +398,7 @@ static int compute(pb_engine* e, bool time_pileup) {
         for (int i = 0; i < nb; i++) {
             const DevBatch& d = img[i];
             PBt.b[i].seg = d.seg; PBt.b[i].quals = d.quals; PBt.b[i].bases2 = d.bases2; PBt.b[i].win_first = d.win_first;
-            PBt.b[i].n_cigar = (uint32_t)d.n_cigar; PBt.b[i].fwd = d.fwd; PBt.b[i].back = d.back;
+            PBt.b[i].n_cigar = (uint32_t)d.n_cigar; PBt.b[i].reach = d.reach;
             PBt.b[i].flags = (d.frag ? 1u : 0u) | (d.n_reads ? 2u : 0u);
         }
         if (v7) {
@@ -424,9 +441,9 @@ static int compute(pb_engine* e, bool time_pileup) {
         R.dbg = nullptr;
     }
     // deletion spill: candidates are bounded by the number of deletion groups
-    uint32_t p2 = 1; while (p2 < n_ev) p2 <<= 1;
+    uint32_t p2 = 1; while (p2 < evcap) p2 <<= 1;
     CK(e->spill_scratch.ensure((size_t)p2 * sizeof(int4) + 16, false, s));
-    if (n_ev) { k_spill<<<1, 1024, 2048 * sizeof(int4), s>>>(R, e->spill_scratch.as<int4>(), p2); e->launches++; }
+    if (evcap) { k_spill<<<1, 1024, 2048 * sizeof(int4), s>>>(R, e->spill_scratch.as<int4>(), p2); e->launches++; }
     CK(cudaGetLastError());
     return PB_OK;
 }
@@ -434,11 +451,39 @@ static int compute(pb_engine* e, bool time_pileup) {
 extern "C" int pb_region_compute(pb_engine* e) {
     if (!e || !e->in_region) return fail(PB_ERR_INVALID, "no region");
     CK(cudaSetDevice(e->device));
+    static const bool use_graph = getenv("PB_NOGRAPH") == nullptr;
+    if (use_graph && e->graph_state == 2) {                  // the pass has no host round trip: one call replays it
+        CK(cudaGraphLaunch(e->graph_exec, e->stream));
+        e->launches += e->graph_launches;
+        return PB_OK;
+    }
+    const bool capture = use_graph && e->graph_state == 1;
+    const int64_t l0 = e->launches;
+    if (capture) CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
     int rc = compute(e, false);
-    if (rc != PB_OK) return rc;
     // the group count is only known on the device here: clear through the whole capacity-bounded list
-    k_groups_clear_dev<<<64, 128, 0, e->stream>>>(e->R); e->launches++;
+    if (rc == PB_OK) { k_groups_clear_dev<<<64, 128, 0, e->stream>>>(e->R); e->launches++; }
+    if (capture) {
+        cudaGraph_t g = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+        if (rc != PB_OK || ce != cudaSuccess || !g) {        // something in the pass cannot be captured: stay with plain launches
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            e->graph_state = 3;
+            e->launches = l0;
+            return pb_region_compute(e);
+        }
+        const cudaError_t ci = cudaGraphInstantiate(&e->graph_exec, g, 0);
+        cudaGraphDestroy(g);
+        if (ci != cudaSuccess) { cudaGetLastError(); e->graph_exec = nullptr; e->graph_state = 3; e->launches = l0; return pb_region_compute(e); }
+        e->graph_launches = e->launches - l0;
+        e->graph_state = 2;
+        CK(cudaGraphLaunch(e->graph_exec, e->stream));
+        return PB_OK;
+    }
+    if (rc != PB_OK) return rc;
     e->dirty = false;
+    if (use_graph && e->graph_state == 0) e->graph_state = 1;      // buffers have their final size now
     return PB_OK;
 }
 
@@ -454,6 +499,7 @@ extern "C" int pb_region_compute_timed(pb_engine* e, int iters, float* total_ms,
         // leave the sparse group planes clean for the next iteration
         CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
+        if (e->h_sc->error) return pass_error((uint32_t)e->h_sc->error);
         if (e->h_sc->n_groups) { k_groups_clear<<<(e->h_sc->n_groups + 127) / 128, 128, 0, e->stream>>>(e->R, e->h_sc->n_groups); e->launches++; }
         CK(cudaEventRecord(e->ev1, e->stream));
         CK(cudaEventSynchronize(e->ev1));
@@ -475,11 +521,18 @@ extern "C" int pb_region_finish(pb_engine* e, pb_region_result* res, int32_t* co
     CK(cudaSetDevice(e->device));
     cudaStream_t s = e->stream;
     RegionDev& R = e->R;
-    int rc = compute(e, false);
-    if (rc != PB_OK) { cudaStreamSynchronize(s); return rc; }
-    CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    if (e->h_sc->error) return fail(e->h_sc->error & 4 ? PB_ERR_HASH : PB_ERR_CUDA, "internal error flag set by a kernel");
+    for (int attempt = 0;; attempt++) {
+        int rc = compute(e, false, attempt > 0);
+        if (rc != PB_OK) { cudaStreamSynchronize(s); return rc; }
+        CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (e->h_sc->error == 2 && attempt == 0) {       // the I/D bound did not hold (I/D-only CIGARs): once more, full capacity
+            if ((rc = clean_sparse_planes(e)) != PB_OK) return rc;
+            continue;
+        }
+        if (e->h_sc->error) return pass_error((uint32_t)e->h_sc->error);
+        break;
+    }
     const uint32_t ng = e->h_sc->n_groups;
     // winning strings: sized exactly, then gathered
     std::vector<Group> groups(ng);

@@ -1,8 +1,7 @@
 // pb_kernels.cuh -- sm_100a kernels of the pileup + BaseCall engine.
 //
 // Pipeline per region:
-//   k_prep      thread per read: CIGAR walk -> segments, sparse updates, indel events, physCov diffs
-//   k_index     per batch: window -> first candidate read table
+//   k_prep      thread per read: CIGAR walk -> segments, sparse updates, physCov diffs, window -> first segment table
 //   k_scalars   region coverage / minDepth
 //   (cub radix sort of the indel event keys) -> k_groups -> k_indel_strings
 //   k_scan1/2/3 physCov prefix sums (PileUpRegion.computePhysCov)
@@ -45,7 +44,23 @@ __device__ __forceinline__ void mark_rare(const RegionDev& R, int64_t i) {
     atomicOr(&R.rare_bits[i >> 5], 1u << (i & 31));
 }
 
+// physCov difference array (int2 {count, insert size} per locus) updated with ONE 64-bit add: the count (|sum| < 2^31,
+// there are fewer reads than that) sits in the low word sign-extended, so a negative running count borrows exactly 1
+// from the high word and pc_unpack gives it back; the high word wraps mod 2^32 like the reference's Int.
+__device__ __forceinline__ unsigned long long pc_pack(int32_t dcount, int32_t dins) {
+    return ((unsigned long long)(uint32_t)dins << 32) + (unsigned long long)(long long)dcount;
+}
+__device__ __forceinline__ int2 pc_unpack(int2 d) { d.y += d.x < 0 ? 1 : 0; return d; }
+
 __device__ __forceinline__ uint64_t fnv64(uint64_t h, uint8_t b) { return (h ^ b) * 1099511628211ull; }
+
+// number of 32-locus windows that start at or before `pos` (index into win_first)
+__device__ __forceinline__ int64_t kmin_of(const RegionDev& R, int32_t pos) {
+    const int64_t d = (int64_t)pos - R.start;
+    if (d < 0) return 0;
+    const int64_t k = (d >> 5) + 1;
+    return k > (int64_t)R.n_win + 1 ? (int64_t)R.n_win + 1 : k;
+}
 
 // ---------------------------------------------------------------------------------------------
 // k_prep: one thread per read.  PileUpRegion.addRead (PileUpRegion.scala:102-220) minus the
@@ -57,6 +72,9 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long bc = 0, aligned = 0;
     int rc = 0, unk = 0, fwd = 0, back = 0;
+    // win_first[k] = segment slot of the first read with (pos - start) >= 32 k: thread r owns the windows between its
+    // predecessor's start and its own (usually none or one; long runs are filled by the whole warp further down)
+    int64_t wf0 = 0, wf1 = 0; uint32_t wfv = 0;
     if (r < B.n_reads) {
         const Cfg& cfg = R.cfg;
         const int32_t length = B.read_len[r];
@@ -71,6 +89,8 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
         const uint32_t seq0 = B.seq_off[r];
         const int32_t tlen = B.tlen[r];                                    // every per-read load is issued before the first use
         if (prevStart > aStart) atomicOr(&R.sc->error, 1);                 // batch not sorted by pos
+        wf0 = r == 0 ? 0 : kmin_of(R, prevStart); wf1 = kmin_of(R, aStart); wfv = c0;
+        if (wf1 - wf0 <= 4) { for (int64_t k = wf0; k < wf1; k++) B.win_first[k] = wfv; wf1 = wf0; }
         const int32_t flank = cfg.flank;
         int64_t clipped = 0, reflen = 0;
         for (uint32_t k = c0; k < c1; k++) {
@@ -142,11 +162,28 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
             if (!paired) { s = aStart < aEnd ? aStart : aEnd; e = aStart > aEnd ? aStart : aEnd; }
             else { s = aStart; e = (int64_t)aStart + tlen; }
             ins = wrap32(e - s); s = wrap32(s); e = wrap32(e);
-            if (s >= R.start && s <= R.stop) { atomicAdd(&R.pc_diff[s - R.start].x, 1); atomicAdd(&R.pc_diff[s - R.start].y, ins); }
+            // one 64-bit RED per end instead of two 32-bit ones: count diff in the low word, insert-size diff in the high
+            // word; pc_unpack() removes the borrow a negative count leaves in the high word, so both sums stay exact
+            // (mod 2^32, as the JVM's Int fields are)
+            if (s >= R.start && s <= R.stop) atomicAdd(reinterpret_cast<unsigned long long*>(&R.pc_diff[s - R.start]), pc_pack(1, ins));
             else if (s < R.start && !(e < R.start)) { atomicAdd(&R.sc->phys_cov_start, 1); atomicAdd(&R.sc->insert_size_start, ins); }
-            if (e >= R.start && e <= R.stop) { atomicAdd(&R.pc_diff[e - R.start].x, -1); atomicAdd(&R.pc_diff[e - R.start].y, -ins); }
+            if (e >= R.start && e <= R.stop) atomicAdd(reinterpret_cast<unsigned long long*>(&R.pc_diff[e - R.start]), pc_pack(-1, wrap32(-(int64_t)ins)));
         }
         B.insert_out[r] = ins;
+    }
+    {   // long window runs (gaps in the coverage, the stretch before the first read) and the tail after the last read
+        unsigned longm = __ballot_sync(FULL, wf1 > wf0);
+        while (longm) {
+            const int j = __ffs(longm) - 1; longm &= longm - 1;
+            const long long k0 = __shfl_sync(FULL, (long long)wf0, j), k1 = __shfl_sync(FULL, (long long)wf1, j);
+            const uint32_t v = __shfl_sync(FULL, wfv, j);
+            for (long long k = k0 + (threadIdx.x & 31); k < k1; k += 32) B.win_first[k] = v;
+        }
+        const unsigned lastm = __ballot_sync(FULL, r == B.n_reads - 1);
+        if (lastm) {
+            const long long k1 = __shfl_sync(FULL, (long long)kmin_of(R, r < B.n_reads ? B.pos[r] : 0), __ffs(lastm) - 1);
+            for (long long k = k1 + (threadIdx.x & 31); k <= (long long)R.n_win; k += 32) B.win_first[k] = (uint32_t)B.n_cigar;
+        }
     }
     // warp-aggregate the region scalars, then one atomic per quantity per warp into one of SC_SLOTS slots
     // (same-address L2 atomics serialise; a block-level reduction would make every warp wait for the slowest)
@@ -286,26 +323,6 @@ __global__ void __launch_bounds__(128) k_indel(RegionDev R, const DevBatch* __re
     if (drop) atomicAdd(&R.slots[threadIdx.x & (SC_SLOTS - 1)].dropped_oob, drop);
 }
 
-// ---------------------------------------------------------------------------------------------
-// k_index: win_first[k] = segment slot (cigar offset) of the first read with (pos - start) >= 32*k, k = 0..n_win
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int64_t kmin_of(const RegionDev& R, int32_t pos) {
-    const int64_t d = (int64_t)pos - R.start;
-    if (d < 0) return 0;
-    const int64_t k = (d >> 5) + 1;
-    return k > (int64_t)R.n_win + 1 ? (int64_t)R.n_win + 1 : k;
-}
-
-__global__ void __launch_bounds__(256) k_index(RegionDev R, DevBatch B) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= B.n_reads) return;
-    const int64_t k1 = kmin_of(R, B.pos[r]);
-    const int64_t k0 = r == 0 ? 0 : kmin_of(R, B.pos[r - 1]);
-    const uint32_t so = B.cigar_off[r];
-    for (int64_t k = k0; k < k1; k++) B.win_first[k] = so;
-    if (r == B.n_reads - 1) for (int64_t k = k1; k <= R.n_win; k++) B.win_first[k] = (uint32_t)B.n_cigar;
-}
-
 // region coverage and minDepth (PileUpRegion.scala:36; GenomeRegion.scala:221-224)
 // launched once per group of <= 8 batches with 32 threads: folds the slots, then (last group only)
 // coverage and minDepth
@@ -353,9 +370,14 @@ __global__ void k_fold(RegionDev R, int32_t* reach0, int nb, int last) {
 // inside a group the strict-majority string (PileUp.scala:219-220, the only one hetIndelCall can accept) is
 // found with a Boyer-Moore vote over the 64-bit string identities -- no ordering of the strings is needed.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_event_keys(const EventKey* __restrict__ ev_key, uint32_t* keys, uint32_t* idx, uint32_t n) {
+// `cap` slots are sorted whatever the number of events turns out to be (it is only known on the device): the
+// unused ones get the largest key and sort to the end, so no host round trip sizes the sort
+__global__ void __launch_bounds__(256) k_event_keys(RegionDev R, uint32_t* keys, uint32_t* idx, uint32_t cap) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { keys[i] = (uint32_t)ev_key[i].lk; idx[i] = i; }      // lk = locus index << 1 | kind  < 2^32
+    if (i >= cap) return;
+    const uint32_t n = min(R.sc->n_events, R.ev_cap);
+    keys[i] = i < n ? (uint32_t)R.ev_key[i].lk : 0xFFFFFFFFu;         // lk = locus index << 1 | kind  < 2^32 - 1
+    idx[i] = i;
 }
 
 // byte t of the string of event e (insertion: rotated read bases; deletion: raw reference bytes)
@@ -374,6 +396,7 @@ __global__ void __launch_bounds__(256) k_groups(RegionDev R, const DevBatch* bat
                                                 const uint32_t* perm, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
+    n = min(n, min(R.sc->n_events, R.ev_cap));                           // `n` slots were sorted, the events come first
     const bool is_start = i < n && (i == 0 || keys[i - 1] != keys[i]);
     unsigned starts = __ballot_sync(FULL, is_start);
     while (starts) {
@@ -489,9 +512,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan1(RegionDev R, uint2* bloc
     if (base + SCAN_ITEMS <= R.size) {
         const int4* p = reinterpret_cast<const int4*>(R.pc_diff + base);
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS / 2; k++) { const int4 v = p[k]; acc.x += (unsigned)v.x + (unsigned)v.z; acc.y += (unsigned)v.y + (unsigned)v.w; }
+        for (int k = 0; k < SCAN_ITEMS / 2; k++) {
+            const int4 v = p[k];
+            const int2 a = pc_unpack(make_int2(v.x, v.y)), b = pc_unpack(make_int2(v.z, v.w));
+            acc.x += (unsigned)a.x + (unsigned)b.x; acc.y += (unsigned)a.y + (unsigned)b.y;
+        }
     } else {
-        for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < R.size) { const int2 d = R.pc_diff[base + k]; acc.x += (unsigned)d.x; acc.y += (unsigned)d.y; }
+        for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < R.size) { const int2 d = pc_unpack(R.pc_diff[base + k]); acc.x += (unsigned)d.x; acc.y += (unsigned)d.y; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { acc.x += __shfl_xor_sync(FULL, acc.x, o); acc.y += __shfl_xor_sync(FULL, acc.y, o); }
@@ -543,15 +570,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan3(RegionDev R, const uint2
         for (int k = 0; k < SCAN_ITEMS / 2; k++) {
             const int4 d = p[k];
             p[k] = make_int4(0, 0, 0, 0);
-            run.x += (unsigned)d.x; run.y += (unsigned)d.y; v[2 * k] = run;
-            run.x += (unsigned)d.z; run.y += (unsigned)d.w; v[2 * k + 1] = run;
+            const int2 a = pc_unpack(make_int2(d.x, d.y)), b = pc_unpack(make_int2(d.z, d.w));
+            run.x += (unsigned)a.x; run.y += (unsigned)a.y; v[2 * k] = run;
+            run.x += (unsigned)b.x; run.y += (unsigned)b.y; v[2 * k + 1] = run;
         }
     } else {
 #pragma unroll
         for (int k = 0; k < SCAN_ITEMS; k++) {
             const int64_t i = base + k;
             int2 d = make_int2(0, 0);
-            if (i < R.size) { d = R.pc_diff[i]; R.pc_diff[i] = make_int2(0, 0); }
+            if (i < R.size) { d = pc_unpack(R.pc_diff[i]); R.pc_diff[i] = make_int2(0, 0); }
             run.x += (unsigned)d.x; run.y += (unsigned)d.y;
             v[k] = run;
         }
@@ -683,8 +711,8 @@ __global__ void __launch_bounds__(PILEUP_WARPS * 32) k_pileup(RegionDev R, const
         const int64_t depth = n + r_del;
         const int64_t qtot = in.q[0] + in.q[1] + in.q[2] + in.q[3];
         uint32_t fl = 0;
-        if (R.read_count != 0)                                           // GenomeRegion.scala:229-231
-            fl = classify(call, depth, R.min_depth, ref_class(ref_at(R, (int64_t)R.start + loc)), R.cfg.fix_amb);
+        if (R.sc->read_count != 0)                                       // GenomeRegion.scala:229-231
+            fl = classify(call, depth, R.sc->min_depth, ref_class(ref_at(R, (int64_t)R.start + loc)), R.cfg.fix_amb);
         reinterpret_cast<int4*>(R.o_cnt)[loc] = make_int4((int)c0, (int)c1, (int)c2, (int)c3);
         reinterpret_cast<longlong2*>(R.o_qs)[2 * (int64_t)loc] = make_longlong2((long long)q0, (long long)q1);
         reinterpret_cast<longlong2*>(R.o_qs)[2 * (int64_t)loc + 1] = make_longlong2((long long)q2, (long long)q3);

@@ -116,8 +116,8 @@ __device__ __forceinline__ void finish_locus(const RegionDev& R, int64_t w, int 
         call = compute_call(R.cfg, in, &ilen);
     }
     uint32_t fl = 0;
-    if (R.read_count != 0)                                                                  // GenomeRegion.scala:229-231
-        fl = classify(call, depth, R.min_depth, ref_class(refb), R.cfg.fix_amb);
+    if (R.sc->read_count != 0)                                                              // GenomeRegion.scala:229-231
+        fl = classify(call, depth, R.sc->min_depth, ref_class(refb), R.cfg.fix_amb);      // (both written by k_fold)
     if ((R.exp_flags & 8) && call != 0x1234567812345678ull) return;
     reinterpret_cast<int4*>(R.o_cnt)[loc] = make_int4((int)c[0], (int)c[1], (int)c[2], (int)c[3]);
     reinterpret_cast<longlong2*>(R.o_qs)[2 * (int64_t)loc] = make_longlong2((long long)q[0], (long long)q[1]);

@@ -105,8 +105,8 @@ __global__ void __launch_bounds__((P4_CW + 1) * 32) k_pileup4(RegionDev R, const
             if (bb + lane < n_batches) {
                 const DevBatch& Bl = batches[bb + lane];
                 if (Bl.n_reads) {
-                    const int64_t x = (int64_t)t0 - Bl.fwd + 1;
-                    const int64_t y = (int64_t)t0 + P4_TILE + Bl.back;
+                    const int64_t x = (int64_t)t0 - Bl.reach[0] + 1;
+                    const int64_t y = (int64_t)t0 + P4_TILE + Bl.reach[1];
                     int64_t khi = (y + 31) >> 5; if (khi > R.n_win) khi = R.n_win;
                     my_slo = x <= 0 ? 0u : Bl.win_first[x >> 5];
                     my_shi = (y > ((int64_t)R.n_win << 5)) ? (uint32_t)Bl.n_cigar : Bl.win_first[khi];

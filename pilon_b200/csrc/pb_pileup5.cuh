@@ -70,8 +70,8 @@ __global__ void __launch_bounds__(P5_WARPS * 32, 4) k_pileup5(const RegionDev R,
     if (lane < n_batches) {
         const PileBatch& Bl = PB.b[lane];
         if (Bl.flags & 2) {
-            const int64_t x = (int64_t)w0 - Bl.fwd + 1;
-            const int64_t y = (int64_t)w0 + 32 + Bl.back;
+            const int64_t x = (int64_t)w0 - Bl.reach[0] + 1;
+            const int64_t y = (int64_t)w0 + 32 + Bl.reach[1];
             int64_t khi = (y + 31) >> 5; if (khi > R.n_win) khi = R.n_win;
             my_slo = x <= 0 ? 0u : Bl.win_first[x >> 5];
             const uint32_t shi = (y > ((int64_t)R.n_win << 5)) ? Bl.n_cigar : Bl.win_first[khi];

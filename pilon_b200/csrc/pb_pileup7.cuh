@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
             if (lane < n_batches) {
                 const PileBatch& Bl = PB.b[lane];
                 if (Bl.flags & 2) {
-                    const int64_t x = (int64_t)t0 - Bl.fwd + 1;
-                    const int64_t y = (int64_t)t0 + T + Bl.back;
+                    const int64_t x = (int64_t)t0 - Bl.reach[0] + 1;
+                    const int64_t y = (int64_t)t0 + T + Bl.reach[1];
                     int64_t khi = (y + 31) >> 5; if (khi > R.n_win) khi = R.n_win;
                     my_slo = x <= 0 ? 0u : Bl.win_first[x >> 5];
                     const uint32_t shi = (y > ((int64_t)R.n_win << 5)) ? Bl.n_cigar : Bl.win_first[khi];
