@@ -296,3 +296,45 @@ def test_device_resident_batches_match_host_batches(engine):
     engine.finish(res, ins)
     H.assert_results_equal(res, ref, "device-resident batch vs C oracle")
     assert np.array_equal(ins[0], ins_ref[0])
+
+
+def test_insertion_only_cigars_break_the_event_bound_and_are_retried():
+    """The region pass sizes its indel event list by a host-side bound (CIGAR operations minus reads); reads whose CIGAR
+    is a single I operation break it, the kernels raise the capacity flag and pb_region_finish repeats the pass at full
+    capacity.  Results must match the oracle exactly as if nothing had happened."""
+    rng = random.Random(5)
+    contig = bytes(rng.choice(b"ACGT") for _ in range(1500))
+    reads = []
+    for i in range(40):                                  # ordinary coverage
+        p = 100 + 20 * i
+        reads.append(po.Read(pos=p, cigar=[("M", 80)], bases=contig[p - 1:p + 79], quals=bytes([30]) * 80, mapq=50))
+    for i in range(150):                                 # 150 single-op insertions > the 64-entry slack of the bound
+        p = 300 + 3 * i
+        ins = bytes(rng.choice(b"ACGT") for _ in range(2))
+        reads.append(po.Read(pos=p, cigar=[("I", 2)], bases=ins, quals=bytes([25, 25]), mapq=40))
+    reads.sort(key=lambda r: r.pos)
+    cfg = po.Config(flank=0)
+    e = Engine(0, eng_cfg(cfg))
+    try:
+        res, _ = run_both(e, contig, 1, 1500, [(reads, True)], cfg)
+        assert int(res["insertions"].sum()) == 150
+    finally:
+        e.close()
+
+
+def test_graph_replayed_passes_leave_the_engine_clean(engine):
+    """pb_region_compute: plain pass, captured pass, graph replays -- each must consume and re-zero the sparse planes
+    exactly like pb_region_finish's own pass, so the results read afterwards are still bit-exact."""
+    contig, start, stop, reads = H.clean_case(31, n=9000, start=301, stop=7000, depth=30, n_sites=12)
+    packed = pack_records(reads)
+    ref, ins_ref = H.run_c_oracle(contig, start, stop, [(packed, True)])
+    from pilon_b200.packing import ResultBuffers
+    engine.region_begin(contig, start, stop)
+    engine.add_batch(packed, True)
+    for _ in range(5):
+        engine.compute()
+    res = ResultBuffers(stop + 1 - start, None, 1 << 16, 1 << 20)
+    ins = [np.zeros(packed.n_reads, np.int32)]
+    engine.finish(res, ins)
+    H.assert_results_equal(res, ref, "after five async passes")
+    assert np.array_equal(ins[0], ins_ref[0])
