@@ -63,7 +63,8 @@ __device__ __forceinline__ int64_t udiv_fast(uint64_t n, uint64_t d) {      // d
 __device__ __forceinline__ void finish_locus(const RegionDev& R, int64_t w, int lane, int32_t loc,
                                              const uint32_t c[4], const uint64_t q[4],
                                              uint32_t mqS, uint32_t qS, uint32_t bp, uint32_t fragN,
-                                             uint32_t rb, uint8_t refb) {
+                                             uint32_t rb, uint8_t refb, int2 rc_md = make_int2(-1, 0)) {
+    // rc_md = the region's {read count, minDepth} (k_fold's device scalars) when the caller already holds them
     const bool inr = loc < R.size;
     int32_t r_ins = 0, r_insq = 0, r_del = 0, r_delq = 0, r_q = 0, r_mq = 0, r_clips = 0, r_delfrag = 0;
     uint32_t gi = 0, gd = 0;
@@ -116,8 +117,9 @@ __device__ __forceinline__ void finish_locus(const RegionDev& R, int64_t w, int 
         call = compute_call(R.cfg, in, &ilen);
     }
     uint32_t fl = 0;
-    if (R.sc->read_count != 0)                                                              // GenomeRegion.scala:229-231
-        fl = classify(call, depth, R.sc->min_depth, ref_class(refb), R.cfg.fix_amb);      // (both written by k_fold)
+    if (rc_md.x < 0) rc_md = make_int2(R.sc->read_count, R.sc->min_depth);
+    if (rc_md.x != 0)                                                                       // GenomeRegion.scala:229-231
+        fl = classify(call, depth, rc_md.y, ref_class(refb), R.cfg.fix_amb);
     if ((R.exp_flags & 8) && call != 0x1234567812345678ull) return;
     reinterpret_cast<int4*>(R.o_cnt)[loc] = make_int4((int)c[0], (int)c[1], (int)c[2], (int)c[3]);
     reinterpret_cast<longlong2*>(R.o_qs)[2 * (int64_t)loc] = make_longlong2((long long)q[0], (long long)q[1]);

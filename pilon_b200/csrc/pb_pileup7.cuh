@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
 
     // ---- epilogue: warp per 32-locus window of the tile ----
     const uint32_t dom = S.dom;
+    const int2 rc_md = make_int2(R.sc->read_count, R.sc->min_depth);      // k_fold's device scalars, once per warp
     for (int wl = warp; wl < T / 32; wl += P7_WARPS) {
         const int64_t w = ((int64_t)t0 >> 5) + wl;
         if (w >= R.n_win) break;
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
             n = c[0] + c[1] + c[2] + c[3];
         }
         if (R.exp_flags & 1) { if (c[0] == 0xdeadbeef) R.o_mq[loc] = (int32_t)q[0]; continue; }
-        finish_locus(R, w, lane, (int32_t)loc, c, q, mqS, qS, bp, n - nfc, pre_rb, pre_ref);
+        finish_locus(R, w, lane, (int32_t)loc, c, q, mqS, qS, bp, n - nfc, pre_rb, pre_ref, rc_md);
     }
 }
 
