@@ -388,25 +388,96 @@ __device__ __forceinline__ uint8_t event_byte(const RegionDev& R, const DevBatch
     return b;
 }
 
+// one thread: record the group [g0, ge) of key lk whose most frequent tested string identity is h (cnt events, lowest
+// event index rep)
+__device__ __forceinline__ void emit_group(const RegionDev& R, const DevBatch* batches, const uint32_t* perm, uint64_t lk,
+                                           uint32_t g0, uint32_t ge, uint64_t h, uint32_t cnt, uint32_t rep) {
+    const uint32_t len = ge - g0;
+    const Event wev = R.ev[rep];
+    // hashed identities (long / non-ACGT insertions): make sure the candidate's events really are one string
+    if ((h >> 63) && !(lk & 1)) {
+        uint32_t same = 0;
+        for (uint32_t j = g0; j < ge; j++) {
+            if (R.ev_key[perm[j]].h != h) continue;
+            const Event e2 = R.ev[perm[j]];
+            bool eq = e2.len == wev.len;
+            for (uint32_t t = 0; eq && t < wev.len; t++) eq = event_byte(R, batches, lk, e2, t) == event_byte(R, batches, lk, wev, t);
+            same += eq;
+        }
+        if (same != cnt) atomicOr(&R.sc->error, 4);                  // 63-bit hash collision (never observed)
+    }
+    Group g;
+    g.loc = (int32_t)(lk >> 1); g.kind = (int32_t)(lk & 1) + 1; g.list_len = (int32_t)len;
+    const bool majority = cnt >= 2 && cnt > len / 2;
+    g.win_count = majority ? (int32_t)cnt : 0;                       // only a strict majority is ever consumed
+    g.win_len = majority ? (int32_t)wev.len : 0;
+    g.win_ev = rep; g.pad = 0; g.str_off = 0;
+    int has_n = 0;
+    if (majority) for (uint32_t t = 0; t < wev.len; t++) has_n |= event_byte(R, batches, lk, wev, t) == 'N';   // PileUp.scala:222
+    g.win_has_n = has_n;
+    const uint32_t gi = atomicAdd(&R.sc->n_groups, 1u);
+    if (gi < R.groups_cap) {
+        R.groups[gi] = g;
+        ((lk & 1) ? R.r_gdel : R.r_gins)[g.loc] = gi + 1;            // locus already has its rare bit (k_prep)
+    } else atomicOr(&R.sc->error, 2);
+}
+
 // `keys` = (locus << 1 | kind) sorted, `perm[i]` = original event index of sorted position i.
-// Thread per event finds the group starts; every group is then worked on by the whole warp (a 5000x pile-up has
-// groups of thousands of events): each lane runs the Boyer-Moore vote over its strided share -- a strict majority of
-// the group is a strict majority of at least one share -- and the distinct surviving candidates are counted exactly.
+// Thread per event finds the group starts.  A group of at most 64 events (any ordinary depth) is handled by its own
+// thread: Boyer-Moore vote, recount, record.  Longer groups (a 5000x pile-up has thousands of events per indel) are
+// worked on by the whole warp: each lane votes over its strided share -- a strict majority of the group is a strict
+// majority of at least one share -- and the distinct surviving candidates are counted exactly.
 __global__ void __launch_bounds__(256) k_groups(RegionDev R, const DevBatch* batches, const uint32_t* keys,
                                                 const uint32_t* perm, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     n = min(n, min(R.sc->n_events, R.ev_cap));                           // `n` slots were sorted, the events come first
     const bool is_start = i < n && (i == 0 || keys[i - 1] != keys[i]);
-    unsigned starts = __ballot_sync(FULL, is_start);
+    bool big = false;
+    if (is_start) {
+        const uint32_t key = keys[i];
+        uint64_t h = 0; uint32_t votes = 0, ge = i;
+        for (; ge < n && ge < i + 65 && keys[ge] == key; ge++) {
+            const uint64_t hj = R.ev_key[perm[ge]].h;
+            if (votes == 0) { h = hj; votes = 1; } else if (hj == h) votes++; else votes--;
+        }
+        big = ge == i + 65;                                              // longer than 64: the warp takes it below
+        if (!big) {
+            uint32_t cnt = 0, rep = 0xFFFFFFFFu;
+            for (uint32_t j = i; j < ge; j++) {
+                const uint32_t ej = perm[j];
+                if (R.ev_key[ej].h == h) { cnt++; rep = min(rep, ej); }
+            }
+            emit_group(R, batches, perm, (uint64_t)key, i, ge, h, cnt, rep);
+        }
+    }
+    unsigned starts = __ballot_sync(FULL, big);
     while (starts) {
         const int js = __ffs(starts) - 1; starts &= starts - 1;
         const uint32_t g0 = __shfl_sync(FULL, i, js);
         const uint32_t key = keys[g0];
-        uint32_t lo = g0 + 1, hi = n;                                    // group end: keys are sorted, equal keys contiguous
-        while (lo < hi) { const uint32_t m = lo + ((hi - lo) >> 1); if (keys[m] == key) lo = m + 1; else hi = m; }
+        // group end = first index > g0 whose key differs (keys are sorted, equal keys contiguous): the 32 lanes probe
+        // g0 + 2^lane at once, then split the bracket 32 ways per step -- three or four load latencies for any group size
+        uint32_t lo, hi;
+        {
+            const uint64_t p = (uint64_t)g0 + (1ull << lane);
+            const bool mism = p >= n || keys[p] != key;
+            const int kq = __ffs(__ballot_sync(FULL, mism)) - 1;         // lane 31 always reports a mismatch (n < 2^31)
+            const uint64_t h0 = (uint64_t)g0 + (1ull << kq);
+            hi = h0 < (uint64_t)n ? (uint32_t)h0 : n;
+            lo = kq == 0 ? g0 + 1 : g0 + (1u << (kq - 1)) + 1;
+        }
+        while (lo < hi) {                                                // every index < lo matches, index hi does not (or is n)
+            const uint32_t step = (hi - lo + 31) / 32;
+            const uint64_t p = (uint64_t)lo + (uint64_t)lane * step;
+            const bool mism = p >= hi || keys[p] != key;
+            const int j = __ffs(__ballot_sync(FULL, mism)) - 1;          // >= 0: the last lanes reach hi
+            const uint64_t h1 = (uint64_t)lo + (uint64_t)j * step;
+            const uint32_t nhi = h1 < (uint64_t)hi ? (uint32_t)h1 : hi;
+            lo = j == 0 ? lo : lo + (uint32_t)(j - 1) * step + 1;
+            hi = j == 0 ? lo : nhi;
+        }
         const uint32_t ge = lo, len = ge - g0;
-        const uint64_t lk = key;
         uint64_t cand = 0; uint32_t votes = 0;
         for (uint32_t t = g0 + lane; t < ge; t += 32) {
             const uint64_t hj = R.ev_key[perm[t]].h;
@@ -428,34 +499,7 @@ __global__ void __launch_bounds__(256) k_groups(RegionDev R, const DevBatch* bat
             if (my > cnt) { h = c; cnt = my; rep = myrep; }
             if (my > len / 2) break;                                     // the strict majority, unique
         }
-        if (lane != 0) continue;
-        const Event wev = R.ev[rep];
-        // hashed identities (long / non-ACGT insertions): make sure the candidate's events really are one string
-        if ((h >> 63) && !(lk & 1)) {
-            uint32_t same = 0;
-            for (uint32_t j = g0; j < ge; j++) {
-                if (R.ev_key[perm[j]].h != h) continue;
-                const Event e2 = R.ev[perm[j]];
-                bool eq = e2.len == wev.len;
-                for (uint32_t t = 0; eq && t < wev.len; t++) eq = event_byte(R, batches, lk, e2, t) == event_byte(R, batches, lk, wev, t);
-                same += eq;
-            }
-            if (same != cnt) atomicOr(&R.sc->error, 4);                  // 63-bit hash collision (never observed)
-        }
-        Group g;
-        g.loc = (int32_t)(lk >> 1); g.kind = (int32_t)(lk & 1) + 1; g.list_len = (int32_t)len;
-        const bool majority = cnt >= 2 && cnt > len / 2;
-        g.win_count = majority ? (int32_t)cnt : 0;                       // only a strict majority is ever consumed
-        g.win_len = majority ? (int32_t)wev.len : 0;
-        g.win_ev = rep; g.pad = 0; g.str_off = 0;
-        int has_n = 0;
-        if (majority) for (uint32_t t = 0; t < wev.len; t++) has_n |= event_byte(R, batches, lk, wev, t) == 'N';   // PileUp.scala:222
-        g.win_has_n = has_n;
-        const uint32_t gi = atomicAdd(&R.sc->n_groups, 1u);
-        if (gi < R.groups_cap) {
-            R.groups[gi] = g;
-            ((lk & 1) ? R.r_gdel : R.r_gins)[g.loc] = gi + 1;            // locus already has its rare bit (k_prep)
-        } else atomicOr(&R.sc->error, 2);
+        if (lane == 0) emit_group(R, batches, perm, (uint64_t)key, g0, ge, h, cnt, rep);
     }
 }
 
