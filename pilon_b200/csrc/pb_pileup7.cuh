@@ -54,6 +54,7 @@ struct __align__(16) Tile7 {
     uint32_t slo[PB_MAXB], nseg[PB_MAXB];
     uint32_t dom;                // 0 = not chosen yet ((adjMq + 1) >= 1 always)
     uint32_t next;               // next flat grab index to hand out
+    int32_t read_count, min_depth;   // the region's scalars (k_fold), fetched during set-up for the epilogue
     uint2 slow[P7_WARPS][P7_SLOW_CAP];   // per warp: (batch, descriptor index) of segments whose (adjMq + 1) != dom
 };
 
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
     {
         uint32_t* z = reinterpret_cast<uint32_t*>(&S.A[0][0]);
         for (int i = tid; i < 10 * T; i += P7_WARPS * 32) z[i] = 0;
-        if (tid == 0) { S.dom = 0; S.next = 0; }
+        if (tid == 0) { S.dom = 0; S.next = 0; S.read_count = R.sc->read_count; S.min_depth = R.sc->min_depth; }
         if (warp == 0) {
             uint32_t my_slo = 0, my_nseg = 0;
             if (lane < n_batches) {
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
 
     // ---- epilogue: warp per 32-locus window of the tile ----
     const uint32_t dom = S.dom;
-    const int2 rc_md = make_int2(R.sc->read_count, R.sc->min_depth);      // k_fold's device scalars, once per warp
+    const int2 rc_md = make_int2(S.read_count, S.min_depth);
     for (int wl = warp; wl < T / 32; wl += P7_WARPS) {
         const int64_t w = ((int64_t)t0 >> 5) + wl;
         if (w >= R.n_win) break;
