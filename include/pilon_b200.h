@@ -233,9 +233,12 @@ int pb_region_compute_timed(pb_engine* e, int iters, float* total_ms, float* pil
                             int64_t* launches);
 
 /* Same compute pass, launched on the engine's stream without timing and without waiting for it to
- * finish (one short internal wait for an 8 KB scalar read-back remains): lets a caller keep several
- * engines -- one per host thread -- busy on one GPU so that the small kernels of one region overlap
- * the large kernels of another.  Synchronise the stream (pb_stream) before reading anything. */
+ * finish: the pass has no host round trip (sizes and scalars stay on the device), so it is enqueued at
+ * once; from the third call on the same batch set it is replayed as one captured CUDA graph
+ * (PB_NOGRAPH=1 disables that).  Lets a caller keep several engines -- one per host thread -- busy on
+ * one GPU so that the small kernels of one region overlap the large kernels of another.  Error flags
+ * of such a pass are only reported by pb_region_finish / pb_region_compute_timed.  Synchronise the
+ * stream (pb_stream) before reading anything. */
 int pb_region_compute(pb_engine* e);
 
 /* Raw CUDA stream handle (cudaStream_t) so callers can order their own copies against the engine. */

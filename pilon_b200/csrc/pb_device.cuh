@@ -70,7 +70,7 @@ struct DevBatch {
 // k_prep spreads its per-warp partial sums over SC_SLOTS slots (same-address L2 atomics serialise);
 // k_scalars folds them into the Scalars block.
 static constexpr int SC_SLOTS = 64;
-struct ScalarSlot { unsigned long long base_count, aligned_bases; int read_count, unknown_ops, dropped_oob, pad; int fwd[8], back[8]; };
+struct ScalarSlot { unsigned long long base_count, aligned_bases; int read_count, unknown_ops, dropped_oob; unsigned n_work; int fwd[8], back[8]; };
 
 struct Scalars {
     unsigned long long base_count;      // PileUpRegion.baseCount
@@ -111,6 +111,8 @@ struct RegionDev {
     Group* groups; uint32_t groups_cap;
     uint8_t* str_pool; uint64_t str_cap;
     int4* work;  uint32_t work_cap;     // trusted in-region I / D ops queued by k_prep for k_indel: (read, op slot, readOffset | batch << 24, locus)
+    uint32_t work_slots, work_sub;      // the queue is work_slots sub-queues of work_sub entries, one counter each (ScalarSlot.n_work):
+                                        // a single counter is a hot address every warp with an indel would wait on
     int4* cand;  uint32_t cand_cap;     // unordered pass-1 DEL candidates: (locus index, deletions, length, -)
     ScalarSlot* slots;                  // [SC_SLOTS] k_prep partial sums
     int32_t exp_flags;                  // PB_EXP timing experiments (results invalid): 1 skip epilogue, 2 skip compute, 4 skip staging copies

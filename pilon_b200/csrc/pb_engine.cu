@@ -327,6 +327,8 @@ static int compute(pb_engine* e, bool time_pileup, bool full_cap = false) {
     R.groups = e->groups.as<Group>(); R.groups_cap = cap;
     R.cand = e->cand.as<int4>(); R.cand_cap = cap;
     R.work = e->work.as<int4>(); R.work_cap = evcap;
+    R.work_slots = full_cap ? 1u : (uint32_t)SC_SLOTS;           // the retry pass must not fail on an unlucky spread
+    R.work_sub = std::max<uint32_t>(1u, cap / R.work_slots);
     R.str_pool = e->str_pool.as<uint8_t>(); R.str_cap = e->str_pool.cap;
     std::vector<DevBatch>& img = e->img_host;
     img.resize(nb);

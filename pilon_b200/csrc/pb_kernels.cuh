@@ -138,8 +138,9 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
                                          : (locus >= R.start && locus <= R.stop && locus + len - 1 >= R.start && locus + len - 1 <= R.stop);
                 if (valid && readOffset >= tlo && readOffset < thi && inr) {
                     if (readOffset >= (1 << 24) || batch_id >= 256) atomicOr(&R.sc->error, 16);
-                    const uint32_t wi = atomicAdd(&R.sc->n_work, 1u);
-                    if (wi < R.work_cap) R.work[wi] = make_int4((int)r, (int)k, (int)(readOffset & 0xFFFFFF) | (int)(batch_id << 24), (int)locus);
+                    const uint32_t sq = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (R.work_slots - 1);
+                    const uint32_t wi = atomicAdd(&R.slots[sq].n_work, 1u);
+                    if (wi < R.work_sub) R.work[(size_t)sq * R.work_sub + wi] = make_int4((int)r, (int)k, (int)(readOffset & 0xFFFFFF) | (int)(batch_id << 24), (int)locus);
                     else atomicOr(&R.sc->error, 2);
                 }
             } else if (op == 5 || op == 3) {                                                     // H, N  :207-210
@@ -210,10 +211,20 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
 // bases (as the segment of the D op's own slot) and the event record for the majority vote.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_indel(RegionDev R, const DevBatch* __restrict__ batches) {
-    const uint32_t n_work = min(R.sc->n_work, R.work_cap);
+    __shared__ uint32_t pre[SC_SLOTS + 1];                    // flat item index -> (sub-queue, entry)
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (uint32_t q = 0; q < (uint32_t)SC_SLOTS; q++) { pre[q] = acc; if (q < R.work_slots) acc += min(R.slots[q].n_work, R.work_sub); }
+        pre[SC_SLOTS] = acc;
+    }
+    __syncthreads();
+    const uint32_t n_work = pre[SC_SLOTS];
     unsigned long long bc = 0; int drop = 0;
     for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n_work; wi += gridDim.x * blockDim.x) {
-        const int4 it = R.work[wi];
+        uint32_t q = 0;
+#pragma unroll
+        for (uint32_t stp = SC_SLOTS / 2; stp > 0; stp >>= 1) if (pre[q + stp] <= wi) q += stp;
+        const int4 it = R.work[(size_t)q * R.work_sub + (wi - pre[q])];
         const int64_t r = it.x; const uint32_t k = (uint32_t)it.y;
         const uint32_t batch_id = (uint32_t)it.z >> 24;
         const int64_t readOffset = it.z & 0xFFFFFF, locus = it.w;
@@ -336,7 +347,7 @@ __global__ void k_fold(RegionDev R, int32_t* reach0, int nb, int last) {
         bc += sl.base_count; al += sl.aligned_bases; rc += sl.read_count; unk += sl.unknown_ops; drop += sl.dropped_oob;
 #pragma unroll
         for (int j = 0; j < 8; j++) { fw[j] = max(fw[j], sl.fwd[j]); bk[j] = max(bk[j], sl.back[j]); }
-        ScalarSlot z = {}; sl = z;
+        ScalarSlot z = {}; z.n_work = sl.n_work; sl = z;     // the I/D sub-queue counters live until k_indel has run
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
