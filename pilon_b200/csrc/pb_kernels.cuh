@@ -219,8 +219,10 @@ __global__ void __launch_bounds__(128) k_indel(RegionDev R, const DevBatch* __re
     }
     __syncthreads();
     const uint32_t n_work = pre[SC_SLOTS];
+    if (blockIdx.x == 0 && threadIdx.x == 0) R.sc->n_events = n_work;     // event slots in use (one per work item, some stay empty)
     unsigned long long bc = 0; int drop = 0;
     for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n_work; wi += gridDim.x * blockDim.x) {
+        if (wi < R.ev_cap) R.ev_key[wi].lk = ~0ull;                      // "no event" until this item records one
         uint32_t q = 0;
 #pragma unroll
         for (uint32_t stp = SC_SLOTS / 2; stp > 0; stp >>= 1) if (pre[q + stp] <= wi) q += stp;
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(128) k_indel(RegionDev R, const DevBatch* __re
                             hh = fnv64(hh, b);
                         }
                         h = exact ? (h | ((uint64_t)len << 56)) : ((hh >> 1) | (1ull << 63));
-                        const uint32_t ei = atomicAdd(&R.sc->n_events, 1u);
+                        const uint32_t ei = wi;                              // event slot = work item: no shared counter
                         if (ei < R.ev_cap) {
                             R.ev_key[ei].lk = ((uint64_t)i << 1); R.ev_key[ei].h = h;
                             Event ev; ev.src = src; ev.len = (uint32_t)len; ev.rot = rm; ev.batch = batch_id;
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(128) k_indel(RegionDev R, const DevBatch* __re
                         atomicAdd(&R.rare[i].del, 1);
                         if (B.frag) atomicAdd(&R.rare[i].delfrag, 1);
                         mark_rare(R, i);
-                        const uint32_t ei = atomicAdd(&R.sc->n_events, 1u);
+                        const uint32_t ei = wi;                              // event slot = work item: no shared counter
                         if (ei < R.ev_cap) {
                             R.ev_key[ei].lk = ((uint64_t)i << 1) | 1; R.ev_key[ei].h = (uint64_t)len;
                             Event ev; ev.src = 0; ev.len = (uint32_t)len; ev.rot = 0; ev.batch = batch_id;
@@ -387,7 +389,8 @@ __global__ void __launch_bounds__(256) k_event_keys(RegionDev R, uint32_t* keys,
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cap) return;
     const uint32_t n = min(R.sc->n_events, R.ev_cap);
-    keys[i] = i < n ? (uint32_t)R.ev_key[i].lk : 0xFFFFFFFFu;         // lk = locus index << 1 | kind  < 2^32 - 1
+    const uint64_t lk = i < n ? R.ev_key[i].lk : ~0ull;              // ~0: a work item that recorded no event
+    keys[i] = lk == ~0ull ? 0xFFFFFFFFu : (uint32_t)lk;               // lk = locus index << 1 | kind  < 2^32 - 1
     idx[i] = i;
 }
 
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(256) k_groups(RegionDev R, const DevBatch* bat
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     n = min(n, min(R.sc->n_events, R.ev_cap));                           // `n` slots were sorted, the events come first
-    const bool is_start = i < n && (i == 0 || keys[i - 1] != keys[i]);
+    const bool is_start = i < n && keys[i] != 0xFFFFFFFFu && (i == 0 || keys[i - 1] != keys[i]);   // padding keys sort last
     bool big = false;
     if (is_start) {
         const uint32_t key = keys[i];
