@@ -175,9 +175,9 @@ def pin_batch(torch, c):
     n = 0
     for name, count, width in _BATCH_FIELDS:
         nb = _field_bytes(c, count, width)
-        if name == "quals" and c.quals4:
-            nb = int(c.n_seq) // 2
-            name = "quals4"
+        if name == "quals" and c.qual_codes:
+            nb = (int(c.n_seq) * int(c.qual_code_bits) + 7) // 8
+            name = "qual_codes"
         if nb:
             rt.cudaHostRegister(getattr(c, name), nb, 0)
             n += nb
@@ -356,8 +356,9 @@ def run_gpu_arm(args):
     if args.quals8:
         for r in regions:
             for b in r.batches:
-                b.c.quals4 = None
-    q4 = all(bool(b.c.quals4) for r in regions for b in r.batches)
+                b.c.qual_codes = None
+    q4 = all(bool(b.c.qual_codes) for r in regions for b in r.batches)
+    qbits = max([int(b.c.qual_code_bits) for r in regions for b in r.batches] or [0]) if q4 else 8
     h2d = sum(pin_batch(torch, b.c) for r in regions for b in r.batches) + sum(r.size + 1 for r in regions)
     planes = FIX_PLANES if args.planes == "fix" else None
     n_workers = args.e2e_workers
@@ -453,8 +454,8 @@ def run_gpu_arm(args):
                           "timing": "CUDA events: first launch of the timed steps -> last engine stream done, regions launched by %d host threads onto one stream per region; "
                                     "sequential_ms_per_step = sum of per-region event intervals with one region at a time (the pileup kernel's launches are timed in that pass)" % args.host_threads,
                           "e2e_planes": args.planes,
-                          "e2e_quals": ("4-bit codes + 16-entry table (the workload has <= 16 distinct quality bytes), expanded on the device"
-                                        if q4 else "1 byte per base")},
+                          "e2e_quals": ("%d-bit codes + table (the workload has <= %d distinct quality bytes), expanded on the device"
+                                        % (qbits, 1 << qbits) if q4 else "1 byte per base")},
                "wall_ms_per_step": wall_step_ms, "sequential_ms_per_step": seq_step_ms,
                "e2e": {"value": job_aligned / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": job_h2d, "d2h_bytes_per_step": job_d2h,
                        "ms_per_step": 1e3 * e2e_sec, "streams_per_gpu": n_workers},
@@ -482,7 +483,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-workers", type=int, default=3, help="engines (host threads + streams) per GPU in the e2e arm")
     ap.add_argument("--quals8", action="store_true", help="e2e arm: upload one quality byte per base even when the batch "
-                    "offers the 4-bit transport (pb_batch.quals4)")
+                    "offers the packed transport (pb_batch.qual_codes)")
     ap.add_argument("--host-threads", type=int, default=4, help="host threads feeding region passes to the GPU")
     args = ap.parse_args()
     if args.impl == "reference":

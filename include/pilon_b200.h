@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB_ABI_VERSION 2
+#define PB_ABI_VERSION 3
 
 /* ---- status codes ---------------------------------------------------------------------- */
 #define PB_OK                 0
@@ -98,13 +98,15 @@ typedef struct pb_batch {
     const uint8_t*  exc_base;   /* [n_exc] original ASCII read byte                           */
     const uint8_t*  exc_qual;   /* [n_exc] original quality byte                              */
     int32_t mem;                /* PB_MEM_HOST | PB_MEM_DEVICE                                */
-    int32_t reserved;
+    int32_t qual_code_bits;     /* 0: no packed qualities; 3 or 4: width of the codes in qual_codes */
     /* Optional compact transport of `quals` for PB_MEM_HOST batches (the end-to-end path is PCIe-bound):
-     * when quals4 is non-NULL the engine uploads these n_seq / 2 bytes instead of `quals` and expands
-     * them on the device, quals[i] = qual_lut[(quals4[i >> 1] >> (4 * (i & 1))) & 15].  Possible whenever
-     * a batch uses at most 16 distinct quality bytes (binned instrument qualities); pb_packer_view fills
-     * it in automatically, else leaves it NULL.  `quals` may then be NULL for the engine. */
-    const uint8_t*  quals4;     /* [n_seq / 2] or NULL                                        */
+     * when qual_codes is non-NULL the engine uploads these ceil(n_seq * qual_code_bits / 8) bytes instead
+     * of `quals` and expands them on the device: code i occupies bits [i * bits, (i + 1) * bits) of the
+     * little-endian bit stream and quals[i] = qual_lut[code i].  Possible whenever a batch uses at most
+     * 8 (3-bit) or 16 (4-bit) distinct quality bytes -- binned instrument qualities; pb_packer_view fills
+     * it in automatically with the narrowest width, else leaves it NULL.  `quals` may then be NULL for
+     * the engine.  The buffer must be readable up to the next multiple of 16 bytes. */
+    const uint8_t*  qual_codes; /* packed codes or NULL                                       */
     uint8_t qual_lut[16];       /* code -> quality byte (0..127, or 0x80)                     */
 } pb_batch;
 

@@ -34,8 +34,8 @@ class pb_batch(C.Structure):
                 ("mapq", C.c_void_p), ("flags", C.c_void_p), ("cigar_off", C.c_void_p),
                 ("cigar", C.c_void_p), ("seq_off", C.c_void_p), ("quals", C.c_void_p),
                 ("bases2", C.c_void_p), ("exc_idx", C.c_void_p), ("exc_base", C.c_void_p),
-                ("exc_qual", C.c_void_p), ("mem", C.c_int32), ("reserved", C.c_int32),
-                ("quals4", C.c_void_p), ("qual_lut", C.c_uint8 * 16)]
+                ("exc_qual", C.c_void_p), ("mem", C.c_int32), ("qual_code_bits", C.c_int32),
+                ("qual_codes", C.c_void_p), ("qual_lut", C.c_uint8 * 16)]
 
 
 class pb_indel(C.Structure):
@@ -108,7 +108,7 @@ def load_library() -> C.CDLL:
                  "pb_packer_destroy", "pb_packer_reset", "pb_packer_add", "pb_packer_add_many",
                  "pb_packer_view"):
         getattr(lib, name).restype = C.c_int
-    if lib.pb_abi_version() != 2:
+    if lib.pb_abi_version() != 3:
         raise RuntimeError("libpilonb200.so ABI version mismatch")
     _lib = lib
     return lib

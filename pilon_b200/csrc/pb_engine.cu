@@ -220,7 +220,7 @@ static int stage(pb_engine* e, HostBatch& hb, const T* src, size_t n, int mem, c
     return PB_OK;
 }
 
-// 4-bit quality codes -> quality bytes (pb_batch.quals4).  A thread expands 16 bases: the low / high half of an input
+// 4-bit quality codes -> quality bytes (pb_batch.qual_codes, qual_code_bits == 4).  A thread expands 16 bases: the low / high half of an input
 // word is directly a PRMT selector (one code per nibble); codes 0..7 and 8..15 come from two 8-byte pools, bit 3 picks.
 __global__ void __launch_bounds__(256) k_unpack_quals4(const uint2* __restrict__ in, uint4* __restrict__ out, size_t groups,
                                                        uint32_t l0, uint32_t l1, uint32_t l2, uint32_t l3) {
@@ -233,6 +233,21 @@ __global__ void __launch_bounds__(256) k_unpack_quals4(const uint2* __restrict__
         return (hi & m) | (lo & ~m);
     };
     out[i] = make_uint4(four(w.x & 0xFFFFu), four(w.x >> 16), four(w.y & 0xFFFFu), four(w.y >> 16));
+}
+
+// 3-bit quality codes: a thread expands 32 bases = 96 bits = three input words into two 16-byte outputs.  Four codes
+// (12 bits) are spread into the four nibbles of a PRMT selector over the 8-entry table.
+__global__ void __launch_bounds__(256) k_unpack_quals3(const uint32_t* __restrict__ in, uint4* __restrict__ out, size_t groups,
+                                                       uint32_t l0, uint32_t l1) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= groups) return;
+    const uint32_t w0 = in[3 * i], w1 = in[3 * i + 1], w2 = in[3 * i + 2];
+    auto four = [&](uint32_t x) {                                    // x: 12 bits = 4 codes
+        const uint32_t sel = (x & 0x7u) | ((x & 0x38u) << 1) | ((x & 0x1C0u) << 2) | ((x & 0xE00u) << 3);
+        return __byte_perm(l0, l1, sel);
+    };
+    out[2 * i] = make_uint4(four(w0 & 0xFFFu), four((w0 >> 12) & 0xFFFu), four(__funnelshift_r(w0, w1, 24) & 0xFFFu), four((w1 >> 4) & 0xFFFu));
+    out[2 * i + 1] = make_uint4(four((w1 >> 16) & 0xFFFu), four(__funnelshift_r(w1, w2, 28) & 0xFFFu), four((w2 >> 8) & 0xFFFu), four((w2 >> 20) & 0xFFFu));
 }
 
 extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, int long_read_type) {
@@ -253,20 +268,25 @@ extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, in
 #define ST(field, count) if ((rc = stage(e, hb, b->field, (size_t)(count), b->mem, &d.field)) != PB_OK) return rc
     ST(pos, n); ST(tlen, n); ST(read_len, n); ST(mapq, n); ST(flags, n); ST(cigar_off, n + 1);
     ST(cigar, b->n_cigar); ST(seq_off, n); ST(bases2, b->n_seq / 4);
-    if (b->mem == PB_MEM_HOST && b->quals4) {          // compact transport: upload 4-bit codes, expand on the device
-        const size_t groups = ((size_t)b->n_seq + 15) / 16;
+    if (b->mem == PB_MEM_HOST && b->qual_codes) {      // compact transport: upload 3- / 4-bit codes, expand on the device
+        const int bits = b->qual_code_bits;
+        if (bits != 3 && bits != 4) return fail(PB_ERR_INVALID, "qual_code_bits must be 3 or 4 when qual_codes is given");
+        const size_t per = bits == 4 ? 16 : 32;                       // bases expanded by one thread
+        const size_t groups = ((size_t)b->n_seq + per - 1) / per;
+        const size_t in_bytes = ((size_t)b->n_seq * bits + 7) / 8;
         void *pin = nullptr, *pout = nullptr;
-        CK(cudaMallocAsync(&pin, groups * 8 + 64, e->stream)); hb.owned.push_back(pin);
-        CK(cudaMallocAsync(&pout, groups * 16 + 64, e->stream)); hb.owned.push_back(pout);
+        CK(cudaMallocAsync(&pin, groups * (bits == 4 ? 8 : 12) + 64, e->stream)); hb.owned.push_back(pin);
+        CK(cudaMallocAsync(&pout, groups * per + 64, e->stream)); hb.owned.push_back(pout);
         if (b->n_seq) {
-            CK(cudaMemcpyAsync(pin, b->quals4, (size_t)b->n_seq / 2, cudaMemcpyHostToDevice, e->stream));
+            CK(cudaMemcpyAsync(pin, b->qual_codes, in_bytes, cudaMemcpyHostToDevice, e->stream));
             uint32_t l[4]; memcpy(l, b->qual_lut, 16);
-            k_unpack_quals4<<<(unsigned)((groups + 255) / 256), 256, 0, e->stream>>>((const uint2*)pin, (uint4*)pout, groups, l[0], l[1], l[2], l[3]);
+            if (bits == 4) k_unpack_quals4<<<(unsigned)((groups + 255) / 256), 256, 0, e->stream>>>((const uint2*)pin, (uint4*)pout, groups, l[0], l[1], l[2], l[3]);
+            else k_unpack_quals3<<<(unsigned)((groups + 255) / 256), 256, 0, e->stream>>>((const uint32_t*)pin, (uint4*)pout, groups, l[0], l[1]);
             e->launches++;
         }
         d.quals = (const uint8_t*)pout;
     } else {
-        if (!b->quals && b->n_seq) return fail(PB_ERR_INVALID, "batch has neither quals nor quals4");
+        if (!b->quals && b->n_seq) return fail(PB_ERR_INVALID, "batch has neither quals nor qual_codes");
         ST(quals, b->n_seq);
     }
     ST(exc_idx, b->n_exc); ST(exc_base, b->n_exc); ST(exc_qual, b->n_exc);
@@ -599,7 +619,7 @@ extern "C" int pb_region_finish(pb_engine* e, pb_region_result* res, int32_t* co
 // ---------------------------------------------------------------------------------------------
 struct pb_packer {
     std::vector<int32_t> pos, tlen, read_len;
-    std::vector<uint8_t> mapq, flags, quals, bases2, exc_base, exc_qual, quals4;
+    std::vector<uint8_t> mapq, flags, quals, bases2, exc_base, exc_qual, qual_codes;
     std::vector<uint32_t> cigar_off{0}, cigar, seq_off, exc_idx;
     // alphabet of the stored quality bytes: at most 16 distinct values -> the 4-bit transport is possible
     uint8_t code_of[256]; uint8_t lut[16]; int n_codes = 0; bool q4_ok = true;
@@ -617,7 +637,7 @@ extern "C" int pb_packer_reset(pb_packer* p) {
     if (!p) return fail(PB_ERR_INVALID, "null");
     p->pos.clear(); p->tlen.clear(); p->read_len.clear(); p->mapq.clear(); p->flags.clear(); p->quals.clear();
     p->bases2.clear(); p->exc_base.clear(); p->exc_qual.clear(); p->cigar_off.assign(1, 0); p->cigar.clear();
-    p->seq_off.clear(); p->exc_idx.clear(); p->quals4.clear();
+    p->seq_off.clear(); p->exc_idx.clear(); p->qual_codes.clear();
     memset(p->code_of, 0xFF, sizeof(p->code_of)); memset(p->lut, 0, sizeof(p->lut)); p->n_codes = 0; p->q4_ok = true; p->note(0);
     return PB_OK;
 }
@@ -676,11 +696,17 @@ extern "C" int pb_packer_view(pb_packer* p, pb_batch* b) {
     b->cigar = p->cigar.data(); b->seq_off = p->seq_off.data(); b->quals = p->quals.data();
     b->bases2 = p->bases2.data(); b->exc_idx = p->exc_idx.data(); b->exc_base = p->exc_base.data();
     b->exc_qual = p->exc_qual.data(); b->mem = PB_MEM_HOST;
-    if (p->q4_ok) {                                     // binned qualities: offer the 4-bit transport as well
+    if (p->q4_ok) {                                     // binned qualities: offer the packed transport as well
         const size_t ns = p->quals.size();
-        p->quals4.assign(ns / 2 + 16, 0);
-        for (size_t i = 0; i < ns; i++) p->quals4[i >> 1] |= (uint8_t)(p->code_of[p->quals[i]] << (4 * (i & 1)));
-        b->quals4 = p->quals4.data(); memcpy(b->qual_lut, p->lut, 16);
+        const int bits = p->n_codes <= 8 ? 3 : 4;
+        p->qual_codes.assign((ns * bits + 7) / 8 + 32, 0);
+        for (size_t i = 0; i < ns; i++) {
+            const uint32_t c = p->code_of[p->quals[i]];
+            const size_t bit = i * bits;
+            p->qual_codes[bit >> 3] |= (uint8_t)(c << (bit & 7));
+            if ((bit & 7) + bits > 8) p->qual_codes[(bit >> 3) + 1] |= (uint8_t)(c >> (8 - (bit & 7)));
+        }
+        b->qual_codes = p->qual_codes.data(); b->qual_code_bits = bits; memcpy(b->qual_lut, p->lut, 16);
     }
     return PB_OK;
 }

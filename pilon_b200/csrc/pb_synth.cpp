@@ -153,8 +153,8 @@ struct Gen {
     std::vector<int32_t> pos, tlen, read_len;
     std::vector<uint8_t> mapq, flags, quals, bases2, exc_base, exc_qual;
     std::vector<uint32_t> cigar_off, cigar, seq_off, exc_idx;
-    std::vector<uint8_t> quals4;            // 4-bit transport of quals (pb_batch.quals4) when <= 16 distinct bytes occur
-    uint8_t lut[16] = {0}; bool q4_ok = false;
+    std::vector<uint8_t> qual_codes;        // packed transport of quals (pb_batch.qual_codes) when <= 16 distinct bytes occur
+    uint8_t lut[16] = {0}; bool q4_ok = false; int code_bits = 0;
     int64_t aligned = 0;
 };
 
@@ -336,10 +336,21 @@ void* ps_generate(const ps_params* Pp, int64_t lo, int64_t hi) {
         for (int v = 0; v < 256; v++) if (seen[v]) { if (n_codes < 16) { code_of[v] = (uint8_t)n_codes; g->lut[n_codes] = (uint8_t)v; } n_codes++; }
         g->q4_ok = n_codes <= 16;
         if (g->q4_ok) {
-            g->quals4.assign((size_t)ns / 2 + 16, 0);
+            const int bits = n_codes <= 8 ? 3 : 4;
+            g->code_bits = bits;
+            g->qual_codes.assign(((size_t)ns * bits + 7) / 8 + 32, 0);
+            if (bits == 4) {
 #pragma omp parallel for schedule(static)
-            for (int64_t j = 0; j < ns / 2; j++)
-                g->quals4[j] = (uint8_t)(code_of[g->quals[2 * j]] | (code_of[g->quals[2 * j + 1]] << 4));
+                for (int64_t j = 0; j < ns / 2; j++)
+                    g->qual_codes[j] = (uint8_t)(code_of[g->quals[2 * j]] | (code_of[g->quals[2 * j + 1]] << 4));
+            } else {                                             // 8 codes = 24 bits = 3 bytes: groups never share a byte
+#pragma omp parallel for schedule(static)
+                for (int64_t j = 0; j < (ns + 7) / 8; j++) {
+                    uint32_t v = 0;
+                    for (int t = 0; t < 8; t++) if (8 * j + t < ns) v |= (uint32_t)code_of[g->quals[8 * j + t]] << (3 * t);
+                    g->qual_codes[3 * j] = (uint8_t)v; g->qual_codes[3 * j + 1] = (uint8_t)(v >> 8); g->qual_codes[3 * j + 2] = (uint8_t)(v >> 16);
+                }
+            }
         }
     }
     return g;
@@ -355,7 +366,7 @@ void ps_view(void* h, pb_batch* b, int64_t* aligned) {
     b->cigar = g->cigar.data(); b->seq_off = g->seq_off.data(); b->quals = g->quals.data();
     b->bases2 = g->bases2.data(); b->exc_idx = g->exc_idx.data(); b->exc_base = g->exc_base.data();
     b->exc_qual = g->exc_qual.data(); b->mem = PB_MEM_HOST;
-    if (g->q4_ok) { b->quals4 = g->quals4.data(); memcpy(b->qual_lut, g->lut, 16); }
+    if (g->q4_ok) { b->qual_codes = g->qual_codes.data(); b->qual_code_bits = g->code_bits; memcpy(b->qual_lut, g->lut, 16); }
     if (aligned) *aligned = g->aligned;
 }
 

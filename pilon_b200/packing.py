@@ -40,7 +40,8 @@ class ReadBatch:
     exc_idx: np.ndarray
     exc_base: np.ndarray
     exc_qual: np.ndarray
-    quals4: Optional[np.ndarray] = None        # pb_batch.quals4: 4-bit codes, two bases per byte (compact H2D transport)
+    qual_codes: Optional[np.ndarray] = None    # pb_batch.qual_codes: packed 3- or 4-bit codes (compact H2D transport)
+    qual_code_bits: int = 0                    # pb_batch.qual_code_bits
     qual_lut: Optional[np.ndarray] = None      # pb_batch.qual_lut: code -> quality byte
 
     @property
@@ -61,29 +62,40 @@ class ReadBatch:
             arr = getattr(self, name)
             assert arr.flags["C_CONTIGUOUS"]
             setattr(b, name, arr.ctypes.data)
-        if self.quals4 is not None:
-            assert self.quals4.flags["C_CONTIGUOUS"] and self.quals4.shape[0] >= self.quals.shape[0] // 2
-            b.quals4 = self.quals4.ctypes.data
+        if self.qual_codes is not None:
+            assert self.qual_codes.flags["C_CONTIGUOUS"]
+            assert self.qual_codes.shape[0] >= (self.quals.shape[0] * self.qual_code_bits + 7) // 8
+            b.qual_codes = self.qual_codes.ctypes.data
+            b.qual_code_bits = self.qual_code_bits
             for i in range(16):
                 b.qual_lut[i] = int(self.qual_lut[i])
         b.mem = capi.PB_MEM_HOST
         b._keepalive = self
         return b
 
-    def with_quals4(self) -> "ReadBatch":
-        """Adds the 4-bit quality transport when the batch uses at most 16 distinct quality bytes
-        (what pb_packer_view does natively); returns self unchanged otherwise."""
+    def with_packed_quals(self) -> "ReadBatch":
+        """Adds the packed quality transport when the batch uses at most 8 (3-bit codes) or 16 (4-bit codes) distinct
+        quality bytes -- what pb_packer_view does natively; returns self unchanged otherwise."""
         vals = np.unique(np.concatenate([self.quals, np.zeros(1, np.uint8)]))
         if vals.shape[0] > 16:
             return self
+        bits = 3 if vals.shape[0] <= 8 else 4
         lut = np.zeros(16, np.uint8)
         lut[:vals.shape[0]] = vals
         code = np.zeros(256, np.uint8)
         code[vals] = np.arange(vals.shape[0], dtype=np.uint8)
-        c = code[self.quals]
-        q4 = np.zeros(self.quals.shape[0] // 2 + 16, np.uint8)
-        q4[:self.quals.shape[0] // 2] = c[0::2] | (c[1::2] << 4)
-        return dataclasses.replace(self, quals4=q4, qual_lut=lut)
+        c = code[self.quals].astype(np.uint32)
+        n = c.shape[0]
+        if bits == 4:
+            packed = (c[0::2] | (c[1::2] << 4)).astype(np.uint8)
+        else:
+            c8 = np.zeros((n + 7) // 8 * 8, np.uint32)
+            c8[:n] = c
+            v = (c8.reshape(-1, 8) << (3 * np.arange(8, dtype=np.uint32))).sum(axis=1, dtype=np.uint32)
+            packed = np.stack([v & 0xFF, (v >> 8) & 0xFF, (v >> 16) & 0xFF], axis=1).astype(np.uint8).reshape(-1)
+        buf = np.zeros(packed.shape[0] + 32, np.uint8)
+        buf[:packed.shape[0]] = packed
+        return dataclasses.replace(self, qual_codes=buf, qual_code_bits=bits, qual_lut=lut)
 
     def slice_reads(self, lo: int, hi: int) -> "ReadBatch":
         """Sub-batch of reads [lo, hi) (re-based offsets); used to split a region's reads."""

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 15
     for n in names:
         assert hasattr(lib, n), "libpilonb200.so does not export %s" % n
-    assert lib.pb_abi_version() == 2
+    assert lib.pb_abi_version() == 3
 
 
 def test_struct_sizes_match_header():
@@ -80,46 +80,47 @@ def test_c_packer_matches_numpy_packer():
         lib.pb_packer_destroy(pk)
 
 
-def _decode4(b):
-    q4 = np.ctypeslib.as_array(C.cast(b.quals4, C.POINTER(C.c_uint8)), shape=(b.n_seq // 2,))
-    lut = np.array(list(b.qual_lut), np.uint8)
-    dec = np.empty(b.n_seq, np.uint8)
-    dec[0::2] = lut[q4 & 15]
-    dec[1::2] = lut[q4 >> 4]
-    return dec
+def _decode_codes(b):
+    bits = b.qual_code_bits
+    nbytes = (b.n_seq * bits + 7) // 8
+    raw = np.ctypeslib.as_array(C.cast(b.qual_codes, C.POINTER(C.c_uint8)), shape=(nbytes,))
+    stream = np.unpackbits(raw, bitorder="little")[:b.n_seq * bits].reshape(b.n_seq, bits)
+    codes = (stream * (1 << np.arange(bits, dtype=np.uint8))).sum(axis=1).astype(np.uint8)
+    return np.array(list(b.qual_lut), np.uint8)[codes]
 
 
-def test_packer_offers_4bit_quality_transport_only_for_small_alphabets():
-    """pb_batch.quals4 / qual_lut (include/pilon_b200.h): offered iff the stored quality bytes take <= 16 values,
-    and then it decodes to exactly `quals`; packing.ReadBatch.with_quals4 is the numpy twin."""
+def test_packer_offers_packed_quality_transport_only_for_small_alphabets():
+    """pb_batch.qual_codes / qual_code_bits / qual_lut (include/pilon_b200.h): offered iff the stored quality bytes take
+    <= 16 values (3-bit codes up to 8 values, 4-bit up to 16), and then it decodes to exactly `quals`;
+    packing.ReadBatch.with_packed_quals is the numpy twin."""
     lib = capi.load_library()
     rng = np.random.default_rng(5)
-    for n_values, expect in ((5, True), (14, True), (16, False), (40, False)):   # + padding byte 0 and the 0x80 mark
+    for n_values, want_bits in ((4, 3), (6, 3), (7, 4), (14, 4), (16, 0), (40, 0)):   # + padding byte 0 and the 0x80 mark
         pk = C.c_void_p()
         assert lib.pb_packer_create(C.byref(pk)) == 0
         alphabet = rng.choice(np.arange(1, 94), n_values, replace=False).astype(np.uint8)
         for r in range(40):
-            L = int(rng.integers(1, 90))
+            L = int(rng.integers(1, 90)) if r else 95
             seq = rng.choice(np.frombuffer(b"ACGTN", np.uint8), L, p=[.24, .24, .24, .24, .04]).astype(np.uint8)
-            q = np.ascontiguousarray(np.concatenate([alphabet, rng.choice(alphabet, L)])[:L].astype(np.uint8)) if r == 0 and L >= n_values \
-                else rng.choice(alphabet, L).astype(np.uint8)
+            if r == 0:
+                seq[-1] = ord("N")                                               # the 0x80 mark is certainly present
+            q = rng.choice(alphabet, L).astype(np.uint8)
+            if r == 0:
+                q[:n_values] = alphabet                                          # every value is certainly present
             cig = np.array([(L << 4) | 0], np.uint32)
             assert lib.pb_packer_add(pk, 100 + r, 0, 60, 0, cig.ctypes.data, 1, seq.ctypes.data, q.ctypes.data, L) == 0
         b = capi.pb_batch()
         assert lib.pb_packer_view(pk, C.byref(b)) == 0
         q8 = np.ctypeslib.as_array(C.cast(b.quals, C.POINTER(C.c_uint8)), shape=(b.n_seq,)).copy()
-        distinct = len(np.unique(np.concatenate([q8, np.zeros(1, np.uint8)])))
-        assert bool(b.quals4) == (distinct <= 16)
-        if expect:
-            assert bool(b.quals4)
-        if b.quals4:
-            assert np.array_equal(_decode4(b), q8)
+        assert (b.qual_code_bits if b.qual_codes else 0) == want_bits
+        if b.qual_codes:
+            assert np.array_equal(_decode_codes(b), q8)
         lib.pb_packer_destroy(pk)
 
     from pilon_b200.packing import pack_records
     from tests import helpers as H
-    contig, start, stop, reads = H.random_case(3)
-    rb = pack_records(reads).with_quals4()
-    if rb.quals4 is not None:
-        c = rb.to_c()
-        assert np.array_equal(_decode4(c), rb.quals)
+    for seed in (3, 4):
+        contig, start, stop, reads = H.random_case(seed)
+        rb = pack_records(reads).with_packed_quals()
+        if rb.qual_codes is not None:
+            assert np.array_equal(_decode_codes(rb.to_c()), rb.quals)

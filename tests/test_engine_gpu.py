@@ -229,29 +229,30 @@ def test_facade_mirrors_reference_surface():
     assert pur.changes() == sorted((i, kinds[k]) for i, (k, _) in gr.changeMap.items())
 
 
-def test_4bit_quality_transport_matches_byte_transport(engine):
-    """pb_batch.quals4: the engine uploads the 4-bit codes and expands them on the device; results must be identical to
-    the byte transport (and to the oracle, which always reads `quals`)."""
+@pytest.mark.parametrize("levels", [(2, 12, 25, 37), (2, 6, 9, 12, 17, 22, 25, 27, 30, 33, 37, 40)])
+def test_packed_quality_transport_matches_byte_transport(engine, levels):
+    """pb_batch.qual_codes: the engine uploads 3- or 4-bit codes and expands them on the device; results must be identical
+    to the byte transport (and to the oracle, which always reads `quals`)."""
     from pilon_b200.packing import ResultBuffers
     rng = random.Random(11)
     contig, start, stop, reads = H.clean_case(11, n=8000, start=501, stop=6500, depth=30, n_sites=10)
     for r in reads:                                       # binned qualities
         if r.quals:
-            r.quals = bytes(rng.choice((2, 12, 25, 37)) for _ in r.quals)
+            r.quals = bytes(rng.choice(levels) for _ in r.quals)
     packed = pack_records(reads)
-    q4 = packed.with_quals4()
-    assert q4.quals4 is not None
+    pq = packed.with_packed_quals()
+    assert pq.qual_codes is not None and pq.qual_code_bits == (3 if len(levels) <= 6 else 4)
     ref, ins_ref = H.run_c_oracle(contig, start, stop, [(packed, True)])
     res8, ins8 = engine.run_region(contig, start, stop, [(packed, True)])
     H.assert_results_equal(res8, ref, "byte transport vs C oracle")
-    only4 = q4.to_c()
-    only4.quals = None                                     # the engine must not need the bytes
+    only_codes = pq.to_c()
+    only_codes.quals = None                                # the engine must not need the bytes
     engine.region_begin(contig, start, stop)
-    engine.add_batch(only4, True)
+    engine.add_batch(only_codes, True)
     res4 = ResultBuffers(stop + 1 - start, None, 1 << 16, 1 << 20)
     ins4 = [np.zeros(packed.n_reads, np.int32)]
     engine.finish(res4, ins4)
-    H.assert_results_equal(res4, ref, "4-bit transport vs C oracle")
+    H.assert_results_equal(res4, ref, "packed transport vs C oracle")
     assert np.array_equal(ins4[0], ins_ref[0])
 
 
