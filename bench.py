@@ -175,13 +175,25 @@ def pin_batch(torch, c):
     n = 0
     for name, count, width in _BATCH_FIELDS:
         nb = _field_bytes(c, count, width)
+        if name == "bases2" and c.base_delta_idx:
+            for nm, w in (("base_delta_idx", 4), ("base_delta_code", 1)):
+                if c.n_base_delta:
+                    _register(rt, getattr(c, nm), int(c.n_base_delta) * w)
+                    n += int(c.n_base_delta) * w
+            continue
         if name == "quals" and c.qual_codes:
             nb = (int(c.n_seq) * int(c.qual_code_bits) + 7) // 8
             name = "qual_codes"
         if nb:
-            rt.cudaHostRegister(getattr(c, name), nb, 0)
+            _register(rt, getattr(c, name), nb)
             n += nb
     return n
+
+
+def _register(rt, ptr, nbytes):
+    err = rt.cudaHostRegister(ptr, nbytes, 0)
+    if int(err) != 0:
+        raise RuntimeError("cudaHostRegister(%d bytes) failed: %s" % (nbytes, err))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -358,8 +370,20 @@ def run_gpu_arm(args):
             for b in r.batches:
                 b.c.qual_codes = None
     q4 = all(bool(b.c.qual_codes) for r in regions for b in r.batches)
+    if not args.bases2:                                   # reference-delta transport of the 2-bit bases (pb_base_delta_encode)
+        from pilon_b200.packing import base_delta_encode
+        for r in regions:
+            for b in r.batches:
+                b.delta_idx, b.delta_code = base_delta_encode(b.c, r.contig, r.start, r.stop)
+                b.c.base_delta_idx = b.delta_idx.ctypes.data
+                b.c.base_delta_code = b.delta_code.ctypes.data
+                b.c.n_base_delta = int(b.delta_idx.shape[0]) - 16
     qbits = max([int(b.c.qual_code_bits) for r in regions for b in r.batches] or [0]) if q4 else 8
-    h2d = sum(pin_batch(torch, b.c) for r in regions for b in r.batches) + sum(r.size + 1 for r in regions)
+    h2d = sum(pin_batch(torch, b.c) for r in regions for b in r.batches)
+    halo = 16384                                          # PB_REF_HALO: the reference window a pass uploads
+    h2d += sum(min(len(r.contig), r.stop + halo) - max(1, r.start - halo) + 1 for r in regions)
+    for cbuf in {id(r.contig): r.contig for r in regions}.values():      # the contigs are pinned once, like the reads
+        _register(torch.cuda.cudart(), np.frombuffer(cbuf, np.uint8).ctypes.data, len(cbuf))
     planes = FIX_PLANES if args.planes == "fix" else None
     n_workers = args.e2e_workers
     max_size = max(r.size for r in regions)
@@ -369,13 +393,22 @@ def run_gpu_arm(args):
     per_locus = sum(np.dtype(dt).itemsize * per for name, dt, per in capi.RESULT_PLANES if planes is None or name in planes)
     d2h = per_locus * total_loci
 
+    trace = [[0.0, 0.0, 0.0] for _ in range(n_workers)] if os.environ.get("PB_E2E_TRACE") else None
+
     def e2e_region(slot, r):
         eng, res = workers[slot]
         res.c.size = r.size
+        t_a = time.perf_counter()
         eng.region_begin(r.contig, r.start, r.stop)
+        t_b = time.perf_counter()
         for b in r.batches:
             eng.add_batch(b, b.frag)
+        t_c = time.perf_counter()
         eng.finish(res)
+        if trace is not None:                              # host seconds inside begin / add_batch / finish, per worker
+            t_d = time.perf_counter()
+            for k, dt in enumerate((t_b - t_a, t_c - t_b, t_d - t_c)):
+                trace[slot][k] += dt
         return int(res.c.aligned_bases)
 
     def e2e_step():
@@ -410,6 +443,10 @@ def run_gpu_arm(args):
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     assert got == total_aligned * e2e_steps, (got, total_aligned)
+    if trace is not None and rank == 0:
+        for slot, t in enumerate(trace):
+            print("e2e worker %d: begin %.1f ms, add_batch %.1f ms, finish %.1f ms per step" %
+                  ((slot,) + tuple(1e3 * x / (e2e_steps + 1) for x in t)), file=sys.stderr)
     for eng, _ in workers:
         eng.close()
 
@@ -455,7 +492,9 @@ def run_gpu_arm(args):
                                     "sequential_ms_per_step = sum of per-region event intervals with one region at a time (the pileup kernel's launches are timed in that pass)" % args.host_threads,
                           "e2e_planes": args.planes,
                           "e2e_quals": ("%d-bit codes + table (the workload has <= %d distinct quality bytes), expanded on the device"
-                                        % (qbits, 1 << qbits) if q4 else "1 byte per base")},
+                                        % (qbits, 1 << qbits) if q4 else "1 byte per base"),
+                          "e2e_bases": ("2 bits per base" if args.bases2 else
+                                        "deltas against the reference (5 B per differing base), bases2 rebuilt on the device")},
                "wall_ms_per_step": wall_step_ms, "sequential_ms_per_step": seq_step_ms,
                "e2e": {"value": job_aligned / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": job_h2d, "d2h_bytes_per_step": job_d2h,
                        "ms_per_step": 1e3 * e2e_sec, "streams_per_gpu": n_workers},
@@ -482,6 +521,8 @@ def main():
     ap.add_argument("--planes", default="fix", choices=["fix", "vcf"], help="per-locus results copied back in the e2e arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-workers", type=int, default=3, help="engines (host threads + streams) per GPU in the e2e arm")
+    ap.add_argument("--bases2", action="store_true", help="e2e arm: upload the 2-bit bases as they are instead of their "
+                    "deltas against the reference (pb_batch.base_delta_idx)")
     ap.add_argument("--quals8", action="store_true", help="e2e arm: upload one quality byte per base even when the batch "
                     "offers the packed transport (pb_batch.qual_codes)")
     ap.add_argument("--host-threads", type=int, default=4, help="host threads feeding region passes to the GPU")

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB_ABI_VERSION 3
+#define PB_ABI_VERSION 4
 
 /* ---- status codes ---------------------------------------------------------------------- */
 #define PB_OK                 0
@@ -108,7 +108,21 @@ typedef struct pb_batch {
      * the engine.  The buffer must be readable up to the next multiple of 16 bytes. */
     const uint8_t*  qual_codes; /* packed codes or NULL                                       */
     uint8_t qual_lut[16];       /* code -> quality byte (0..127, or 0x80)                     */
+    /* Optional compact transport of `bases2` for PB_MEM_HOST batches: only the bases that differ from what
+     * the reference predicts (the CRAM idea).  The predicted code of a read base is the code of the
+     * reference byte an M/=/X operation aligns it to -- when that byte is exactly 'A','C','G','T' and its
+     * locus lies in [region start - PB_REF_HALO, region stop + PB_REF_HALO] and in the contig -- and 0
+     * otherwise (inserted and soft-clipped bases, any other reference byte, padding).  base_delta_idx
+     * lists, sorted, the batch base indices whose stored code differs from the prediction and
+     * base_delta_code their stored codes (one per byte).  When base_delta_idx is non-NULL the engine
+     * uploads these 5 bytes per entry instead of `bases2` and rebuilds the array on the device;
+     * `bases2` may then be NULL for the engine.  pb_base_delta_encode computes them. */
+    const uint32_t* base_delta_idx;   /* [n_base_delta] or NULL                               */
+    const uint8_t*  base_delta_code;  /* [n_base_delta]                                       */
+    int64_t n_base_delta;
 } pb_batch;
+
+#define PB_REF_HALO 16384   /* loci of reference kept on the device on either side of a region */
 
 /* ---- per-locus call record (PileUp.BaseCall, PileUp.scala:132-167) -----------------------
  * Computed on the FINAL per-locus state, i.e. after pass 1 spilled homozygous-deletion counts
@@ -242,6 +256,12 @@ int pb_region_compute_timed(pb_engine* e, int iters, float* total_ms, float* pil
  * of such a pass are only reported by pb_region_finish / pb_region_compute_timed.  Synchronise the
  * stream (pb_stream) before reading anything. */
 int pb_region_compute(pb_engine* e);
+
+/* Base deltas of a host batch (see pb_batch.base_delta_idx) against `contig` for the region [start, stop]
+ * the batch will be added to.  *idx_out / *code_out are malloc'ed (release with pb_free), *n_out entries. */
+int pb_base_delta_encode(const pb_batch* b, const uint8_t* contig, int64_t contig_len, int32_t start, int32_t stop,
+                         uint32_t** idx_out, uint8_t** code_out, int64_t* n_out);
+void pb_free(void* p);
 
 /* Raw CUDA stream handle (cudaStream_t) so callers can order their own copies against the engine. */
 int pb_stream(pb_engine* e, void** stream_out);

@@ -35,7 +35,8 @@ class pb_batch(C.Structure):
                 ("cigar", C.c_void_p), ("seq_off", C.c_void_p), ("quals", C.c_void_p),
                 ("bases2", C.c_void_p), ("exc_idx", C.c_void_p), ("exc_base", C.c_void_p),
                 ("exc_qual", C.c_void_p), ("mem", C.c_int32), ("qual_code_bits", C.c_int32),
-                ("qual_codes", C.c_void_p), ("qual_lut", C.c_uint8 * 16)]
+                ("qual_codes", C.c_void_p), ("qual_lut", C.c_uint8 * 16),
+                ("base_delta_idx", C.c_void_p), ("base_delta_code", C.c_void_p), ("n_base_delta", C.c_int64)]
 
 
 class pb_indel(C.Structure):
@@ -103,12 +104,16 @@ def load_library() -> C.CDLL:
     lib.pb_packer_add.argtypes = [vp, i32, i32, i32, C.c_uint32, vp, i32, vp, vp, i32]
     lib.pb_packer_add_many.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.pb_packer_view.argtypes = [vp, C.POINTER(pb_batch)]
+    lib.pb_base_delta_encode.argtypes = [C.POINTER(pb_batch), vp, i64, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
+    lib.pb_base_delta_encode.restype = C.c_int
+    lib.pb_free.argtypes = [vp]
+    lib.pb_free.restype = None
     for name in ("pb_device_count", "pb_create", "pb_destroy", "pb_region_begin", "pb_region_add_batch",
                  "pb_region_finish", "pb_region_compute_timed", "pb_region_compute", "pb_stream", "pb_packer_create",
                  "pb_packer_destroy", "pb_packer_reset", "pb_packer_add", "pb_packer_add_many",
-                 "pb_packer_view"):
+                 "pb_packer_view", "pb_base_delta_encode"):
         getattr(lib, name).restype = C.c_int
-    if lib.pb_abi_version() != 3:
+    if lib.pb_abi_version() != 4:
         raise RuntimeError("libpilonb200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -94,8 +94,9 @@ struct RegionDev {
     int32_t start, stop;
     int64_t size;
     int32_t n_win;              // ceil(size / 32)
-    int32_t ref_locus0;         // locus of ref[0]  (= max(start - 1, 1))
-    const uint8_t* ref;         // raw contig bytes for loci [ref_locus0, stop]
+    int32_t ref_locus0;         // locus of ref[0]  (= max(start - PB_REF_HALO, 1))
+    int32_t ref_end;            // last locus held   (= min(stop + PB_REF_HALO, contig length))
+    const uint8_t* ref;         // raw contig bytes for loci [ref_locus0, ref_end]
     Cfg cfg;
     int32_t read_count, min_depth;   // host copies of the region scalars, valid for kernels launched after k_scalars' read-back
     Scalars* sc;
@@ -126,6 +127,31 @@ struct RegionDev {
     uint8_t* o_flags;
     uint64_t* o_call;
 };
+
+// ---------------------------------------------------------------------------------------------
+// Reference-predicted 2-bit codes of one read (pb_batch.base_delta_idx): emit(code) is called once per stored base
+// slot of the read, padding included, in order.  Shared by the host encoder and the device rebuild kernel.
+// ---------------------------------------------------------------------------------------------
+template <class Emit>
+__host__ __device__ __forceinline__ void predicted_codes(int32_t pos, const uint32_t* cigar, uint32_t n_ops, int32_t read_len,
+                                                         const uint8_t* ref, int64_t ref_lo, int64_t ref_hi, Emit&& emit) {
+    int64_t locus = pos; int32_t done = 0;
+    for (uint32_t k = 0; k < n_ops && done < read_len; k++) {
+        const uint32_t e = cigar[k]; const int op = (int)(e & 15); const int64_t len = (int64_t)(e >> 4);
+        if (op == 0 || op == 7 || op == 8) {                         // M = X: predicted from the reference
+            for (int64_t j = 0; j < len && done < read_len; j++, done++) {
+                const int64_t l = locus + j;
+                uint32_t code = 0;
+                if (l >= ref_lo && l <= ref_hi) { const uint8_t b = ref[l - ref_lo]; code = b == 'C' ? 1u : b == 'G' ? 2u : b == 'T' ? 3u : 0u; }
+                emit(code);
+            }
+            locus += len;
+        } else if (op == 1 || op == 4) {                             // I S: no reference counterpart
+            for (int64_t j = 0; j < len && done < read_len; j++, done++) emit(0u);
+        } else if (op == 2 || op == 3) locus += len;                 // D N
+    }
+    for (const int32_t padded = (read_len + 3) & ~3; done < padded; done++) emit(0u);
+}
 
 // ---------------------------------------------------------------------------------------------
 // JVM arithmetic (Utils.scala:22-27)

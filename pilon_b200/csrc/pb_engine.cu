@@ -8,7 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -58,6 +60,13 @@ struct HostBatch {
 
 }  // namespace
 
+// Uploads of host batches are chained across the engines of one device (each waits for the previous one's upload to finish):
+// the host->device DMA engine then serves one batch at full rate instead of interleaving several at a fraction each, so
+// concurrent engines fall into a pipeline (one uploads while another computes / downloads) instead of moving in lock step.
+// PB_UPLOAD_FIFO=0 turns the chaining off.
+static std::mutex g_upload_mu;
+static cudaEvent_t g_last_upload[64] = {};
+
 struct pb_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -81,6 +90,9 @@ struct pb_engine {
     cudaGraphExec_t graph_exec = nullptr;
     int64_t graph_launches = 0;      // kernels inside the captured pass
     std::vector<DevBatch> img_host;  // image of the batch table; a captured H2D copy reads it at every replay
+    cudaEvent_t upload_done = nullptr;   // see g_last_upload
+    // PB_PHASE_TIMING=1 (diagnostics): device time of upload / pass / download per region, printed by pb_destroy
+    bool phase_timing = false; cudaEvent_t ph[4] = {}; double ph_ms[3] = {0, 0, 0}; int64_t ph_regions = 0;
     int pileup_version = 0;          // 0 = choose per region (k_pileup7 scatter / k_pileup5 gather); PB_PILEUP=1..5,7 forces one (A/B runs)
 };
 
@@ -126,6 +138,8 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
     CK(cudaFuncSetAttribute(k_pileup2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * P2_WARPS)));
     CK(cudaFuncSetAttribute(k_pileup2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * P2_WARPS)));
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    { const char* f = getenv("PB_UPLOAD_FIFO"); if (!(f && f[0] == '0') && device < 64) CK(cudaEventCreateWithFlags(&e->upload_done, cudaEventDisableTiming)); }
+    if (getenv("PB_PHASE_TIMING")) { e->phase_timing = true; for (auto& ev : e->ph) CK(cudaEventCreate(&ev)); }
     CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
     CK(cudaEventCreate(&e->evp0)); CK(cudaEventCreate(&e->evp1));
     CK(cudaEventCreateWithFlags(&e->ev_sc, cudaEventDisableTiming));
@@ -139,6 +153,14 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
 }
 
 extern "C" int pb_destroy(pb_engine* e) {
+    if (e && e->upload_done) {
+        std::lock_guard<std::mutex> lk(g_upload_mu);
+        if (g_last_upload[e->device] == e->upload_done) g_last_upload[e->device] = nullptr;
+        cudaEventDestroy(e->upload_done); e->upload_done = nullptr;
+    }
+    if (e && e->phase_timing && e->ph_regions)
+        fprintf(stderr, "pilon_b200 phases over %lld regions: upload %.2f ms, pass %.2f ms, download %.2f ms per region\n",
+                (long long)e->ph_regions, e->ph_ms[0] / e->ph_regions, e->ph_ms[1] / e->ph_regions, e->ph_ms[2] / e->ph_regions);
     if (!e) return PB_OK;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
@@ -168,13 +190,15 @@ extern "C" int pb_region_begin(pb_engine* e, const uint8_t* contig, int64_t cont
     CK(cudaSetDevice(e->device));
     cudaStream_t s = e->stream;
     if (free_batches(e) != PB_OK) return PB_ERR_CUDA;
+    if (e->phase_timing) CK(cudaEventRecord(e->ph[0], s));
     RegionDev& R = e->R;
     R = RegionDev{};
     R.start = start; R.stop = stop; R.size = S; R.n_win = (int32_t)((S + 31) >> 5);
-    R.ref_locus0 = start - 1 > 1 ? start - 1 : 1;
+    R.ref_locus0 = start - PB_REF_HALO > 1 ? start - PB_REF_HALO : 1;
+    R.ref_end = (int32_t)std::min<int64_t>(contig_len, (int64_t)stop + PB_REF_HALO);
     R.cfg = e->cfg;
-    const size_t ref_bytes = (size_t)(stop - R.ref_locus0 + 1);
-    CK(e->ref.ensure(ref_bytes, false, s));
+    const size_t ref_bytes = (size_t)(R.ref_end - R.ref_locus0 + 1);
+    CK(e->ref.ensure(ref_bytes + 8, false, s));                                     // k_rebuild_bases reads whole words
     CK(cudaMemcpyAsync(e->ref.p, contig + (R.ref_locus0 - 1), ref_bytes, cudaMemcpyHostToDevice, s));
     R.ref = e->ref.as<uint8_t>();
     if (e->dirty) { int rcc = clean_sparse_planes(e); if (rcc != PB_OK) return rcc; e->dirty = false; }
@@ -220,6 +244,147 @@ static int stage(pb_engine* e, HostBatch& hb, const T* src, size_t n, int mem, c
     return PB_OK;
 }
 
+// bases2 from the reference prediction + the batch's base deltas (pb_batch.base_delta_idx): thread per read; a read owns
+// whole bytes of bases2 (its first base index is a multiple of 4), so no two threads touch the same byte.  Same rule as
+// predicted_codes() (pb_device.cuh, which the host encoder uses), with a fast path that turns four reference bytes into
+// one output byte at a time: x = (b >> 1) & 3, code = x ^ (x >> 1) maps A C G T to 0 1 2 3; any other byte gives 0.
+__device__ __forceinline__ uint32_t ref_code4(uint32_t w) {          // four reference bytes -> four codes, one per byte
+    const uint32_t x = (w >> 1) & 0x03030303u;
+    uint32_t c = x ^ ((x >> 1) & 0x01010101u);
+    const uint32_t t = w ^ 0x41414141u;                             // A C G T -> 0x00 0x02 0x06 0x15
+    uint32_t keep = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t ti = (t >> (8 * i)) & 0xFFu;
+        const bool ok = ti < 32u && ((0x00200045u >> ti) & 1u);
+        keep |= ok ? (0xFFu << (8 * i)) : 0u;
+    }
+    return c & keep;
+}
+
+// The 128 reads of a block own one contiguous run of output bytes: it is assembled in shared memory (byte stores are
+// cheap there) and written out with coalesced 16-byte stores; a run longer than the staging buffer (long reads) is
+// written directly.
+static constexpr int RB_THREADS = 128;
+static constexpr uint32_t RB_STAGE = 16384;         // bytes of staging per block (128 reads of up to 512 bases)
+
+__global__ void __launch_bounds__(RB_THREADS) k_rebuild_bases(RegionDev R, DevBatch B, const uint32_t* __restrict__ didx,
+                                                              const uint8_t* __restrict__ dcode, int64_t nd, uint8_t* out) {
+    __shared__ __align__(16) uint8_t stage[RB_STAGE + 16];
+    const int64_t r0 = (int64_t)blockIdx.x * RB_THREADS;
+    const int64_t r = r0 + threadIdx.x;
+    const int64_t rl = min(r0 + RB_THREADS, B.n_reads) - 1;             // last read of the block
+    const uint32_t byte0 = B.seq_off[r0] >> 2;                          // the block's run of output bytes: [byte0, byte1)
+    const uint32_t byte1 = (B.seq_off[rl] >> 2) + (uint32_t)((B.read_len[rl] + 3) >> 2);
+    const bool staged = byte1 - byte0 <= RB_STAGE;                      // block-uniform
+    if (r < B.n_reads) {
+        const uint32_t soff = B.seq_off[r];
+        const int32_t L = B.read_len[r];
+        const uint32_t c0 = B.cigar_off[r], c1 = B.cigar_off[r + 1];
+        uint8_t* o = staged ? stage + ((soff >> 2) - byte0) : out + (soff >> 2);
+        const int64_t lo = R.ref_locus0, hi = R.ref_end;
+        uint32_t acc = 0; int nacc = 0, bytei = 0; int32_t done = 0;
+        auto emit = [&](uint32_t code) { acc |= code << (2 * nacc); if (++nacc == 4) { o[bytei++] = (uint8_t)acc; acc = 0; nacc = 0; } };
+        auto one = [&](int64_t l) -> uint32_t {
+            if (l < lo || l > hi) return 0u;
+            const uint8_t b = R.ref[l - lo];
+            return b == 'C' ? 1u : b == 'G' ? 2u : b == 'T' ? 3u : 0u;
+        };
+        int64_t locus = B.pos[r];
+        for (uint32_t k = c0; k < c1 && done < L; k++) {
+            const uint32_t e = B.cigar[k]; const int op = (int)(e & 15); const int64_t len = (int64_t)(e >> 4);
+            if (op == 0 || op == 7 || op == 8) {
+                int64_t j = 0;
+                for (; j < len && done < L && nacc != 0; j++, done++) emit(one(locus + j));      // up to the next output byte
+                // one output byte per trip from a sliding window over aligned reference words
+                int64_t l = locus + j;
+                if (j + 4 <= len && done + 4 <= L && l >= lo && l + 3 <= hi) {
+                    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(R.ref);         // R.ref is 256-byte aligned (cudaMalloc)
+                    uint64_t wi = (uint64_t)(l - lo) >> 2;
+                    const uint32_t sh = (uint32_t)((l - lo) & 3) << 3;
+                    const uint64_t wlast = (uint64_t)(hi - lo) >> 2;
+                    uint32_t cur = w32[wi];
+                    for (; j + 4 <= len && done + 4 <= L && l + 3 <= hi; j += 4, done += 4, l += 4) {
+                        const uint32_t nxt = wi + 1 <= wlast ? w32[wi + 1] : 0u;
+                        const uint32_t c = ref_code4(__funnelshift_r(cur, nxt, sh));
+                        o[bytei++] = (uint8_t)((c * 0x01041040u) >> 24);                      // c0 | c1 << 2 | c2 << 4 | c3 << 6
+                        cur = nxt; wi++;
+                    }
+                }
+                for (; j < len && done < L; j++, done++) emit(one(locus + j));
+                locus += len;
+            } else if (op == 1 || op == 4) {
+                for (int64_t j = 0; j < len && done < L; j++, done++) emit(0u);
+            } else if (op == 2 || op == 3) locus += len;
+        }
+        for (const int32_t padded = (L + 3) & ~3; done < padded; done++) emit(0u);
+        const uint32_t end = soff + (uint32_t)((L + 3) & ~3);
+        int64_t dl = 0, dh = nd;
+        while (dl < dh) { const int64_t m = (dl + dh) >> 1; if (didx[m] < soff) dl = m + 1; else dh = m; }
+        for (int64_t i = dl; i < nd && didx[i] < end; i++) {
+            const uint32_t bi = didx[i] - soff, sh = 2 * (bi & 3);
+            o[bi >> 2] = (uint8_t)((o[bi >> 2] & ~(3u << sh)) | ((uint32_t)dcode[i] << sh));
+        }
+    }
+    if (!staged) return;
+    __syncthreads();
+    // coalesced write-out of [byte0, byte1): bytes up to the first 16-byte boundary, 16-byte stores, the rest
+    const uint32_t nbytes = byte1 - byte0;
+    const uint32_t head = min(nbytes, (16u - (byte0 & 15u)) & 15u);
+    for (uint32_t i = threadIdx.x; i < head; i += RB_THREADS) out[byte0 + i] = stage[i];
+    const uint32_t nvec = (nbytes - head) >> 4;
+    for (uint32_t v = threadIdx.x; v < nvec; v += RB_THREADS) {
+        const uint8_t* sp = stage + head + 16u * v;                     // (not 16-byte aligned in shared memory: four word loads)
+        uint4 x;
+        x.x = (uint32_t)sp[0] | ((uint32_t)sp[1] << 8) | ((uint32_t)sp[2] << 16) | ((uint32_t)sp[3] << 24);
+        x.y = (uint32_t)sp[4] | ((uint32_t)sp[5] << 8) | ((uint32_t)sp[6] << 16) | ((uint32_t)sp[7] << 24);
+        x.z = (uint32_t)sp[8] | ((uint32_t)sp[9] << 8) | ((uint32_t)sp[10] << 16) | ((uint32_t)sp[11] << 24);
+        x.w = (uint32_t)sp[12] | ((uint32_t)sp[13] << 8) | ((uint32_t)sp[14] << 16) | ((uint32_t)sp[15] << 24);
+        *reinterpret_cast<uint4*>(out + byte0 + head + 16u * v) = x;
+    }
+    for (uint32_t i = head + 16u * nvec + threadIdx.x; i < nbytes; i += RB_THREADS) out[byte0 + i] = stage[i];
+}
+
+extern "C" void pb_free(void* p) { free(p); }
+
+extern "C" int pb_base_delta_encode(const pb_batch* b, const uint8_t* contig, int64_t contig_len, int32_t start, int32_t stop,
+                                    uint32_t** idx_out, uint8_t** code_out, int64_t* n_out) {
+    if (!b || !contig || !idx_out || !code_out || !n_out) return fail(PB_ERR_INVALID, "null argument");
+    if (b->mem != PB_MEM_HOST || !b->bases2) return fail(PB_ERR_INVALID, "pb_base_delta_encode needs a host batch with bases2");
+    if (start < 1 || stop < start || stop > contig_len) return fail(PB_ERR_INVALID, "region must satisfy 1 <= start <= stop <= contig_len");
+    const int64_t ref_lo = start - PB_REF_HALO > 1 ? start - PB_REF_HALO : 1;
+    const int64_t ref_hi = std::min<int64_t>(contig_len, (int64_t)stop + PB_REF_HALO);
+    const uint8_t* ref = contig + (ref_lo - 1);
+    const int64_t n = b->n_reads;
+    const unsigned nt = (unsigned)std::max<int64_t>(1, std::min<int64_t>(16, n / 4096));
+    std::vector<std::vector<uint32_t>> vi(nt); std::vector<std::vector<uint8_t>> vc(nt);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) th.emplace_back([&, t]() {
+        const int64_t r0 = n * t / nt, r1 = n * (t + 1) / nt;
+        for (int64_t r = r0; r < r1; r++) {
+            uint32_t bi = b->seq_off[r];
+            predicted_codes(b->pos[r], b->cigar + b->cigar_off[r], b->cigar_off[r + 1] - b->cigar_off[r], b->read_len[r], ref, ref_lo, ref_hi,
+                            [&](uint32_t code) {
+                                const uint32_t have = (b->bases2[bi >> 2] >> (2 * (bi & 3))) & 3u;
+                                if (have != code) { vi[t].push_back(bi); vc[t].push_back((uint8_t)have); }
+                                bi++;
+                            });
+        }
+    });
+    for (auto& x : th) x.join();
+    size_t total = 0;
+    for (auto& v : vi) total += v.size();
+    uint32_t* oi = (uint32_t*)malloc(total * 4 + 64); uint8_t* oc = (uint8_t*)malloc(total + 64);
+    if (!oi || !oc) { free(oi); free(oc); return fail(PB_ERR_OOM, "out of host memory"); }
+    size_t at = 0;
+    for (unsigned t = 0; t < nt; t++) {
+        if (!vi[t].empty()) { memcpy(oi + at, vi[t].data(), vi[t].size() * 4); memcpy(oc + at, vc[t].data(), vc[t].size()); }
+        at += vi[t].size();
+    }
+    *idx_out = oi; *code_out = oc; *n_out = (int64_t)total;
+    return PB_OK;
+}
+
 // 4-bit quality codes -> quality bytes (pb_batch.qual_codes, qual_code_bits == 4).  A thread expands 16 bases: the low / high half of an input
 // word is directly a PRMT selector (one code per nibble); codes 0..7 and 8..15 come from two 8-byte pools, bit 3 picks.
 __global__ void __launch_bounds__(256) k_unpack_quals4(const uint2* __restrict__ in, uint4* __restrict__ out, size_t groups,
@@ -258,6 +423,19 @@ extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, in
     if (b->n_cigar >= (1ll << 32) || b->n_reads >= (1ll << 31)) return fail(PB_ERR_INVALID, "batch too large");
     CK(cudaSetDevice(e->device));
     drop_graph(e);                                   // the captured pass belongs to the previous batch set
+    struct UploadTurn {                              // host batches: take this engine's turn in the device's upload chain
+        pb_engine* e; bool on;
+        UploadTurn(pb_engine* e_, bool on_) : e(e_), on(on_) {
+            if (!on) return;
+            g_upload_mu.lock();
+            if (cudaEvent_t prev = g_last_upload[e->device]) cudaStreamWaitEvent(e->stream, prev, 0);
+        }
+        ~UploadTurn() {
+            if (!on) return;
+            if (cudaEventRecord(e->upload_done, e->stream) == cudaSuccess) g_last_upload[e->device] = e->upload_done;
+            g_upload_mu.unlock();
+        }
+    } turn(e, b->mem == PB_MEM_HOST && e->upload_done != nullptr);
     e->batches.emplace_back();
     HostBatch& hb = e->batches.back();
     DevBatch& d = hb.d;
@@ -267,7 +445,27 @@ extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, in
     int rc;
 #define ST(field, count) if ((rc = stage(e, hb, b->field, (size_t)(count), b->mem, &d.field)) != PB_OK) return rc
     ST(pos, n); ST(tlen, n); ST(read_len, n); ST(mapq, n); ST(flags, n); ST(cigar_off, n + 1);
-    ST(cigar, b->n_cigar); ST(seq_off, n); ST(bases2, b->n_seq / 4);
+    ST(cigar, b->n_cigar); ST(seq_off, n);
+    if (b->mem == PB_MEM_HOST && b->base_delta_idx) {   // compact transport: upload the deltas, rebuild bases2 on the device
+        if (b->n_base_delta < 0 || (b->n_base_delta && !b->base_delta_code)) return fail(PB_ERR_INVALID, "bad base delta arrays");
+        void *pi = nullptr, *pc = nullptr, *pout = nullptr;
+        const size_t nd = (size_t)b->n_base_delta;
+        CK(cudaMallocAsync(&pi, nd * 4 + 64, e->stream)); hb.owned.push_back(pi);
+        CK(cudaMallocAsync(&pc, nd + 64, e->stream)); hb.owned.push_back(pc);
+        CK(cudaMallocAsync(&pout, (size_t)b->n_seq / 4 + 64, e->stream)); hb.owned.push_back(pout);
+        if (nd) {
+            CK(cudaMemcpyAsync(pi, b->base_delta_idx, nd * 4, cudaMemcpyHostToDevice, e->stream));
+            CK(cudaMemcpyAsync(pc, b->base_delta_code, nd, cudaMemcpyHostToDevice, e->stream));
+        }
+        d.bases2 = (const uint8_t*)pout;
+        if (n) {
+            k_rebuild_bases<<<(unsigned)((n + RB_THREADS - 1) / RB_THREADS), RB_THREADS, 0, e->stream>>>(e->R, d, (const uint32_t*)pi, (const uint8_t*)pc, (int64_t)nd, (uint8_t*)pout);
+            e->launches++;
+        }
+    } else {
+        if (!b->bases2 && b->n_seq) return fail(PB_ERR_INVALID, "batch has neither bases2 nor base deltas");
+        ST(bases2, b->n_seq / 4);
+    }
     if (b->mem == PB_MEM_HOST && b->qual_codes) {      // compact transport: upload 3- / 4-bit codes, expand on the device
         const int bits = b->qual_code_bits;
         if (bits != 3 && bits != 4) return fail(PB_ERR_INVALID, "qual_code_bits must be 3 or 4 when qual_codes is given");
@@ -473,7 +671,9 @@ static int compute(pb_engine* e, bool time_pileup, bool full_cap = false) {
 extern "C" int pb_region_compute(pb_engine* e) {
     if (!e || !e->in_region) return fail(PB_ERR_INVALID, "no region");
     CK(cudaSetDevice(e->device));
-    static const bool use_graph = getenv("PB_NOGRAPH") == nullptr;
+    // plain launches under Nsight Compute (it sets NV_COMPUTE_PROFILER_PERFWORKS_DIR): capturing on several host threads
+    // while the profiler serialises kernels crashed the tool, and a launch list wants to see every kernel anyway
+    static const bool use_graph = getenv("PB_NOGRAPH") == nullptr && getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") == nullptr;
     if (use_graph && e->graph_state == 2) {                  // the pass has no host round trip: one call replays it
         CK(cudaGraphLaunch(e->graph_exec, e->stream));
         e->launches += e->graph_launches;
@@ -544,6 +744,7 @@ extern "C" int pb_region_finish(pb_engine* e, pb_region_result* res, int32_t* co
     cudaStream_t s = e->stream;
     RegionDev& R = e->R;
     for (int attempt = 0;; attempt++) {
+        if (e->phase_timing && attempt == 0) CK(cudaEventRecord(e->ph[1], s));
         int rc = compute(e, false, attempt > 0);
         if (rc != PB_OK) { cudaStreamSynchronize(s); return rc; }
         CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
@@ -555,6 +756,7 @@ extern "C" int pb_region_finish(pb_engine* e, pb_region_result* res, int32_t* co
         if (e->h_sc->error) return pass_error((uint32_t)e->h_sc->error);
         break;
     }
+    if (e->phase_timing) CK(cudaEventRecord(e->ph[2], s));
     const uint32_t ng = e->h_sc->n_groups;
     // winning strings: sized exactly, then gathered
     std::vector<Group> groups(ng);
@@ -583,7 +785,12 @@ extern "C" int pb_region_finish(pb_engine* e, pb_region_result* res, int32_t* co
             if (insert_sizes_out[i] && e->batches[i].d.n_reads)
                 CK(cudaMemcpyAsync(insert_sizes_out[i], e->batches[i].d.insert_out, (size_t)e->batches[i].d.n_reads * 4, cudaMemcpyDeviceToHost, s));
     std::vector<uint8_t> pool;
+    if (e->phase_timing) CK(cudaEventRecord(e->ph[3], s));
     CK(cudaStreamSynchronize(s));
+    if (e->phase_timing) {
+        for (int i = 0; i < 3; i++) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, e->ph[i], e->ph[i + 1])); e->ph_ms[i] += ms; }
+        e->ph_regions++;
+    }
     CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (e->h_sc->error) return fail(PB_ERR_CUDA, "internal error flag set by a kernel");

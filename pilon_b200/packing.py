@@ -18,6 +18,25 @@ import numpy as np
 
 from . import _capi as capi
 
+def base_delta_encode(cb, contig, start: int, stop: int):
+    """pb_base_delta_encode on a C batch; returns (idx uint32[n + 16], code uint8[n + 16]) numpy copies (16 spare entries
+    keep the arrays non-empty and addressable)."""
+    lib = capi.load_library()
+    pi, pc, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+    buf = contig if isinstance(contig, (bytes, bytearray)) else None
+    cptr = C.cast(C.c_char_p(bytes(contig)) if buf is not None else C.c_void_p(contig.ctypes.data), C.c_void_p)
+    clen = len(contig) if buf is not None else int(contig.shape[0])
+    capi.check(lib.pb_base_delta_encode(C.byref(cb), cptr, clen, start, stop, C.byref(pi), C.byref(pc), C.byref(n)))
+    idx = np.zeros(n.value + 16, np.uint32)
+    code = np.zeros(n.value + 16, np.uint8)
+    if n.value:
+        idx[:n.value] = np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_uint32)), shape=(n.value,))
+        code[:n.value] = np.ctypeslib.as_array(C.cast(pc, C.POINTER(C.c_uint8)), shape=(n.value,))
+    lib.pb_free(pi)
+    lib.pb_free(pc)
+    return idx, code
+
+
 _OPCODE = {op: i for i, op in enumerate(capi.CIGAR_OPS)}
 _BASE_CODE = np.full(256, 255, np.uint8)
 for _i, _c in enumerate(b"ACGT"):
@@ -43,6 +62,8 @@ class ReadBatch:
     qual_codes: Optional[np.ndarray] = None    # pb_batch.qual_codes: packed 3- or 4-bit codes (compact H2D transport)
     qual_code_bits: int = 0                    # pb_batch.qual_code_bits
     qual_lut: Optional[np.ndarray] = None      # pb_batch.qual_lut: code -> quality byte
+    base_delta_idx: Optional[np.ndarray] = None    # pb_batch.base_delta_idx / base_delta_code: bases that differ from
+    base_delta_code: Optional[np.ndarray] = None   # the reference prediction (compact H2D transport of bases2)
 
     @property
     def n_reads(self) -> int:
@@ -69,9 +90,18 @@ class ReadBatch:
             b.qual_code_bits = self.qual_code_bits
             for i in range(16):
                 b.qual_lut[i] = int(self.qual_lut[i])
+        if self.base_delta_idx is not None:
+            b.base_delta_idx = self.base_delta_idx.ctypes.data
+            b.base_delta_code = self.base_delta_code.ctypes.data
+            b.n_base_delta = int(self.base_delta_idx.shape[0]) - 16      # (the arrays carry 16 spare entries)
         b.mem = capi.PB_MEM_HOST
         b._keepalive = self
         return b
+
+    def with_base_deltas(self, contig: bytes, start: int, stop: int) -> "ReadBatch":
+        """Adds the reference-delta transport of bases2 for the region [start, stop] (pb_base_delta_encode)."""
+        idx, code = base_delta_encode(self.to_c(), contig, start, stop)
+        return dataclasses.replace(self, base_delta_idx=idx, base_delta_code=code)
 
     def with_packed_quals(self) -> "ReadBatch":
         """Adds the packed quality transport when the batch uses at most 8 (3-bit codes) or 16 (4-bit codes) distinct

@@ -26,13 +26,13 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 15
     for n in names:
         assert hasattr(lib, n), "libpilonb200.so does not export %s" % n
-    assert lib.pb_abi_version() == 3
+    assert lib.pb_abi_version() == 4
 
 
 def test_struct_sizes_match_header():
     # sizes implied by the header's field lists (LP64)
     assert C.sizeof(capi.pb_config) == 40
-    assert C.sizeof(capi.pb_batch) == 4 * 8 + 13 * 8 + 8 + 8 + 16
+    assert C.sizeof(capi.pb_batch) == 4 * 8 + 13 * 8 + 8 + 8 + 16 + 24
     assert C.sizeof(capi.pb_indel) == 32
     assert C.sizeof(capi.pb_region_result) == 4 * 8 + 4 * 4 + 2 * 8 + 18 * 8 + 4 * 8
 
@@ -124,3 +124,40 @@ def test_packer_offers_packed_quality_transport_only_for_small_alphabets():
         rb = pack_records(reads).with_packed_quals()
         if rb.qual_codes is not None:
             assert np.array_equal(_decode_codes(rb.to_c()), rb.quals)
+
+
+def test_base_delta_transport_round_trips():
+    """pb_base_delta_encode (include/pilon_b200.h, pb_batch.base_delta_idx): the deltas applied to an independent Python
+    restatement of the reference prediction give back bases2 exactly."""
+    from pilon_b200.packing import pack_records
+    from tests import helpers as H
+    halo = 16384
+    table = {ord("C"): 1, ord("G"): 2, ord("T"): 3}
+    for seed in (0, 1, 5, 9, 14):
+        contig, start, stop, reads = H.random_case(seed)
+        rb = pack_records(reads)
+        rd = rb.with_base_deltas(contig, start, stop)
+        n = rd.base_delta_idx.shape[0] - 16
+        assert np.all(np.diff(rd.base_delta_idx[:n].astype(np.int64)) > 0)
+        lo, hi = max(1, start - halo), min(len(contig), stop + halo)
+        codes = np.zeros(rb.quals.shape[0], np.uint8)
+        for r in range(rb.n_reads):
+            bi, L, done, locus = int(rb.seq_off[r]), int(rb.read_len[r]), 0, int(rb.pos[r])
+            for k in range(int(rb.cigar_off[r]), int(rb.cigar_off[r + 1])):
+                e = int(rb.cigar[k])
+                op, ln = e & 15, e >> 4
+                if op in (0, 7, 8):
+                    for j in range(ln):
+                        if done >= L:
+                            break
+                        l = locus + j
+                        codes[bi + done] = table.get(contig[l - 1], 0) if lo <= l <= hi else 0
+                        done += 1
+                    locus += ln
+                elif op in (1, 4):
+                    done = min(L, done + ln)
+                elif op in (2, 3):
+                    locus += ln
+        codes[rd.base_delta_idx[:n]] = rd.base_delta_code[:n]
+        c4 = codes.reshape(-1, 4)
+        assert np.array_equal((c4[:, 0] | (c4[:, 1] << 2) | (c4[:, 2] << 4) | (c4[:, 3] << 6)).astype(np.uint8), rb.bases2)

@@ -339,3 +339,25 @@ def test_graph_replayed_passes_leave_the_engine_clean(engine):
     engine.finish(res, ins)
     H.assert_results_equal(res, ref, "after five async passes")
     assert np.array_equal(ins[0], ins_ref[0])
+
+
+@pytest.mark.parametrize("seed", [2, 8, 17, 33])
+def test_base_delta_transport_matches_byte_transport(engine, seed):
+    """pb_batch.base_delta_idx: the engine uploads only the bases that differ from the reference prediction and rebuilds
+    bases2 on the device; together with the packed qualities nothing of the per-base arrays is uploaded as is."""
+    from pilon_b200.packing import ResultBuffers
+    contig, start, stop, reads = H.random_case(seed)
+    packed = pack_records(reads)
+    ref, ins_ref = H.run_c_oracle(contig, start, stop, [(packed, True)])
+    compact = packed.with_base_deltas(contig, start, stop).with_packed_quals()
+    cb = compact.to_c()
+    cb.bases2 = None                                       # the engine must not need the bytes
+    if compact.qual_codes is not None:
+        cb.quals = None
+    engine.region_begin(contig, start, stop)
+    engine.add_batch(cb, True)
+    res = ResultBuffers(stop + 1 - start, None, 1 << 16, 1 << 20)
+    ins = [np.zeros(packed.n_reads, np.int32)]
+    engine.finish(res, ins)
+    H.assert_results_equal(res, ref, "base-delta transport vs C oracle")
+    assert np.array_equal(ins[0], ins_ref[0])
