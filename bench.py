@@ -370,7 +370,7 @@ def run_gpu_arm(args):
             for b in r.batches:
                 b.c.qual_codes = None
     q4 = all(bool(b.c.qual_codes) for r in regions for b in r.batches)
-    if not args.bases2:                                   # reference-delta transport of the 2-bit bases (pb_base_delta_encode)
+    if args.base_deltas:                                   # reference-delta transport of the 2-bit bases (pb_base_delta_encode)
         from pilon_b200.packing import base_delta_encode
         for r in regions:
             for b in r.batches:
@@ -383,6 +383,8 @@ def run_gpu_arm(args):
     halo = 16384                                          # PB_REF_HALO: the reference window a pass uploads
     h2d += sum(min(len(r.contig), r.stop + halo) - max(1, r.start - halo) + 1 for r in regions)
     for cbuf in {id(r.contig): r.contig for r in regions}.values():      # the contigs are pinned once, like the reads
+        if os.environ.get("PB_BENCH_PIN_CONTIG") != "1":     # measured: pinning them costs ~10 % (profiles/README.md)
+            break
         _register(torch.cuda.cudart(), np.frombuffer(cbuf, np.uint8).ctypes.data, len(cbuf))
     planes = FIX_PLANES if args.planes == "fix" else None
     n_workers = args.e2e_workers
@@ -493,8 +495,8 @@ def run_gpu_arm(args):
                           "e2e_planes": args.planes,
                           "e2e_quals": ("%d-bit codes + table (the workload has <= %d distinct quality bytes), expanded on the device"
                                         % (qbits, 1 << qbits) if q4 else "1 byte per base"),
-                          "e2e_bases": ("2 bits per base" if args.bases2 else
-                                        "deltas against the reference (5 B per differing base), bases2 rebuilt on the device")},
+                          "e2e_bases": ("deltas against the reference (5 B per differing base), bases2 rebuilt on the device"
+                                        if args.base_deltas else "2 bits per base")},
                "wall_ms_per_step": wall_step_ms, "sequential_ms_per_step": seq_step_ms,
                "e2e": {"value": job_aligned / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": job_h2d, "d2h_bytes_per_step": job_d2h,
                        "ms_per_step": 1e3 * e2e_sec, "streams_per_gpu": n_workers},
@@ -521,8 +523,8 @@ def main():
     ap.add_argument("--planes", default="fix", choices=["fix", "vcf"], help="per-locus results copied back in the e2e arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-workers", type=int, default=3, help="engines (host threads + streams) per GPU in the e2e arm")
-    ap.add_argument("--bases2", action="store_true", help="e2e arm: upload the 2-bit bases as they are instead of their "
-                    "deltas against the reference (pb_batch.base_delta_idx)")
+    ap.add_argument("--base-deltas", action="store_true", help="e2e arm: upload the 2-bit bases as their deltas against the "
+                    "reference (pb_batch.base_delta_idx) instead of as they are; fewer bytes, no measured gain")
     ap.add_argument("--quals8", action="store_true", help="e2e arm: upload one quality byte per base even when the batch "
                     "offers the packed transport (pb_batch.qual_codes)")
     ap.add_argument("--host-threads", type=int, default=4, help="host threads feeding region passes to the GPU")

@@ -8,7 +8,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -60,13 +59,6 @@ struct HostBatch {
 
 }  // namespace
 
-// Uploads of host batches are chained across the engines of one device (each waits for the previous one's upload to finish):
-// the host->device DMA engine then serves one batch at full rate instead of interleaving several at a fraction each, so
-// concurrent engines fall into a pipeline (one uploads while another computes / downloads) instead of moving in lock step.
-// PB_UPLOAD_FIFO=0 turns the chaining off.
-static std::mutex g_upload_mu;
-static cudaEvent_t g_last_upload[64] = {};
-
 struct pb_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -90,7 +82,6 @@ struct pb_engine {
     cudaGraphExec_t graph_exec = nullptr;
     int64_t graph_launches = 0;      // kernels inside the captured pass
     std::vector<DevBatch> img_host;  // image of the batch table; a captured H2D copy reads it at every replay
-    cudaEvent_t upload_done = nullptr;   // see g_last_upload
     // PB_PHASE_TIMING=1 (diagnostics): device time of upload / pass / download per region, printed by pb_destroy
     bool phase_timing = false; cudaEvent_t ph[4] = {}; double ph_ms[3] = {0, 0, 0}; int64_t ph_regions = 0;
     int pileup_version = 0;          // 0 = choose per region (k_pileup7 scatter / k_pileup5 gather); PB_PILEUP=1..5,7 forces one (A/B runs)
@@ -138,7 +129,6 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
     CK(cudaFuncSetAttribute(k_pileup2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * P2_WARPS)));
     CK(cudaFuncSetAttribute(k_pileup2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * P2_WARPS)));
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-    { const char* f = getenv("PB_UPLOAD_FIFO"); if (!(f && f[0] == '0') && device < 64) CK(cudaEventCreateWithFlags(&e->upload_done, cudaEventDisableTiming)); }
     if (getenv("PB_PHASE_TIMING")) { e->phase_timing = true; for (auto& ev : e->ph) CK(cudaEventCreate(&ev)); }
     CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
     CK(cudaEventCreate(&e->evp0)); CK(cudaEventCreate(&e->evp1));
@@ -153,11 +143,6 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
 }
 
 extern "C" int pb_destroy(pb_engine* e) {
-    if (e && e->upload_done) {
-        std::lock_guard<std::mutex> lk(g_upload_mu);
-        if (g_last_upload[e->device] == e->upload_done) g_last_upload[e->device] = nullptr;
-        cudaEventDestroy(e->upload_done); e->upload_done = nullptr;
-    }
     if (e && e->phase_timing && e->ph_regions)
         fprintf(stderr, "pilon_b200 phases over %lld regions: upload %.2f ms, pass %.2f ms, download %.2f ms per region\n",
                 (long long)e->ph_regions, e->ph_ms[0] / e->ph_regions, e->ph_ms[1] / e->ph_regions, e->ph_ms[2] / e->ph_regions);
@@ -423,19 +408,6 @@ extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, in
     if (b->n_cigar >= (1ll << 32) || b->n_reads >= (1ll << 31)) return fail(PB_ERR_INVALID, "batch too large");
     CK(cudaSetDevice(e->device));
     drop_graph(e);                                   // the captured pass belongs to the previous batch set
-    struct UploadTurn {                              // host batches: take this engine's turn in the device's upload chain
-        pb_engine* e; bool on;
-        UploadTurn(pb_engine* e_, bool on_) : e(e_), on(on_) {
-            if (!on) return;
-            g_upload_mu.lock();
-            if (cudaEvent_t prev = g_last_upload[e->device]) cudaStreamWaitEvent(e->stream, prev, 0);
-        }
-        ~UploadTurn() {
-            if (!on) return;
-            if (cudaEventRecord(e->upload_done, e->stream) == cudaSuccess) g_last_upload[e->device] = e->upload_done;
-            g_upload_mu.unlock();
-        }
-    } turn(e, b->mem == PB_MEM_HOST && e->upload_done != nullptr);
     e->batches.emplace_back();
     HostBatch& hb = e->batches.back();
     DevBatch& d = hb.d;
