@@ -389,28 +389,35 @@ def run_gpu_arm(args):
     planes = FIX_PLANES if args.planes == "fix" else None
     n_workers = args.e2e_workers
     max_size = max(r.size for r in regions)
-    workers = [(Engine(local), ResultBuffers(max_size, planes, indels_cap=1 << 20, indel_bytes_cap=1 << 23, pinned=True))
-               for _ in range(n_workers)]
+    depth = max(1, args.e2e_depth)                       # passes in flight per host thread (one engine + result set each)
+    workers = [[(Engine(local), ResultBuffers(max_size, planes, indels_cap=1 << 20, indel_bytes_cap=1 << 23, pinned=True))
+                for _ in range(depth)] for _ in range(n_workers)]
     from pilon_b200 import _capi as capi
     per_locus = sum(np.dtype(dt).itemsize * per for name, dt, per in capi.RESULT_PLANES if planes is None or name in planes)
     d2h = per_locus * total_loci
 
     trace = [[0.0, 0.0, 0.0] for _ in range(n_workers)] if os.environ.get("PB_E2E_TRACE") else None
 
-    def e2e_region(slot, r):
-        eng, res = workers[slot]
+    def e2e_submit(slot, k, r):
+        """pb_region_begin + pb_region_add_batch: asynchronous, the uploads are queued on the engine's stream."""
+        eng, res = workers[slot][k]
         res.c.size = r.size
         t_a = time.perf_counter()
         eng.region_begin(r.contig, r.start, r.stop)
         t_b = time.perf_counter()
         for b in r.batches:
             eng.add_batch(b, b.frag)
+        if trace is not None:                              # host seconds inside begin / add_batch / finish, per host thread
+            trace[slot][0] += t_b - t_a
+            trace[slot][1] += time.perf_counter() - t_b
+
+    def e2e_collect(slot, k):
+        """pb_region_finish: the pass, the download into the pinned result planes, and the wait for both."""
+        eng, res = workers[slot][k]
         t_c = time.perf_counter()
         eng.finish(res)
-        if trace is not None:                              # host seconds inside begin / add_batch / finish, per worker
-            t_d = time.perf_counter()
-            for k, dt in enumerate((t_b - t_a, t_c - t_b, t_d - t_c)):
-                trace[slot][k] += dt
+        if trace is not None:
+            trace[slot][2] += time.perf_counter() - t_c
         return int(res.c.aligned_bases)
 
     def e2e_step():
@@ -419,21 +426,31 @@ def run_gpu_arm(args):
         done = [0]
 
         def work(slot):
+            # each host thread keeps `depth` regions in flight: region i+1 is uploading while region i computes and downloads
+            inflight, n, got = [], 0, 0
             while True:
                 with lock:
-                    if not order:
-                        return
-                    i = order.pop(0)
-                v = e2e_region(slot, regions[i])
-                with lock:
-                    done[0] += v
+                    i = order.pop(0) if order else None
+                if i is None:
+                    break
+                if len(inflight) == depth:
+                    got += e2e_collect(slot, inflight.pop(0))
+                k = n % depth
+                n += 1
+                e2e_submit(slot, k, regions[i])
+                inflight.append(k)
+            for k in inflight:
+                got += e2e_collect(slot, k)
+            with lock:
+                done[0] += got
         ts = [threading.Thread(target=work, args=(s,)) for s in range(n_workers)]
         [t.start() for t in ts]
         [t.join() for t in ts]
         return done[0]
 
     e2e_steps = max(1, min(args.steps, 3))
-    e2e_step()
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -448,9 +465,10 @@ def run_gpu_arm(args):
     if trace is not None and rank == 0:
         for slot, t in enumerate(trace):
             print("e2e worker %d: begin %.1f ms, add_batch %.1f ms, finish %.1f ms per step" %
-                  ((slot,) + tuple(1e3 * x / (e2e_steps + 1) for x in t)), file=sys.stderr)
-    for eng, _ in workers:
-        eng.close()
+                  ((slot,) + tuple(1e3 * x / (e2e_steps + max(1, min(args.warmup, 3))) for x in t)), file=sys.stderr)
+    for w in workers:
+        for eng, _ in w:
+            eng.close()
 
     # ---- aggregate over ranks -----------------------------------------------------------------
     vals = torch.tensor([dev_ms / args.steps, pil_ms / args.steps, wall_ms / args.steps, e2e_s, seq_ms / args.steps], dtype=torch.float64, device=dev)
@@ -499,7 +517,8 @@ def run_gpu_arm(args):
                                         if args.base_deltas else "2 bits per base")},
                "wall_ms_per_step": wall_step_ms, "sequential_ms_per_step": seq_step_ms,
                "e2e": {"value": job_aligned / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": job_h2d, "d2h_bytes_per_step": job_d2h,
-                       "ms_per_step": 1e3 * e2e_sec, "streams_per_gpu": n_workers},
+                       "ms_per_step": 1e3 * e2e_sec, "streams_per_gpu": n_workers * depth,
+                       "host_threads_per_gpu": n_workers, "passes_in_flight_per_thread": depth},
                "gpu_launches": int(job_launches),
                "roofline": {"bound": "hbm", "kernel": "k_pileup", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -522,7 +541,9 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrinks the genome (not the depth); 1.0 = the BASELINE config")
     ap.add_argument("--planes", default="fix", choices=["fix", "vcf"], help="per-locus results copied back in the e2e arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-workers", type=int, default=3, help="engines (host threads + streams) per GPU in the e2e arm")
+    ap.add_argument("--e2e-workers", type=int, default=3, help="host threads per GPU in the e2e arm")
+    ap.add_argument("--e2e-depth", type=int, default=1, help="regions in flight per host thread in the e2e arm (one engine "
+                    "and one result set each): the next region uploads while the previous one computes and downloads")
     ap.add_argument("--base-deltas", action="store_true", help="e2e arm: upload the 2-bit bases as their deltas against the "
                     "reference (pb_batch.base_delta_idx) instead of as they are; fewer bytes, no measured gain")
     ap.add_argument("--quals8", action="store_true", help="e2e arm: upload one quality byte per base even when the batch "
