@@ -389,9 +389,9 @@ def run_gpu_arm(args):
     planes = FIX_PLANES if args.planes == "fix" else None
     n_workers = args.e2e_workers
     max_size = max(r.size for r in regions)
-    depth = max(1, args.e2e_depth)                       # passes in flight per host thread (one engine + result set each)
+    e2e_depth = max(1, args.e2e_depth)                       # passes in flight per host thread (one engine + result set each)
     workers = [[(Engine(local), ResultBuffers(max_size, planes, indels_cap=1 << 20, indel_bytes_cap=1 << 23, pinned=True))
-                for _ in range(depth)] for _ in range(n_workers)]
+                for _ in range(e2e_depth)] for _ in range(n_workers)]
     from pilon_b200 import _capi as capi
     per_locus = sum(np.dtype(dt).itemsize * per for name, dt, per in capi.RESULT_PLANES if planes is None or name in planes)
     d2h = per_locus * total_loci
@@ -426,16 +426,16 @@ def run_gpu_arm(args):
         done = [0]
 
         def work(slot):
-            # each host thread keeps `depth` regions in flight: region i+1 is uploading while region i computes and downloads
+            # each host thread keeps `e2e_depth` regions in flight: region i+1 is uploading while region i computes and downloads
             inflight, n, got = [], 0, 0
             while True:
                 with lock:
                     i = order.pop(0) if order else None
                 if i is None:
                     break
-                if len(inflight) == depth:
+                if len(inflight) == e2e_depth:
                     got += e2e_collect(slot, inflight.pop(0))
-                k = n % depth
+                k = n % e2e_depth
                 n += 1
                 e2e_submit(slot, k, regions[i])
                 inflight.append(k)
@@ -517,8 +517,8 @@ def run_gpu_arm(args):
                                         if args.base_deltas else "2 bits per base")},
                "wall_ms_per_step": wall_step_ms, "sequential_ms_per_step": seq_step_ms,
                "e2e": {"value": job_aligned / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": job_h2d, "d2h_bytes_per_step": job_d2h,
-                       "ms_per_step": 1e3 * e2e_sec, "streams_per_gpu": n_workers * depth,
-                       "host_threads_per_gpu": n_workers, "passes_in_flight_per_thread": depth},
+                       "ms_per_step": 1e3 * e2e_sec, "streams_per_gpu": n_workers * e2e_depth,
+                       "host_threads_per_gpu": n_workers, "passes_in_flight_per_thread": e2e_depth},
                "gpu_launches": int(job_launches),
                "roofline": {"bound": "hbm", "kernel": "k_pileup", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
