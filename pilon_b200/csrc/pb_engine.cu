@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(RB_THREADS) k_rebuild_bases(RegionDev R, DevBa
     for (uint32_t i = threadIdx.x; i < head; i += RB_THREADS) out[byte0 + i] = stage[i];
     const uint32_t nvec = (nbytes - head) >> 4;
     for (uint32_t v = threadIdx.x; v < nvec; v += RB_THREADS) {
-        const uint8_t* sp = stage + head + 16u * v;                     // (not 16-byte aligned in shared memory: four word loads)
+        const uint8_t* sp = stage + head + 16u * v;                     // (not aligned in shared memory: assembled from byte loads)
         uint4 x;
         x.x = (uint32_t)sp[0] | ((uint32_t)sp[1] << 8) | ((uint32_t)sp[2] << 16) | ((uint32_t)sp[3] << 24);
         x.y = (uint32_t)sp[4] | ((uint32_t)sp[5] << 8) | ((uint32_t)sp[6] << 16) | ((uint32_t)sp[7] << 24);
