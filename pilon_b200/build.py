@@ -10,7 +10,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libpilonb200.so")
 SOURCES = ["pb_engine.cu"]
-DEPS = ["pb_engine.cu", "pb_kernels.cuh", "pb_pileup2.cuh", "pb_pileup3.cuh", "pb_pileup4.cuh", "pb_pileup5.cuh", "pb_device.cuh", os.path.join("..", "..", "include", "pilon_b200.h")]
+
+
+def deps():
+    """Every source the library is compiled from: all of csrc/*.cu, csrc/*.cuh and the public header."""
+    out = [f for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    return out + [os.path.join("..", "..", "include", "pilon_b200.h")]
+
 
 
 def nvcc_path() -> str:
@@ -24,14 +30,14 @@ def needs_build() -> bool:
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in deps())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xcompiler", "-fPIC", "-shared", "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-diag-suppress=20013,20015", "-Xcompiler", "-fPIC", "-shared", "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd, cwd=CSRC)

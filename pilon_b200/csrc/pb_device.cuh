@@ -48,7 +48,9 @@ struct PileBatch {
     uint32_t n_cigar; uint32_t flags;      // flags: 1 = counts toward fragCoverage, 2 = has reads
 };
 static constexpr int PB_MAXB = 20;
-struct PileBatches { int32_t n; int32_t pad; PileBatch b[PB_MAXB]; };
+// `ext` != nullptr (more than PB_MAXB batches): the table lives in device memory instead
+struct PileBatches { int32_t n; int32_t pad; const PileBatch* ext; PileBatch b[PB_MAXB]; };
+__device__ __forceinline__ const PileBatch& pile_batch(const PileBatches& PB, int i) { return PB.ext ? PB.ext[i] : PB.b[i]; }
 
 struct DevBatch {
     int64_t n_reads, n_cigar, n_seq, n_exc;
@@ -117,7 +119,6 @@ struct RegionDev {
     int4* cand;  uint32_t cand_cap;     // unordered pass-1 DEL candidates: (locus index, deletions, length, -)
     ScalarSlot* slots;                  // [SC_SLOTS] k_prep partial sums
     int32_t exp_flags;                  // PB_EXP timing experiments (results invalid): 1 skip epilogue, 2 skip compute, 4 skip staging copies
-    long long* dbg; int32_t dbg_tile;   // optional timeline of one tile (PB_DEBUG_TILE), 8 warps x 256 (tag, clock) pairs
     // outputs (final state)
     int32_t* o_cnt;   // [size*4]
     int64_t* o_qs;    // [size*4]

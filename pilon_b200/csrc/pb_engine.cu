@@ -67,16 +67,17 @@ struct pb_engine {
     bool in_region = false;
     RegionDev R{};
     std::vector<HostBatch> batches;
-    DBuf d_batches;                  // DevBatch[] image
+    DBuf d_batches, d_pile;          // DevBatch[] image; PileBatch[] image (only for > PB_MAXB batches)
     // per-locus buffers
     DBuf ref, rare, gplane[2], rare_bits, pc_diff, block_sums, scalars;
     DBuf o_cnt, o_qs, o_i32[12], o_wq, o_wmq, o_flags, o_call;
     // event buffers
-    DBuf ev_key, ev, perm, sort_buf, groups, cand, work, spill_scratch, str_pool, cub_tmp, dbg;
+    DBuf ev_key, ev, perm, sort_buf, groups, cand, work, spill_scratch, str_pool, cub_tmp;
     Scalars* h_sc = nullptr;         // pinned
     int64_t launches = 0;
     float last_pileup_ms = 0.f;
     bool dirty = false;              // rare planes may be non-zero after a failed run
+    bool unverified = false;         // pb_region_compute passes whose device error flag nobody has read yet
     // pb_region_compute replays a captured CUDA graph of the pass while the region's batches stay the same
     int graph_state = 0;             // 0: next pass runs plainly (and grows every buffer), 1: next pass is captured, 2: replay, 3: never
     cudaGraphExec_t graph_exec = nullptr;
@@ -84,7 +85,8 @@ struct pb_engine {
     std::vector<DevBatch> img_host;  // image of the batch table; a captured H2D copy reads it at every replay
     // PB_PHASE_TIMING=1 (diagnostics): device time of upload / pass / download per region, printed by pb_destroy
     bool phase_timing = false; cudaEvent_t ph[4] = {}; double ph_ms[3] = {0, 0, 0}; int64_t ph_regions = 0;
-    int pileup_version = 0;          // 0 = choose per region (k_pileup7 scatter / k_pileup5 gather); PB_PILEUP=1..5,7 forces one (A/B runs)
+    int pileup_version = 0;          // 0 = choose per region (k_pileup7 scatter / k_pileup5 gather); PB_PILEUP=5 or 7 forces one (A/B runs)
+    std::vector<PileBatch> pile_host; // image of the pileup kernels' batch table (device-side copy when there are more than PB_MAXB batches)
 };
 
 static int clean_sparse_planes(pb_engine* e);
@@ -117,17 +119,11 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
     e->cfg.min_qual = c->min_qual; e->cfg.min_mq = c->min_mq; e->cfg.flank = c->flank;
     e->cfg.default_qual = c->default_qual; e->cfg.min_min_depth = c->min_min_depth;
     e->cfg.old_indel = c->old_indel; e->cfg.fix_amb = c->fix_amb; e->cfg.min_depth = c->min_depth;
-    if (const char* v = getenv("PB_PILEUP")) { const int pv = atoi(v); if (pv >= 1 && pv <= 7 && pv != 6) e->pileup_version = pv; }
+    if (const char* v = getenv("PB_PILEUP")) { const int pv = atoi(v); if (pv == 5 || pv == 7) e->pileup_version = pv; }
     CK(cudaFuncSetAttribute(k_pileup7<false, P7_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile7<P7_TILE>)));
     CK(cudaFuncSetAttribute(k_pileup7<true, P7_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile7<P7_TILE>)));
     CK(cudaFuncSetAttribute(k_pileup5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_pileup5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CK(cudaFuncSetAttribute(k_pileup4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem4)));
-    CK(cudaFuncSetAttribute(k_pileup4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem4)));
-    CK(cudaFuncSetAttribute(k_pileup3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem3)));
-    CK(cudaFuncSetAttribute(k_pileup3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem3)));
-    CK(cudaFuncSetAttribute(k_pileup2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * P2_WARPS)));
-    CK(cudaFuncSetAttribute(k_pileup2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * P2_WARPS)));
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     if (getenv("PB_PHASE_TIMING")) { e->phase_timing = true; for (auto& ev : e->ph) CK(cudaEventCreate(&ev)); }
     CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
@@ -151,9 +147,9 @@ extern "C" int pb_destroy(pb_engine* e) {
     cudaStreamSynchronize(e->stream);
     free_batches(e);
     cudaStreamSynchronize(e->stream);
-    DBuf* all[] = {&e->d_batches, &e->ref, &e->rare_bits, &e->pc_diff, &e->block_sums, &e->scalars,
+    DBuf* all[] = {&e->d_batches, &e->d_pile, &e->ref, &e->rare_bits, &e->pc_diff, &e->block_sums, &e->scalars,
                    &e->o_cnt, &e->o_qs, &e->o_wq, &e->o_wmq, &e->o_flags, &e->o_call, &e->ev_key, &e->ev, &e->perm,
-                   &e->groups, &e->cand, &e->work, &e->dbg, &e->spill_scratch, &e->str_pool, &e->cub_tmp};
+                   &e->groups, &e->cand, &e->work, &e->spill_scratch, &e->str_pool, &e->cub_tmp};
     for (DBuf* b : all) b->release();
     e->rare.release(); for (auto& b : e->gplane) b.release();
     for (auto& b : e->o_i32) b.release();
@@ -186,6 +182,12 @@ extern "C" int pb_region_begin(pb_engine* e, const uint8_t* contig, int64_t cont
     CK(e->ref.ensure(ref_bytes + 8, false, s));                                     // k_rebuild_bases reads whole words
     CK(cudaMemcpyAsync(e->ref.p, contig + (R.ref_locus0 - 1), ref_bytes, cudaMemcpyHostToDevice, s));
     R.ref = e->ref.as<uint8_t>();
+    if (e->unverified && e->scalars.p) {              // asynchronous passes since the last read-back: did one of them raise a flag?
+        CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (e->h_sc->error) e->dirty = true;
+    }
+    e->unverified = false;
     if (e->dirty) { int rcc = clean_sparse_planes(e); if (rcc != PB_OK) return rcc; e->dirty = false; }
     const size_t n4 = (size_t)S * 4;
     CK(e->rare.ensure((size_t)S * sizeof(Rare), true, s));
@@ -400,15 +402,38 @@ __global__ void __launch_bounds__(256) k_unpack_quals3(const uint32_t* __restric
     out[2 * i + 1] = make_uint4(four((w1 >> 16) & 0xFFFu), four(__funnelshift_r(w1, w2, 28) & 0xFFFu), four((w2 >> 8) & 0xFFFu), four((w2 >> 20) & 0xFFFu));
 }
 
+static int stage_batch(pb_engine* e, const pb_batch* b, int frag);
+
 extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, int long_read_type) {
     if (!e || !b) return fail(PB_ERR_INVALID, "null argument");
     if (!e->in_region) return fail(PB_ERR_INVALID, "pb_region_begin has not been called");
     if (long_read_type != 0) return fail(PB_ERR_UNSUPPORTED, "long-read branches (PileUpRegion.scala:120-134,160,180,190) are gated off");
     if (b->n_seq >= (1ll << 32) || (b->n_seq & 3)) return fail(PB_ERR_INVALID, "n_seq must be a multiple of 4 and < 2^32");
     if (b->n_cigar >= (1ll << 32) || b->n_reads >= (1ll << 31)) return fail(PB_ERR_INVALID, "batch too large");
+    if (b->n_reads < 0 || b->n_cigar < 0 || b->n_seq < 0 || b->n_exc < 0) return fail(PB_ERR_INVALID, "negative count in pb_batch");
+    if (e->batches.size() >= MAX_BATCHES) return fail(PB_ERR_INVALID, "too many batches in one region");
+    if (b->mem != PB_MEM_HOST && b->mem != PB_MEM_DEVICE) return fail(PB_ERR_INVALID, "pb_batch.mem must be PB_MEM_HOST or PB_MEM_DEVICE");
+    const bool deltas = b->mem == PB_MEM_HOST && b->base_delta_idx, qcodes = b->mem == PB_MEM_HOST && b->qual_codes;
+    if (deltas && (b->n_base_delta < 0 || (b->n_base_delta && !b->base_delta_code))) return fail(PB_ERR_INVALID, "bad base delta arrays");
+    if (!deltas && !b->bases2 && b->n_seq) return fail(PB_ERR_INVALID, "batch has neither bases2 nor base deltas");
+    if (qcodes && b->qual_code_bits != 3 && b->qual_code_bits != 4) return fail(PB_ERR_INVALID, "qual_code_bits must be 3 or 4 when qual_codes is given");
+    if (!qcodes && !b->quals && b->n_seq) return fail(PB_ERR_INVALID, "batch has neither quals nor qual_codes");
+    if (b->n_reads && (!b->pos || !b->tlen || !b->read_len || !b->mapq || !b->flags || !b->cigar_off || !b->seq_off))
+        return fail(PB_ERR_INVALID, "null per-read array in pb_batch");
+    if ((b->n_cigar && !b->cigar) || (b->n_exc && (!b->exc_idx || !b->exc_base || !b->exc_qual))) return fail(PB_ERR_INVALID, "null array in pb_batch");
     CK(cudaSetDevice(e->device));
     drop_graph(e);                                   // the captured pass belongs to the previous batch set
+    // every argument has been validated: from here on only CUDA calls can fail, and then the half-staged batch is withdrawn
     e->batches.emplace_back();
+    const int rc_stage = stage_batch(e, b, frag);
+    if (rc_stage != PB_OK) {
+        for (void* p : e->batches.back().owned) cudaFreeAsync(p, e->stream);
+        e->batches.pop_back();
+    }
+    return rc_stage;
+}
+
+static int stage_batch(pb_engine* e, const pb_batch* b, int frag) {
     HostBatch& hb = e->batches.back();
     DevBatch& d = hb.d;
     memset(&d, 0, sizeof(d));
@@ -419,7 +444,6 @@ extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, in
     ST(pos, n); ST(tlen, n); ST(read_len, n); ST(mapq, n); ST(flags, n); ST(cigar_off, n + 1);
     ST(cigar, b->n_cigar); ST(seq_off, n);
     if (b->mem == PB_MEM_HOST && b->base_delta_idx) {   // compact transport: upload the deltas, rebuild bases2 on the device
-        if (b->n_base_delta < 0 || (b->n_base_delta && !b->base_delta_code)) return fail(PB_ERR_INVALID, "bad base delta arrays");
         void *pi = nullptr, *pc = nullptr, *pout = nullptr;
         const size_t nd = (size_t)b->n_base_delta;
         CK(cudaMallocAsync(&pi, nd * 4 + 64, e->stream)); hb.owned.push_back(pi);
@@ -435,12 +459,10 @@ extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, in
             e->launches++;
         }
     } else {
-        if (!b->bases2 && b->n_seq) return fail(PB_ERR_INVALID, "batch has neither bases2 nor base deltas");
         ST(bases2, b->n_seq / 4);
     }
     if (b->mem == PB_MEM_HOST && b->qual_codes) {      // compact transport: upload 3- / 4-bit codes, expand on the device
         const int bits = b->qual_code_bits;
-        if (bits != 3 && bits != 4) return fail(PB_ERR_INVALID, "qual_code_bits must be 3 or 4 when qual_codes is given");
         const size_t per = bits == 4 ? 16 : 32;                       // bases expanded by one thread
         const size_t groups = ((size_t)b->n_seq + per - 1) / per;
         const size_t in_bytes = ((size_t)b->n_seq * bits + 7) / 8;
@@ -456,7 +478,6 @@ extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, in
         }
         d.quals = (const uint8_t*)pout;
     } else {
-        if (!b->quals && b->n_seq) return fail(PB_ERR_INVALID, "batch has neither quals nor qual_codes");
         ST(quals, b->n_seq);
     }
     ST(exc_idx, b->n_exc); ST(exc_base, b->n_exc); ST(exc_qual, b->n_exc);
@@ -465,7 +486,6 @@ extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, in
     CK(cudaMallocAsync(&p, ((size_t)b->n_cigar + 1) * sizeof(Seg), e->stream)); hb.owned.push_back(p); d.seg = (Seg*)p;
     CK(cudaMallocAsync(&p, ((size_t)e->R.n_win + 2) * 4, e->stream)); hb.owned.push_back(p); d.win_first = (uint32_t*)p;
     CK(cudaMallocAsync(&p, (n + 1) * 4, e->stream)); hb.owned.push_back(p); d.insert_out = (int32_t*)p;
-    if (e->batches.size() > MAX_BATCHES) return fail(PB_ERR_INVALID, "too many batches in one region");
     d.reach = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(e->scalars.p) + SC_REACH_OFF) + 2 * (e->batches.size() - 1);
     return PB_OK;
 }
@@ -575,63 +595,39 @@ static int compute(pb_engine* e, bool time_pileup, bool full_cap = false) {
         const int64_t depth = R.size > 0 ? (int64_t)(total_seq / (size_t)R.size) : 0;      // stored bases per locus: >= depth
         pv = (tiles >= 256 && depth <= 1000) ? 7 : 5;
     }
-    if (R.exp_flags & 256) {               // knock-out: everything but the pileup kernel (what the rest of the pass costs)
-    } else if (pv == 1) {
-        const unsigned grid = (unsigned)((R.n_win + PILEUP_WARPS - 1) / PILEUP_WARPS);
-        if (e->cfg.min_qual > 0) k_pileup<true><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
-        else k_pileup<false><<<grid, PILEUP_WARPS * 32, 0, s>>>(R, dB, nb);
-    } else if (pv >= 5 && nb <= PB_MAXB) {
-        const bool v7 = pv == 7;
-        const unsigned grid = v7 ? (unsigned)((R.n_win * 32 + P7_TILE - 1) / P7_TILE)
-                                 : (unsigned)((R.n_win + P5_WARPS - 1) / P5_WARPS);
-        size_t smem = sizeof(Warp5) * P5_WARPS;
-        if (const char* sp = getenv("PB_SMEM_PAD")) smem += (size_t)atoi(sp);    // occupancy experiments
-        PileBatches PBt; memset(&PBt, 0, sizeof(PBt)); PBt.n = nb;
+    if (pv == 7 && nb > PB_MAXB) pv = 5;   // the scatter kernel keeps its per-batch cursors in shared memory: <= PB_MAXB batches
+    PileBatches PBt; memset(&PBt, 0, sizeof(PBt)); PBt.n = nb;
+    {
+        std::vector<PileBatch>& pile = e->pile_host;
+        pile.resize((size_t)std::max(nb, 1));
         for (int i = 0; i < nb; i++) {
             const DevBatch& d = img[i];
-            PBt.b[i].seg = d.seg; PBt.b[i].quals = d.quals; PBt.b[i].bases2 = d.bases2; PBt.b[i].win_first = d.win_first;
-            PBt.b[i].n_cigar = (uint32_t)d.n_cigar; PBt.b[i].reach = d.reach;
-            PBt.b[i].flags = (d.frag ? 1u : 0u) | (d.n_reads ? 2u : 0u);
+            PileBatch& pb_ = pile[i];
+            pb_.seg = d.seg; pb_.quals = d.quals; pb_.bases2 = d.bases2; pb_.win_first = d.win_first;
+            pb_.n_cigar = (uint32_t)d.n_cigar; pb_.reach = d.reach;
+            pb_.flags = (d.frag ? 1u : 0u) | (d.n_reads ? 2u : 0u);
+            if (i < PB_MAXB) PBt.b[i] = pb_;
         }
-        if (v7) {
-            if (e->cfg.min_qual > 0) k_pileup7<true, P7_TILE><<<grid, P7_WARPS * 32, sizeof(Tile7<P7_TILE>), s>>>(R, PBt);
-            else k_pileup7<false, P7_TILE><<<grid, P7_WARPS * 32, sizeof(Tile7<P7_TILE>), s>>>(R, PBt);
-        } else if (e->cfg.min_qual > 0) k_pileup5<true><<<grid, P5_WARPS * 32, smem, s>>>(R, PBt);
-        else k_pileup5<false><<<grid, P5_WARPS * 32, smem, s>>>(R, PBt);
-    } else if (pv >= 4) {      // (also: more batches than k_pileup5's by-value table holds)
-        const unsigned grid = (unsigned)((R.n_win + P4_CW - 1) / P4_CW);
-        if (const char* dt = getenv("PB_DEBUG_TILE")) {
-            CK(e->dbg.ensure(8 * 256 * 16, false, s));
-            CK(cudaMemsetAsync(e->dbg.p, 0, 8 * 256 * 16, s));
-            R.dbg = e->dbg.as<long long>(); R.dbg_tile = atoi(dt);
+        if (nb > PB_MAXB) {                // more BAMs than the by-value table holds: the kernel reads a device-side table
+            CK(e->d_pile.ensure(sizeof(PileBatch) * (size_t)nb, false, s));
+            CK(cudaMemcpyAsync(e->d_pile.p, pile.data(), sizeof(PileBatch) * (size_t)nb, cudaMemcpyHostToDevice, s));
+            PBt.ext = e->d_pile.as<PileBatch>();
         }
-        if (e->cfg.min_qual > 0) k_pileup4<true><<<grid, (P4_CW + 1) * 32, sizeof(Smem4), s>>>(R, dB, nb);
-        else k_pileup4<false><<<grid, (P4_CW + 1) * 32, sizeof(Smem4), s>>>(R, dB, nb);
-    } else if (pv == 3) {
-        const unsigned grid = (unsigned)((R.n_win + P3_CW - 1) / P3_CW);
-        if (e->cfg.min_qual > 0) k_pileup3<true><<<grid, (P3_CW + 1) * 32, sizeof(Smem3), s>>>(R, dB, nb);
-        else k_pileup3<false><<<grid, (P3_CW + 1) * 32, sizeof(Smem3), s>>>(R, dB, nb);
+    }
+    if (R.exp_flags & 256) {               // knock-out: everything but the pileup kernel (what the rest of the pass costs)
+    } else if (pv == 7) {
+        const unsigned grid = (unsigned)((R.n_win * 32 + P7_TILE - 1) / P7_TILE);
+        if (e->cfg.min_qual > 0) k_pileup7<true, P7_TILE><<<grid, P7_WARPS * 32, sizeof(Tile7<P7_TILE>), s>>>(R, PBt);
+        else k_pileup7<false, P7_TILE><<<grid, P7_WARPS * 32, sizeof(Tile7<P7_TILE>), s>>>(R, PBt);
     } else {
-        const unsigned grid = (unsigned)((R.n_win + P2_WARPS - 1) / P2_WARPS);
-        const size_t smem = sizeof(WarpSmem) * P2_WARPS;
-        if (e->cfg.min_qual > 0) k_pileup2<true><<<grid, P2_WARPS * 32, smem, s>>>(R, dB, nb);
-        else k_pileup2<false><<<grid, P2_WARPS * 32, smem, s>>>(R, dB, nb);
+        const unsigned grid = (unsigned)((R.n_win + P5_WARPS - 1) / P5_WARPS);
+        size_t smem = sizeof(Warp5) * P5_WARPS;
+        if (const char* sp = getenv("PB_SMEM_PAD")) smem += (size_t)atoi(sp);    // occupancy experiments
+        if (e->cfg.min_qual > 0) k_pileup5<true><<<grid, P5_WARPS * 32, smem, s>>>(R, PBt);
+        else k_pileup5<false><<<grid, P5_WARPS * 32, smem, s>>>(R, PBt);
     }
     e->launches++;
     if (time_pileup) CK(cudaEventRecord(e->evp1, s));
-    if (R.dbg) {
-        std::vector<long long> h(8 * 256 * 2);
-        CK(cudaStreamSynchronize(s));
-        CK(cudaMemcpy(h.data(), R.dbg, h.size() * 8, cudaMemcpyDeviceToHost));
-        long long t0c = 0;
-        for (int w = 0; w < 8; w++) for (int i = 0; i < 256; i++) { long long t = h[(w * 256 + i) * 2 + 1]; if (t && (!t0c || t < t0c)) t0c = t; }
-        for (int w = 0; w < 8; w++) {
-            printf("DBG warp %d:", w);
-            for (int i = 0; i < 256; i++) { long long tg = h[(w * 256 + i) * 2], t = h[(w * 256 + i) * 2 + 1]; if (!t) break; printf(" %lld.%lld@%lld", tg >> 32, tg & 0xffffffff, t - t0c); }
-            printf("\n");
-        }
-        R.dbg = nullptr;
-    }
     // deletion spill: candidates are bounded by the number of deletion groups
     uint32_t p2 = 1; while (p2 < evcap) p2 <<= 1;
     CK(e->spill_scratch.ensure((size_t)p2 * sizeof(int4) + 16, false, s));
@@ -649,6 +645,7 @@ extern "C" int pb_region_compute(pb_engine* e) {
     if (use_graph && e->graph_state == 2) {                  // the pass has no host round trip: one call replays it
         CK(cudaGraphLaunch(e->graph_exec, e->stream));
         e->launches += e->graph_launches;
+        e->dirty = false; e->unverified = true;              // a pass without error flags leaves the sparse planes zero
         return PB_OK;
     }
     const bool capture = use_graph && e->graph_state == 1;
@@ -673,10 +670,11 @@ extern "C" int pb_region_compute(pb_engine* e) {
         e->graph_launches = e->launches - l0;
         e->graph_state = 2;
         CK(cudaGraphLaunch(e->graph_exec, e->stream));
+        e->dirty = false; e->unverified = true;
         return PB_OK;
     }
     if (rc != PB_OK) return rc;
-    e->dirty = false;
+    e->dirty = false; e->unverified = true;
     if (use_graph && e->graph_state == 0) e->graph_state = 1;      // buffers have their final size now
     return PB_OK;
 }

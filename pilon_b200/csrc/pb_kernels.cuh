@@ -2,11 +2,11 @@
 //
 // Pipeline per region:
 //   k_prep      thread per read: CIGAR walk -> segments, sparse updates, physCov diffs, window -> first segment table
-//   k_scalars   region coverage / minDepth
-//   (cub radix sort of the indel event keys) -> k_groups -> k_indel_strings
+//   k_indel     thread per trusted I / D op: left shift, sparse updates, event records
+//   k_fold      region scalars: coverage / minDepth, reach of the segments
 //   k_scan1/2/3 physCov prefix sums (PileUpRegion.computePhysCov)
-//   k_pileup    THE hot kernel: warp per 32-locus window gathers every overlapping segment,
-//               accumulates in registers, then runs BaseCall + pass-1 classification and flushes
+//   (radix sort of the indel event keys) -> k_groups -> k_indel_strings
+//   the pileup kernel (pb_pileup7.cuh scatter / pb_pileup5.cuh gather) + per-locus epilogue (pb_epilogue.cuh)
 //   k_spill     sequential deletion-spill resolution (GenomeRegion.scala:259-264) + fix-up
 //
 // Reference citations are relative to /root/reference/src/main/scala/org/broadinstitute/pilon/.
@@ -329,6 +329,11 @@ __global__ void __launch_bounds__(128) k_indel(RegionDev R, const DevBatch* __re
             const int64_t f = (int64_t)R.start + sg.loc0 + sg.len - aStart;
             const int fi = (int)(f > 0x3fffffff ? 0x3fffffff : f);
             if (fi > B.reach[0]) atomicMax(&B.reach[0], fi);     // (never beyond the read's own aligned span in practice)
+            // the shift walks read offsets backwards across earlier CIGAR elements (:167): after a long insertion or a
+            // leading soft clip inside a repeat the re-added bases can start LEFT of the read's pos
+            const int64_t bk = (int64_t)aStart - ((int64_t)R.start + sg.loc0);
+            const int bi = (int)(bk > 0x3fffffff ? 0x3fffffff : bk);
+            if (bi > B.reach[1]) atomicMax(&B.reach[1], bi);
         }
     }
     // few threads: plain atomics into the slots that the last k_fold folds
@@ -666,130 +671,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan3(RegionDev R, const uint2
 #pragma unroll
         for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < R.size) { R.o_pc[base + k] = pc[k]; R.o_is[base + k] = is[k]; }
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_pileup: the hot kernel.
-//
-// One warp owns a window of 32 consecutive loci (lane <-> locus) and keeps the ten hot counters
-// of PileUp.add (PileUp.scala:75-84) in registers: no atomics on the per-base path.  Candidate
-// segments are fetched 32 at a time with one coalesced 512-byte load (lane <-> descriptor); a
-// ballot keeps only those that overlap the window, and their descriptors are broadcast with
-// shuffles.  For each overlapping segment every lane reads its own (quality, 2-bit base) pair --
-// consecutive lanes read consecutive bytes -- and accumulates.  The epilogue merges the sparse
-// contributions, runs BaseCall and pass-1 classification and writes every per-locus output once.
-// ---------------------------------------------------------------------------------------------
-static constexpr int PILEUP_WARPS = 8;
-
-template <bool MINQ>
-__global__ void __launch_bounds__(PILEUP_WARPS * 32) k_pileup(RegionDev R, const DevBatch* __restrict__ batches, int n_batches) {
-    const int lane = threadIdx.x & 31;
-    const int64_t w = (int64_t)blockIdx.x * PILEUP_WARPS + (threadIdx.x >> 5);
-    if (w >= R.n_win) return;
-    const int32_t w0 = (int32_t)(w << 5);
-    const int32_t loc = w0 + lane;
-    const int min_qual = R.cfg.min_qual;
-    const uint32_t defq = (uint32_t)(int)(int8_t)R.cfg.default_qual;
-
-    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    uint64_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
-    uint32_t mqS = 0, qS = 0, bp = 0, fragN = 0;
-
-    for (int b = 0; b < n_batches; b++) {
-        const DevBatch& B = batches[b];
-        if (B.n_reads == 0) continue;
-        const uint32_t nbefore = c0 + c1 + c2 + c3;
-        const int32_t fwd = B.reach[0], back = B.reach[1];
-        // candidate reads: (pos - start) in (w0 - fwd, w0 + 32 + back)
-        const int64_t x = (int64_t)w0 - fwd + 1;
-        int64_t khi = (((int64_t)w0 + 32 + back) + 31) >> 5; if (khi > R.n_win) khi = R.n_win;
-        const uint32_t slo = x <= 0 ? 0u : B.win_first[x >> 5];    // x <= 0: reads left of the region count too
-        const uint32_t shi = (((int64_t)w0 + 32 + back) > ((int64_t)R.n_win << 5)) ? (uint32_t)B.n_cigar : B.win_first[khi];
-        const uint8_t* __restrict__ quals = B.quals;
-        const uint8_t* __restrict__ bases2 = B.bases2;
-        for (uint32_t sb = slo; sb < shi; sb += 32) {
-            Seg mine; mine.loc0 = 0; mine.len = 0; mine.src = 0; mine.w = 0;
-            if (sb + lane < shi) mine = B.seg[sb + lane];
-            const bool ov = mine.len > 0 && mine.loc0 < w0 + 32 && mine.loc0 + mine.len > w0;
-            unsigned m = __ballot_sync(FULL, ov);
-            while (m) {
-                const int j = __ffs(m) - 1; m &= m - 1;
-                const int32_t sl0 = __shfl_sync(FULL, mine.loc0, j);
-                const int32_t sln = __shfl_sync(FULL, mine.len, j);
-                const uint32_t ssrc = __shfl_sync(FULL, mine.src, j);
-                const uint32_t sw = __shfl_sync(FULL, mine.w, j);
-                const uint32_t off = (uint32_t)(loc - sl0);
-                if (off < (uint32_t)sln) {
-                    if (sw & SEG_VALID) {
-                        const uint32_t idx = ssrc + off;
-                        const uint32_t qb = quals[idx];
-                        const uint32_t code = (bases2[idx >> 2] >> ((idx & 3) << 1)) & 3;
-                        if (!(qb & 0x80)) {                               // countable base (PileUp.scala:46-52)
-                            const uint32_t q = (sw & SEG_HASQ) ? qb : defq;
-                            if (!MINQ || (int)q >= min_qual) {            // PileUp.scala:77
-                                const uint32_t mq1 = sw & 0xFFFF;
-                                const uint32_t qm = q * mq1;
-                                c0 += code == 0; c1 += code == 1; c2 += code == 2; c3 += code == 3;
-                                q0 += code == 0 ? qm : 0; q1 += code == 1 ? qm : 0;
-                                q2 += code == 2 ? qm : 0; q3 += code == 3 ? qm : 0;
-                                mqS += mq1; qS += q;
-                            }
-                        }
-                    } else bp++;                                          // PileUpRegion.scala:45
-                }
-            }
-        }
-        if (B.frag) fragN += (c0 + c1 + c2 + c3) - nbefore;
-    }
-
-    // ---- epilogue: merge sparse contributions, BaseCall, pass-1 classification, flush -------
-    const bool inr = loc < R.size;
-    const uint32_t rb = R.rare_bits[w];
-    int32_t r_ins = 0, r_insq = 0, r_del = 0, r_delq = 0, r_q = 0, r_mq = 0, r_clips = 0, r_delfrag = 0;
-    uint32_t gi = 0, gd = 0;
-    if (inr && ((rb >> lane) & 1)) {
-        int4* rp = reinterpret_cast<int4*>(&R.rare[loc]);
-        const int4 ra = rp[0], rb2 = rp[1];
-        r_ins = ra.x; r_insq = ra.y; r_del = ra.z; r_delq = ra.w; r_q = rb2.x; r_mq = rb2.y; r_clips = rb2.z; r_delfrag = rb2.w;
-        gi = R.r_gins[loc]; gd = R.r_gdel[loc];
-        rp[0] = make_int4(0, 0, 0, 0); rp[1] = make_int4(0, 0, 0, 0);
-    }
-    if (rb && lane == 0) R.rare_bits[w] = 0;
-    uint32_t cand = 0;
-    if (inr) {
-        CallIn in;
-        in.c[0] = c0; in.c[1] = c1; in.c[2] = c2; in.c[3] = c3;
-        in.q[0] = (int64_t)q0; in.q[1] = (int64_t)q1; in.q[2] = (int64_t)q2; in.q[3] = (int64_t)q3;
-        in.mqSum = (int32_t)(mqS + (uint32_t)r_mq); in.qSum = (int32_t)(qS + (uint32_t)r_q);
-        in.ins = r_ins; in.del = r_del; in.insQual = r_insq; in.delQual = r_delq;
-        in.gins = gi ? &R.groups[gi - 1] : nullptr; in.gdel = gd ? &R.groups[gd - 1] : nullptr;
-        int32_t ilen = 0;
-        const uint64_t call = compute_call(R.cfg, in, &ilen);
-        const int64_t n = (int64_t)c0 + c1 + c2 + c3;
-        const int64_t depth = n + r_del;
-        const int64_t qtot = in.q[0] + in.q[1] + in.q[2] + in.q[3];
-        uint32_t fl = 0;
-        if (R.sc->read_count != 0)                                       // GenomeRegion.scala:229-231
-            fl = classify(call, depth, R.sc->min_depth, ref_class(ref_at(R, (int64_t)R.start + loc)), R.cfg.fix_amb);
-        reinterpret_cast<int4*>(R.o_cnt)[loc] = make_int4((int)c0, (int)c1, (int)c2, (int)c3);
-        reinterpret_cast<longlong2*>(R.o_qs)[2 * (int64_t)loc] = make_longlong2((long long)q0, (long long)q1);
-        reinterpret_cast<longlong2*>(R.o_qs)[2 * (int64_t)loc + 1] = make_longlong2((long long)q2, (long long)q3);
-        R.o_mq[loc] = in.mqSum; R.o_q[loc] = in.qSum; R.o_bp[loc] = (int32_t)bp;
-        R.o_del[loc] = r_del; R.o_delq[loc] = r_delq; R.o_ins[loc] = r_ins; R.o_insq[loc] = r_insq;
-        R.o_clips[loc] = r_clips;
-        R.o_cov[loc] = wrap32(depth);                                    // GenomeRegion.scala:247
-        R.o_frag[loc] = (int32_t)(fragN + (uint32_t)r_delfrag);          // GenomeRegion.scala:296-298
-        R.o_wq[loc] = (int8_t)(uint8_t)roundDivL(qtot, in.mqSum);        // PileUp.scala:60-62, .toByte
-        R.o_wmq[loc] = (int8_t)(uint8_t)roundDivL(qtot, in.qSum);        // PileUp.scala:56-58, .toByte
-        R.o_flags[loc] = (uint8_t)fl;
-        R.o_call[loc] = call;
-        if ((fl & PB_FL_CHANGED) && ((fl >> PB_FL_KIND_SHIFT) & 3) == PB_KIND_DEL) {
-            cand = 1;
-            const uint32_t ci = atomicAdd(&R.sc->n_cand, 1u);
-            if (ci < R.cand_cap) R.cand[ci] = make_int4(loc, r_del, ilen, 0); else atomicOr(&R.sc->error, 2);
-        }
-    }
-    (void)cand;
 }
 
 // ---------------------------------------------------------------------------------------------

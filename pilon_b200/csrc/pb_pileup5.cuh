@@ -18,11 +18,12 @@
 //   flush      warp-uniform shuffle reduction of the packed registers into the table.
 //   epilogue   finish_locus(): sparse merge + BaseCall + pass-1 classification, one write per plane.
 #pragma once
-#include "pb_pileup4.cuh"
+#include "pb_epilogue.cuh"
 
 namespace pb {
 
 static constexpr int P5_WARPS = 8;
+static constexpr uint32_t P5_SPILL_ROWS = 120000;   // rows between folds of the 32-bit quality sums: 120000 * 32512 < 2^32
 
 struct __align__(8) Geo5 { uint32_t colmask; uint16_t qoff; uint16_t flags; };   // flags: mq1 | valid<<9 | hasq<<10 | fast<<11
 
@@ -31,7 +32,7 @@ struct __align__(16) Warp5 {
     uint8_t rows[2][32][64];                     // 48 quality bytes + 12 code bytes (+4) per staged row
     uint8_t tail[16];
     Geo5 geo[2][32];
-    uint32_t tqs[32][4];                         // 32-bit running tables (see Warp4): native shared atomics
+    uint32_t tqs[32][4];                         // 32-bit running tables : native shared atomics
     uint32_t tcnt[32][4];
     uint32_t tmq[32], tq[32], tbp[32];
     unsigned long long codes[32];
@@ -65,19 +66,22 @@ __global__ void __launch_bounds__(P5_WARPS * 32, 4) k_pileup5(const RegionDev R,
 #pragma unroll
         for (int j = 0; j < 4; j++) P8 |= __shfl_sync(FULL, code, kk + j) << (2 * j);
     }
-    // candidate segment range of every batch (lane <-> batch): one load latency for all of them
+    // candidate segment range of 32 batches at a time (lane <-> batch): one load latency for all of them
     uint32_t my_slo = 0, my_nseg = 0;
-    if (lane < n_batches) {
-        const PileBatch& Bl = PB.b[lane];
-        if (Bl.flags & 2) {
-            const int64_t x = (int64_t)w0 - Bl.reach[0] + 1;
-            const int64_t y = (int64_t)w0 + 32 + Bl.reach[1];
-            int64_t khi = (y + 31) >> 5; if (khi > R.n_win) khi = R.n_win;
-            my_slo = x <= 0 ? 0u : Bl.win_first[x >> 5];
-            const uint32_t shi = (y > ((int64_t)R.n_win << 5)) ? Bl.n_cigar : Bl.win_first[khi];
-            my_nseg = shi > my_slo ? shi - my_slo : 0u;
+    auto load_ranges = [&](int b0) {
+        my_slo = 0; my_nseg = 0;
+        if (b0 + lane < n_batches) {
+            const PileBatch& Bl = pile_batch(PB, b0 + lane);
+            if (Bl.flags & 2) {
+                const int64_t x = (int64_t)w0 - Bl.reach[0] + 1;
+                const int64_t y = (int64_t)w0 + 32 + Bl.reach[1];
+                int64_t khi = (y + 31) >> 5; if (khi > R.n_win) khi = R.n_win;
+                my_slo = x <= 0 ? 0u : Bl.win_first[x >> 5];
+                const uint32_t shi = (y > ((int64_t)R.n_win << 5)) ? Bl.n_cigar : Bl.win_first[khi];
+                my_nseg = shi > my_slo ? shi - my_slo : 0u;
+            }
         }
-    }
+    };
     __syncwarp();
 
     uint32_t cnt4 = 0, QLo = 0, QHi = 0, cur_mq = 0, nrows = 0, fragN = 0, nprev = 0, rows_total = 0;
@@ -134,6 +138,7 @@ __global__ void __launch_bounds__(P5_WARPS * 32, 4) k_pileup5(const RegionDev R,
         while (s_b < 0 || s_c >= s_nch) {
             s_b++; s_c = 0;
             if (s_b >= n_batches) return false;
+            if ((s_b & 31) == 0) load_ranges(s_b);      // (warp-uniform) the next 32 batches' ranges
             s_nseg = __shfl_sync(FULL, my_nseg, s_b & 31);
             s_nch = (s_nseg + 31) >> 5;
             s_slo = __shfl_sync(FULL, my_slo, s_b & 31);
@@ -143,7 +148,7 @@ __global__ void __launch_bounds__(P5_WARPS * 32, 4) k_pileup5(const RegionDev R,
     const Seg none = {0, 0, 0, 0};
     Seg next = none;
     bool have_next = advance();
-    if (have_next && (s_c << 5) + lane < s_nseg) next = PB.b[s_b].seg[s_slo + (s_c << 5) + lane];
+    if (have_next && (s_c << 5) + lane < s_nseg) next = pile_batch(PB, s_b).seg[s_slo + (s_c << 5) + lane];
     uint32_t dom_stage = 0;
 
     // per staged buffer: number of rows, dominant mq, batch index (-1: nothing staged)
@@ -152,11 +157,11 @@ __global__ void __launch_bounds__(P5_WARPS * 32, 4) k_pileup5(const RegionDev R,
     auto stage = [&](int buf) {                         // stages the chunk under the cursor, then advances it
         const Seg mine = next;
         const int my_b = s_b;
-        const uint8_t* __restrict__ gquals = PB.b[my_b].quals;
-        const uint8_t* __restrict__ gbases = PB.b[my_b].bases2;
+        const uint8_t* __restrict__ gquals = pile_batch(PB, my_b).quals;
+        const uint8_t* __restrict__ gbases = pile_batch(PB, my_b).bases2;
         have_next = advance();
         next = none;
-        if (have_next && (s_c << 5) + lane < s_nseg) next = PB.b[s_b].seg[s_slo + (s_c << 5) + lane];   // prefetch
+        if (have_next && (s_c << 5) + lane < s_nseg) next = pile_batch(PB, s_b).seg[s_slo + (s_c << 5) + lane];   // prefetch
         const bool ov = mine.len > 0 && mine.loc0 < w0 + 32 && mine.loc0 + mine.len > w0;
         const bool valid = mine.w & SEG_VALID, hasq = mine.w & SEG_HASQ;
         const uint32_t mq1 = mine.w & 0xFFFF;
@@ -229,13 +234,13 @@ __global__ void __launch_bounds__(P5_WARPS * 32, 4) k_pileup5(const RegionDev R,
         const uint32_t dom = buf ? dom_b1 : dom_b0;
         const int bb = buf ? b_b1 : b_b0;
         if (bb != last_b) {                             // first chunk of another batch: close the previous one
-            if (last_b >= 0) batch_end(PB.b[last_b].flags & 1);
+            if (last_b >= 0) batch_end(pile_batch(PB, last_b).flags & 1);
             last_b = bb;
         }
         if (n == 0) return;
         if (dom != cur_mq) { flush(); cur_mq = dom; }
         rows_total += 32;
-        if (rows_total > P4_SPILL_ROWS) { flush(); spill(); }
+        if (rows_total > P5_SPILL_ROWS) { flush(); spill(); }
         uint32_t gm = 0, gf = 0; int32_t gq = (int32_t)rows_base;
         if (lane < n) {
             const Geo5 ge = W.geo[buf][lane];
@@ -334,7 +339,7 @@ __global__ void __launch_bounds__(P5_WARPS * 32, 4) k_pileup5(const RegionDev R,
         __syncwarp();
         cur ^= 1; have_cur = staged;
     }
-    if (last_b >= 0) batch_end(PB.b[last_b].flags & 1);
+    if (last_b >= 0) batch_end(pile_batch(PB, last_b).flags & 1);
     cp_async_wait<0>();
     __syncwarp();
     uint32_t c[4]; uint64_t q[4];

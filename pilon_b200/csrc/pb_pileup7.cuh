@@ -20,7 +20,7 @@
 //     where Bq / C collect `qual * (mq1 - dom)` and `mq1 - dom` of the other reads (two more reductions
 //     per base for those only).  badPair and the bases outside fragCoverage share a fourth word;
 //   * the loads of a lane's next chunk are issued before the reductions of the current one;
-//   * every segment is met once per tile (T = 1024: 13 % halo instead of 5x), quality bytes go from
+//   * every segment is met once per tile (T = 2048: 6 % halo instead of 5x), quality bytes go from
 //     L2 straight into registers, nothing is staged or flushed;
 //   * 12-bit counts: after 4064 descriptors the tile is folded into the 32/64-bit output planes
 //     (deep pile-ups only), then the epilogue (finish_locus) runs per locus as before.
