@@ -211,17 +211,55 @@ def oracle_lib():
     return lib
 
 
-def oracle_region(lib, reg, planes=FIX_PLANES):
+def oracle_region(lib, reg, planes=FIX_PLANES, indels=False):
     from pilon_b200.engine import EngineConfig
     from pilon_b200.packing import ResultBuffers
     cfg = EngineConfig().to_c()
     h = lib.po_region_new(C.byref(cfg), reg.contig.ctypes.data, len(reg.contig), reg.start, reg.stop)
     for b in reg.batches:
         assert lib.po_region_add_batch(h, C.byref(b.c), int(b.frag), 0, None) == 0
-    res = ResultBuffers(reg.size, planes)
+    res = ResultBuffers(reg.size, planes, *(_indel_caps(reg) if indels else (0, 0)))
     assert lib.po_region_finish(h, C.byref(res.c)) == 0
     lib.po_region_free(h)
     return res
+
+
+def _indel_caps(reg):
+    return max(1 << 16, reg.n_cigar // 8), 1 << 24
+
+
+def parity_check(eng, lib_res, reg):
+    """One region through the public C ABI from host buffers (the e2e path) against the C oracle's result for the same
+    region: every scalar, every per-locus plane and every indel evidence entry, bit for bit.  Returns a list of
+    mismatch descriptions (empty = identical)."""
+    from pilon_b200 import _capi as capi
+    from pilon_b200.packing import ResultBuffers
+    res = ResultBuffers(reg.size, None, *_indel_caps(reg))
+    eng.region_begin(reg.contig, reg.start, reg.stop)
+    for b in reg.batches:
+        eng.add_batch(b, b.frag)
+    eng.finish(res)
+    bad = []
+    for f in ("size", "base_count", "coverage", "aligned_bases", "read_count", "min_depth", "unknown_ops", "dropped_oob",
+              "n_indels", "n_indel_bytes"):
+        if getattr(res.c, f) != getattr(lib_res.c, f):
+            bad.append("scalar %s: %r != %r" % (f, getattr(res.c, f), getattr(lib_res.c, f)))
+    for name, _, _ in capi.RESULT_PLANES:
+        if not np.array_equal(res[name], lib_res[name]):
+            bad.append("plane %s differs at %s" % (name, np.argwhere(res[name] != lib_res[name])[:3].tolist()))
+    if res.per_bam() != lib_res.per_bam():
+        bad.append("per-BAM deltas: %r != %r" % (res.per_bam(), lib_res.per_bam()))
+    ia, ib = res.indels(), lib_res.indels()
+    if len(ia) != len(ib):
+        bad.append("indel entries: %d != %d" % (len(ia), len(ib)))
+    for x, y in zip(ia, ib):
+        kx, ky = (x["locus_index"], x["kind"], x["list_len"]), (y["locus_index"], y["kind"], y["list_len"])
+        wx = (x["win_count"], x["win_len"], x["win_has_n"], x["string"]) if x["win_count"] >= 2 and 2 * x["win_count"] > x["list_len"] else None
+        wy = (y["win_count"], y["win_len"], y["win_has_n"], y["string"]) if y["win_count"] >= 2 and 2 * y["win_count"] > y["list_len"] else None
+        if kx != ky or wx != wy:        # the winner is only defined (and consumed, PileUp.scala:219-220) as a strict majority
+            bad.append("indel entry %r != %r" % (x, y))
+            break
+    return bad
 
 
 def time_oracle(regions, threads):
@@ -490,18 +528,35 @@ def run_gpu_arm(args):
         alg = sum(r.alg_bytes for r in regions)                 # this rank's launches
         achieved = alg / (pileup_ms * 1e-3) / 1e9               # GB/s over the pileup kernel's launches of one step
         depth = total_aligned / total_loci
-        cpu = None
+        cpu = parity = None
         if world == 1 and not args.no_cpu_baseline:
             sample, acc = [], 0            # ~2 G aligned bases = 10-20 s of one host core
             for r in sorted(regions, key=lambda r: -r.size):
                 if r.size <= 6_000_000 and acc < 2.0e9:
                     sample.append(r); acc += r.aligned
-            t = time_oracle(sample, 1)
+            # the oracle is timed per region; what it returns is then compared with the engine's result for the same region
+            # through the same C-ABI calls the e2e arm makes (host buffers in, host planes out), outside the timed part
+            lib = oracle_lib()
+            peng = Engine(local)
+            t, mismatches = 0.0, []
+            for r in sample:
+                t0 = time.perf_counter()
+                ref = oracle_region(lib, r, None, True)
+                t += time.perf_counter() - t0
+                mismatches += ["%s contig %d %d-%d: %s" % (wl.name, r.ci, r.start, r.stop, m) for m in parity_check(peng, ref, r)]
+                del ref
+            peng.close()
             sb = sum(r.aligned for r in sample)
             cpu = {"value": sb / t, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": "C restatement of the reference path (oracle/pilon_oracle.c), 1 thread like the reference, "
                              "%d regions of %s (%d loci, %d aligned bases), %.1f s" % (
                                  len(sample), wl.name, sum(r.size for r in sample), sb, t)}
+            parity = {"regions": len(sample), "loci": sum(r.size for r in sample), "aligned_bases": sb,
+                      "compared": "every scalar, all 18 per-locus planes, every indel evidence entry; engine through the C ABI "
+                                  "from host buffers vs oracle/pilon_oracle.c on the same regions",
+                      "ok": not mismatches}
+            if mismatches:
+                parity["mismatches"] = mismatches[:10]
         out = {"metric": METRIC, "value": job_aligned / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "int64", "data": "synthetic",
@@ -525,8 +580,11 @@ def run_gpu_arm(args):
                             "algorithmic_bytes_per_launch": sum(r.alg_bytes for r in regions) / len(regions),
                             "algorithmic_bytes_per_base": alg / total_aligned,
                             "pileup_ms_per_step": pileup_ms, "pileup_share_of_sequential_step": pileup_ms / seq_step_ms},
-               "cpu_baseline": cpu, "clocks": clocks}
+               "cpu_baseline": cpu, "parity": parity, "clocks": clocks}
         print(json.dumps(out))
+        if parity is not None and not parity["ok"]:
+            print("PARITY MISMATCH: " + "; ".join(parity["mismatches"]), file=sys.stderr)
+            sys.exit(3)
     if world > 1:
         dist.destroy_process_group()
 

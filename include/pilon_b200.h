@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB_ABI_VERSION 4
+#define PB_ABI_VERSION 5
 
 /* ---- status codes ---------------------------------------------------------------------- */
 #define PB_OK                 0
@@ -207,6 +207,19 @@ typedef struct pb_region_result {
     /* sparse indel evidence; capacities are inputs, counts come back in n_indels/n_indel_bytes */
     pb_indel* indels;        int64_t indels_cap;
     uint8_t*  indel_bytes;   int64_t indel_bytes_cap;
+
+    /* per-BAM deltas, one entry per pb_region_add_batch call in call order: what BamFile.process brackets its read
+     * loop with (BamFile.scala:120-122,142-146).  batch_cap is an input (entries the three arrays can hold; arrays
+     * may be NULL), n_batches comes back.
+     *   batch_read_count[b]  readCount after - before            (:121,143)
+     *   batch_base_count[b]  baseCount after - before, what BamFile.baseCount accumulates for
+     *                        GenomeFile.coverageSummary            (:120,146; GenomeFile.scala:178-187)
+     *   batch_coverage[b]    coverage after - coverage before, the value process returns (:122,142,147)  */
+    int32_t* batch_read_count;
+    int64_t* batch_base_count;
+    int64_t* batch_coverage;
+    int64_t  batch_cap;
+    int64_t  n_batches;
 } pb_region_result;
 
 typedef struct pb_engine pb_engine;

@@ -52,6 +52,8 @@ typedef struct po_region {
     int32_t unknown_ops, dropped_oob;
     int64_t aligned_bases;
     po_event* ev; int64_t n_ev, cap_ev;
+    /* per-BAM deltas taken around the read loop (BamFile.scala:120-122,142-146) */
+    int32_t bam_reads[256]; int64_t bam_bases[256], bam_cov[256]; int n_bams;
 } po_region;
 
 static void* xcalloc(size_t n, size_t s) { void* p = calloc(n ? n : 1, s); if (!p) abort(); return p; }
@@ -275,6 +277,9 @@ static int32_t addRead(po_region* r, const pb_batch* b, int64_t rd, const uint8_
 /* BamFile.process loop (BamFile.scala:126-139) inside GenomeRegion.processBam (GenomeRegion.scala:287-300) */
 int po_region_add_batch(po_region* r, const pb_batch* b, int frag, int long_read, int32_t* insert_sizes_out) {
     if (long_read != 0) return PB_ERR_UNSUPPORTED;
+    const int32_t readsBefore = r->readCount;                                           /* BamFile.scala:120 */
+    const int64_t baseCountBefore = r->baseCount;                                       /* :121 */
+    const int64_t covBeforeBam = roundDivL(r->baseCount, r->size);                      /* :122; PileUpRegion.scala:36 */
     if (frag) for (int64_t i = 0; i < r->size; i++) r->covBefore[i] = wrap32(depthAt(r, i));   /* :290-293 */
     int32_t maxlen = 0;
     for (int64_t rd = 0; rd < b->n_reads; rd++) if (b->read_len[rd] > maxlen) maxlen = b->read_len[rd];
@@ -289,6 +294,12 @@ int po_region_add_batch(po_region* r, const pb_batch* b, int frag, int long_read
     free(bases); free(quals);
     if (frag) for (int64_t i = 0; i < r->size; i++)
         r->fragCov[i] = wrap32((int64_t)r->fragCov[i] + wrap32(depthAt(r, i)) - r->covBefore[i]);   /* :296-298 */
+    if (r->n_bams < 256) {
+        r->bam_reads[r->n_bams] = r->readCount - readsBefore;                           /* :143 */
+        r->bam_bases[r->n_bams] = r->baseCount - baseCountBefore;                       /* :146 */
+        r->bam_cov[r->n_bams] = roundDivL(r->baseCount, r->size) - covBeforeBam;        /* :142 */
+    }
+    r->n_bams++;
     return PB_OK;
 }
 
@@ -487,6 +498,12 @@ int po_region_finish(po_region* r, pb_region_result* res) {
         ni++; nb += g[k].win_len;
     }
     res->n_indels = ni; res->n_indel_bytes = nb;
+    res->n_batches = r->n_bams;
+    for (int b = 0; b < r->n_bams && b < 256 && b < res->batch_cap; b++) {
+        if (res->batch_read_count) res->batch_read_count[b] = r->bam_reads[b];
+        if (res->batch_base_count) res->batch_base_count[b] = r->bam_bases[b];
+        if (res->batch_coverage) res->batch_coverage[b] = r->bam_cov[b];
+    }
     free(g); free(flags); free(cov); free(wq); free(wmq);
     return PB_OK;
 }

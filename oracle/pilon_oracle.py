@@ -614,6 +614,7 @@ class GenomeRegionHot:
         self.changeMap: Dict[int, Tuple[str, PileUp]] = {}       # :82
         self.pileUpRegion: Optional[PileUpRegion] = None
         self.insert_sizes: List[Tuple[int, bool]] = []           # what BamFile.addInsert receives
+        self.per_bam: List[Tuple[int, int, int]] = []            # (nReads, baseCount delta, meanCoverage) per processBam
         self.log: List[str] = []
 
     def refBase(self, locus: int) -> str:                        # :783-787 (upper-cased)
@@ -627,6 +628,9 @@ class GenomeRegionHot:
         """GenomeRegion.scala:287-300 around BamFile.process (BamFile.scala:108-148).
         `reads` is what queryOverlapping(+-10 kb) returned and validateRead kept."""
         pur = self.pileUpRegion
+        readsBefore = pur.readCount                              # BamFile.scala:120-122
+        baseCountBefore = pur.baseCount
+        covBeforeBam = pur.coverage
         covBefore = [0] * self.size
         if bamType != "jumps":
             for i in range(self.size):
@@ -637,6 +641,10 @@ class GenomeRegionHot:
         if bamType != "jumps":
             for i in range(self.size):
                 self.fragCoverage[i] = i32(self.fragCoverage[i] + i32(pur.pileups[i].depth) - covBefore[i])
+        meanCoverage = pur.coverage - covBeforeBam               # BamFile.scala:142
+        nReads = pur.readCount - readsBefore                     # :143
+        self.per_bam.append((nReads, pur.baseCount - baseCountBefore, meanCoverage))   # :146 feeds BamFile.baseCount
+        return meanCoverage                                      # :147
 
     def postProcess(self):                                       # :214-272
         cfg = self.cfg

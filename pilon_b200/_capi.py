@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libpilonb200.so")
 
 PB_OK = 0
+ABI_VERSION = 5
 PB_ERR_INVALID, PB_ERR_CUDA, PB_ERR_UNSORTED, PB_ERR_UNSUPPORTED, PB_ERR_OOM, PB_ERR_HASH = -1, -2, -3, -4, -5, -6
 
 PB_F_PAIRED, PB_F_PROPER, PB_F_MATE_SAME_REF, PB_F_HAS_QUALS, PB_F_UNMAPPED, PB_F_REVERSE = 1, 2, 4, 8, 16, 32
@@ -58,7 +59,9 @@ class pb_region_result(C.Structure):
                 ("weighted_qual", C.c_void_p), ("weighted_mq", C.c_void_p), ("flags", C.c_void_p),
                 ("call", C.c_void_p),
                 ("indels", C.c_void_p), ("indels_cap", C.c_int64),
-                ("indel_bytes", C.c_void_p), ("indel_bytes_cap", C.c_int64)]
+                ("indel_bytes", C.c_void_p), ("indel_bytes_cap", C.c_int64),
+                ("batch_read_count", C.c_void_p), ("batch_base_count", C.c_void_p), ("batch_coverage", C.c_void_p),
+                ("batch_cap", C.c_int64), ("n_batches", C.c_int64)]
 
 
 # name -> numpy dtype, elements per locus; order follows the struct
@@ -113,7 +116,7 @@ def load_library() -> C.CDLL:
                  "pb_packer_destroy", "pb_packer_reset", "pb_packer_add", "pb_packer_add_many",
                  "pb_packer_view", "pb_base_delta_encode"):
         getattr(lib, name).restype = C.c_int
-    if lib.pb_abi_version() != 4:
+    if lib.pb_abi_version() != ABI_VERSION:
         raise RuntimeError("libpilonb200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -72,7 +72,8 @@ struct DevBatch {
 // k_prep spreads its per-warp partial sums over SC_SLOTS slots (same-address L2 atomics serialise);
 // k_scalars folds them into the Scalars block.
 static constexpr int SC_SLOTS = 64;
-struct ScalarSlot { unsigned long long base_count, aligned_bases; int read_count, unknown_ops, dropped_oob; unsigned n_work; int fwd[8], back[8]; };
+static constexpr int BC_SPREAD = 8;      // partial sums per batch of the region baseCount (RegionDev.batch_bc)
+struct ScalarSlot { unsigned long long aligned_bases; int read_count, unknown_ops, dropped_oob; unsigned n_work; int fwd[8], back[8]; };
 
 struct Scalars {
     unsigned long long base_count;      // PileUpRegion.baseCount
@@ -118,6 +119,7 @@ struct RegionDev {
                                         // a single counter is a hot address every warp with an indel would wait on
     int4* cand;  uint32_t cand_cap;     // unordered pass-1 DEL candidates: (locus index, deletions, length, -)
     ScalarSlot* slots;                  // [SC_SLOTS] k_prep partial sums
+    unsigned long long* batch_bc;       // [batches * BC_SPREAD] PileUpRegion.baseCount contributed by each batch (BamFile.scala:120,146)
     int32_t exp_flags;                  // PB_EXP timing experiments (results invalid): 1 skip epilogue, 2 skip compute, 4 skip staging copies
     // outputs (final state)
     int32_t* o_cnt;   // [size*4]

@@ -31,9 +31,11 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 namespace {
 
 // device/pinned scalar block: Scalars followed by the per-batch reach pairs (k_prep's atomicMax targets)
-constexpr size_t SC_BYTES = 8192;
-constexpr size_t SC_REACH_OFF = sizeof(Scalars) + sizeof(ScalarSlot) * SC_SLOTS;
-constexpr size_t MAX_BATCHES = (SC_BYTES - SC_REACH_OFF) / 8;
+// then the per-batch base counts (BC_SPREAD partial sums per batch: same-address L2 atomics serialise)
+constexpr size_t MAX_BATCHES = 256;
+constexpr size_t SC_REACH_OFF = (sizeof(Scalars) + sizeof(ScalarSlot) * SC_SLOTS + 15) & ~(size_t)15;
+constexpr size_t SC_BC_OFF = SC_REACH_OFF + MAX_BATCHES * 8;
+constexpr size_t SC_BYTES = SC_BC_OFF + MAX_BATCHES * BC_SPREAD * 8;
 
 // grow-only device buffer, zero-filled on growth when asked (the "rare" planes rely on it)
 struct DBuf {
@@ -204,6 +206,7 @@ extern "C" int pb_region_begin(pb_engine* e, const uint8_t* contig, int64_t cont
     CK(e->block_sums.ensure((size_t)nblocks * 8, false, s));
     R.sc = e->scalars.as<Scalars>();
     R.slots = reinterpret_cast<ScalarSlot*>(static_cast<uint8_t*>(e->scalars.p) + sizeof(Scalars));
+    R.batch_bc = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(e->scalars.p) + SC_BC_OFF);
     R.rare = e->rare.as<Rare>();
     R.r_gins = e->gplane[0].as<uint32_t>(); R.r_gdel = e->gplane[1].as<uint32_t>();
     R.rare_bits = e->rare_bits.as<uint32_t>();
@@ -551,7 +554,7 @@ static int compute(pb_engine* e, bool time_pileup, bool full_cap = false) {
 
     if (const char* xf = getenv("PB_EXP")) R.exp_flags = atoi(xf);     // knock-out experiments (tools/knockout_timing.py)
     int32_t* reach_base = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(e->scalars.p) + SC_REACH_OFF);
-    if (nb == 0) { k_fold<<<1, 32, 0, s>>>(R, reach_base, 0, 1); e->launches++; }
+    if (nb == 0) { k_fold<<<1, 32, 0, s>>>(R, reach_base, 0, 1, 0); e->launches++; }
     for (int i0 = 0; i0 < nb; i0 += 8) {     // k_prep folds its block partials into slots that carry 8 batches' reach
         const int i1 = std::min(nb, i0 + 8);
         for (int i = i0; i < i1; i++) {
@@ -562,7 +565,7 @@ static int compute(pb_engine* e, bool time_pileup, bool full_cap = false) {
             e->launches += 1;
         }
         if (i1 == nb) { k_indel<<<148 * 4, 128, 0, s>>>(R, dB); e->launches++; }     // queued I / D ops of every batch
-        k_fold<<<1, 32, 0, s>>>(R, reach_base + 2 * i0, i1 - i0, i1 == nb); e->launches++;
+        k_fold<<<1, 32, 0, s>>>(R, reach_base + 2 * i0, i1 - i0, i1 == nb, nb); e->launches++;
     }
     const int nblocks = (int)((R.size + SCAN_TILE - 1) / SCAN_TILE);
     k_scan1<<<nblocks, SCAN_THREADS, 0, s>>>(R, e->block_sums.as<uint2>());
@@ -762,6 +765,9 @@ extern "C" int pb_region_finish(pb_engine* e, pb_region_result* res, int32_t* co
         e->ph_regions++;
     }
     CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
+    const size_t nbat = e->batches.size();
+    unsigned long long* h_bc = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(e->h_sc) + SC_BC_OFF);
+    if (nbat) CK(cudaMemcpyAsync(h_bc, R.batch_bc, nbat * BC_SPREAD * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (e->h_sc->error) return fail(PB_ERR_CUDA, "internal error flag set by a kernel");
     const size_t nbytes = (size_t)e->h_sc->str_bytes;
@@ -772,6 +778,19 @@ extern "C" int pb_region_finish(pb_engine* e, pb_region_result* res, int32_t* co
     res->size = R.size; res->base_count = (int64_t)sc.base_count; res->coverage = sc.coverage;
     res->aligned_bases = (int64_t)sc.aligned_bases; res->read_count = sc.read_count; res->min_depth = sc.min_depth;
     res->unknown_ops = sc.unknown_ops; res->dropped_oob = sc.dropped_oob;
+    // per-BAM deltas around each batch, as BamFile.process takes them (BamFile.scala:120-122,142-146)
+    res->n_batches = (int64_t)nbat;
+    {
+        int64_t cum = 0;
+        for (size_t b = 0; b < nbat && (int64_t)b < res->batch_cap; b++) {
+            int64_t bc = 0;
+            for (int j = 0; j < BC_SPREAD; j++) bc += (int64_t)h_bc[b * BC_SPREAD + j];
+            if (res->batch_read_count) res->batch_read_count[b] = (int32_t)e->batches[b].d.n_reads;     // readCount += 1 per addRead (:218)
+            if (res->batch_base_count) res->batch_base_count[b] = bc;
+            if (res->batch_coverage) res->batch_coverage[b] = roundDivL(cum + bc, R.size) - roundDivL(cum, R.size);   // PileUpRegion.scala:36
+            cum += bc;
+        }
+    }
     // indel evidence, ordered by (locus, kind)
     std::sort(groups.begin(), groups.end(), [](const Group& a, const Group& b) { return a.loc < b.loc || (a.loc == b.loc && a.kind < b.kind); });
     int64_t ni = 0, nbo = 0;

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
     }
     if ((threadIdx.x & 31) == 0) {
         ScalarSlot* sl = &R.slots[(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (SC_SLOTS - 1)];
-        if (bc) atomicAdd(&sl->base_count, bc);
+        if (bc) atomicAdd(&R.batch_bc[batch_id * BC_SPREAD + ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (BC_SPREAD - 1))], bc);
         if (aligned) atomicAdd(&sl->aligned_bases, aligned);
         if (rc) atomicAdd(&sl->read_count, rc);
         if (unk) atomicAdd(&sl->unknown_ops, unk);
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(128) k_indel(RegionDev R, const DevBatch* __re
     __syncthreads();
     const uint32_t n_work = pre[SC_SLOTS];
     if (blockIdx.x == 0 && threadIdx.x == 0) R.sc->n_events = n_work;     // event slots in use (one per work item, some stay empty)
-    unsigned long long bc = 0; int drop = 0;
+    int drop = 0;
     for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n_work; wi += gridDim.x * blockDim.x) {
         if (wi < R.ev_cap) R.ev_key[wi].lk = ~0ull;                      // "no event" until this item records one
         uint32_t q = 0;
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(128) k_indel(RegionDev R, const DevBatch* __re
                         if (b > a) {
                             sg.loc0 = (int32_t)(a + (locus + len - readOffset) - R.start); sg.len = (int32_t)(b - a);
                             sg.src = seq0 + (uint32_t)a; sg.w = segw | SEG_VALID;
-                            bc += (unsigned long long)sg.len;
+                            atomicAdd(&R.batch_bc[batch_id * BC_SPREAD + (wi & (BC_SPREAD - 1))], (unsigned long long)sg.len);   // :43 (rare)
                         }
                         const int64_t i = dloc - R.start;
                         uint8_t b0, q0; read_base(B, seq0 + (uint32_t)readOffset, &b0, &q0);
@@ -337,21 +337,21 @@ __global__ void __launch_bounds__(128) k_indel(RegionDev R, const DevBatch* __re
         }
     }
     // few threads: plain atomics into the slots that the last k_fold folds
-    if (bc) atomicAdd(&R.slots[threadIdx.x & (SC_SLOTS - 1)].base_count, bc);
     if (drop) atomicAdd(&R.slots[threadIdx.x & (SC_SLOTS - 1)].dropped_oob, drop);
 }
 
 // region coverage and minDepth (PileUpRegion.scala:36; GenomeRegion.scala:221-224)
 // launched once per group of <= 8 batches with 32 threads: folds the slots, then (last group only)
 // coverage and minDepth
-__global__ void k_fold(RegionDev R, int32_t* reach0, int nb, int last) {
+__global__ void k_fold(RegionDev R, int32_t* reach0, int nb, int last, int nb_total) {
     const int lane = threadIdx.x;
     unsigned long long bc = 0, al = 0; int rc = 0, unk = 0, drop = 0; int fw[8], bk[8];
+    if (last) for (int i = lane; i < nb_total * BC_SPREAD; i += 32) bc += R.batch_bc[i];      // every batch's k_prep and k_indel have run
 #pragma unroll
     for (int j = 0; j < 8; j++) { fw[j] = 0; bk[j] = 0; }
     for (int i = lane; i < SC_SLOTS; i += 32) {
         ScalarSlot& sl = R.slots[i];
-        bc += sl.base_count; al += sl.aligned_bases; rc += sl.read_count; unk += sl.unknown_ops; drop += sl.dropped_oob;
+        al += sl.aligned_bases; rc += sl.read_count; unk += sl.unknown_ops; drop += sl.dropped_oob;
 #pragma unroll
         for (int j = 0; j < 8; j++) { fw[j] = max(fw[j], sl.fwd[j]); bk[j] = max(bk[j], sl.back[j]); }
         ScalarSlot z = {}; z.n_work = sl.n_work; sl = z;     // the I/D sub-queue counters live until k_indel has run

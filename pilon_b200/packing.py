@@ -235,7 +235,7 @@ class ResultBuffers:
     """Caller-owned host arrays behind a `pb_region_result`."""
 
     def __init__(self, size: int, planes: Optional[Sequence[str]] = None, indels_cap: int = 0,
-                 indel_bytes_cap: int = 0, pinned: bool = False):
+                 indel_bytes_cap: int = 0, pinned: bool = False, batch_cap: int = 256):
         self.size = size
         self.arrays = {}
         self.c = capi.pb_region_result()
@@ -254,11 +254,24 @@ class ResultBuffers:
             self.indel_bytes = np.zeros(indel_bytes_cap, np.uint8)
             self.c.indel_bytes = self.indel_bytes.ctypes.data
             self.c.indel_bytes_cap = indel_bytes_cap
+        # per-BAM deltas (BamFile.scala:120-122,142-146)
+        self.batch_read_count = np.zeros(batch_cap, np.int32)
+        self.batch_base_count = np.zeros(batch_cap, np.int64)
+        self.batch_coverage = np.zeros(batch_cap, np.int64)
+        self.c.batch_read_count = self.batch_read_count.ctypes.data
+        self.c.batch_base_count = self.batch_base_count.ctypes.data
+        self.c.batch_coverage = self.batch_coverage.ctypes.data
+        self.c.batch_cap = batch_cap
 
     def __getitem__(self, name: str) -> np.ndarray:
         a = self.arrays[name]
         per = {p[0]: p[2] for p in capi.RESULT_PLANES}[name]
         return a.reshape(self.size, per) if per > 1 else a
+
+    def per_bam(self):
+        """[(nReads, baseCount delta, meanCoverage)] per pb_region_add_batch call (BamFile.scala:142-147)."""
+        n = min(int(self.c.n_batches), int(self.c.batch_cap))
+        return [(int(self.batch_read_count[b]), int(self.batch_base_count[b]), int(self.batch_coverage[b])) for b in range(n)]
 
     def indels(self):
         out = []

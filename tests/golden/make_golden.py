@@ -61,7 +61,8 @@ def main():
                     scalars={k: (float(v) if isinstance(v, float) else int(v)) for k, v in py["scalars"].items()},
                     indel_list_len={"%d,%d" % k: int(v) for k, v in py["indel_list_len"].items()},
                     indel_strings={"%d,%d" % k: bytes(v).hex() for k, v in py["indel_strings"].items()},
-                    insert_sizes=[int(v) for v in py["insert_sizes"]])
+                    insert_sizes=[int(v) for v in py["insert_sizes"]],
+                    per_bam=[[int(x) for x in t] for t in py["per_bam"]])
         out["meta"] = np.frombuffer(json.dumps(meta, sort_keys=True).encode(), np.uint8)
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **out)

@@ -127,6 +127,7 @@ def run_py_oracle(contig: bytes, start: int, stop: int, batches: Sequence[Tuple[
     out["scalars"] = dict(base_count=pur.baseCount, read_count=pur.readCount, coverage=pur.coverage,
                           min_depth=gr.minDepth, unknown_ops=pur.unknown_ops, dropped_oob=pur.dropped_oob)
     out["insert_sizes"] = [x[0] for x in gr.insert_sizes]
+    out["per_bam"] = list(gr.per_bam)
     return out
 
 
@@ -138,6 +139,7 @@ def assert_results_equal(a: ResultBuffers, b: ResultBuffers, what: str = ""):
     for f in ("size", "base_count", "coverage", "aligned_bases", "read_count", "min_depth", "unknown_ops",
               "dropped_oob", "n_indels"):
         assert getattr(a.c, f) == getattr(b.c, f), "%s scalar %s: %r != %r" % (what, f, getattr(a.c, f), getattr(b.c, f))
+    assert a.c.n_batches == b.c.n_batches and a.per_bam() == b.per_bam(), "%s per-BAM deltas: %r != %r" % (what, a.per_bam(), b.per_bam())
     for name in PLANE_NAMES:
         if name in a.arrays and name in b.arrays:
             x, y = a[name], b[name]
@@ -177,6 +179,7 @@ def assert_matches_py(res: ResultBuffers, inserts: List[np.ndarray], py: Dict[st
         assert got[key]["string"] == s, (key, got[key], s)
     flat = [int(v) for arr in inserts for v in arr]
     assert flat == py["insert_sizes"]
+    assert res.per_bam() == py["per_bam"], "%s per-BAM deltas: %r != %r" % (what, res.per_bam(), py["per_bam"])
 
 
 # ---------------------------------------------------------------------------------------------

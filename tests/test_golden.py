@@ -26,6 +26,7 @@ def load(path):
     py["indel_list_len"] = {key(k): v for k, v in meta["indel_list_len"].items()}
     py["indel_strings"] = {key(k): bytes.fromhex(v) for k, v in meta["indel_strings"].items()}
     py["insert_sizes"] = meta["insert_sizes"]
+    py["per_bam"] = [tuple(t) for t in meta["per_bam"]]
     return bytes(z["contig"]), meta["start"], meta["stop"], batches, po.Config(**meta["cfg"]), py
 
 

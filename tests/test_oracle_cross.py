@@ -44,3 +44,19 @@ def test_cases_exercise_the_interesting_paths():
         seen["dropped"] += res.c.dropped_oob
         seen["unknown"] += res.c.unknown_ops
     assert all(v > 0 for v in seen.values()), seen
+
+
+def test_c_oracle_matches_python_oracle_on_a_wide_region():
+    """120 k loci, ~25 k paired reads, planted SNP / AMB / INS / DEL sites and the deletion spill: the C restatement
+    (whose BaseCall / hetIndelCall code is close to the device code's) is cross-examined by the literal transliteration
+    well beyond the toy sizes of the random cases."""
+    contig, start, stop, reads = H.clean_case(5, n=130_000, start=5_001, stop=125_000, depth=10, n_sites=150)
+    groups = [([r for i, r in enumerate(reads) if i % 3 != 0], True), ([r for i, r in enumerate(reads) if i % 3 == 0], False)]
+    py = H.run_py_oracle(contig, start, stop, groups)
+    res, ins = H.run_c_oracle(contig, start, stop, [(pack_records(g), f) for g, f in groups], indels_cap=1 << 18, bytes_cap=1 << 22)
+    H.assert_matches_py(res, ins, py, "120 k loci")
+    fl = res["flags"]
+    kind = (fl >> 4) & 3
+    for k in (0, 1, 2):
+        assert (((fl & 2) != 0) & (kind == k)).any()
+    assert (fl & 8).any() and (fl & 4).any()
