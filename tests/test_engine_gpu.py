@@ -106,7 +106,9 @@ def test_empty_region_and_zero_reads(engine):
     H.assert_results_equal(res, ref)
     assert res.c.read_count == 0 and not res["flags"].any()
     res2, _ = engine.run_region(contig, 10, 400, [])
-    H.assert_results_equal(res2, ref)
+    ref2, _ = H.run_c_oracle(contig, 10, 400, [])
+    H.assert_results_equal(res2, ref2)
+    assert res.per_bam() == [(0, 0, 0)] and res2.per_bam() == []
 
 
 def test_unsorted_batch_is_rejected(engine):

@@ -23,7 +23,7 @@ class kernel_choice:
     """PB_PILEUP is read by pb_create: engines made inside the block use the forced kernel (None = the engine's choice)."""
 
     def __init__(self, which):
-        self.val = {None: None, "auto": None, "gather": "5", "scatter": "7"}[which]
+        self.val = {None: None, "auto": None, "gather": "5", "scatter": "9"}[which]
 
     def __enter__(self):
         self.old = os.environ.get("PB_PILEUP")
