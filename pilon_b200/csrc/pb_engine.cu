@@ -600,7 +600,7 @@ static int compute(pb_engine* e, bool time_pileup, bool full_cap = false) {
     if (pv == 0) {
         const int64_t tiles = (R.size + P7_TILE - 1) / P7_TILE;
         const int64_t depth = R.size > 0 ? (int64_t)(total_seq / (size_t)R.size) : 0;      // stored bases per locus: >= depth
-        pv = (tiles >= 256 && depth <= 1000) ? 9 : 5;
+        pv = (tiles >= 256 && depth <= 1000) ? 7 : 5;
     }
     if ((pv == 7 || pv == 9) && nb > PB_MAXB) pv = 5;   // the scatter kernel keeps its per-batch cursors in shared memory: <= PB_MAXB batches
     PileBatches PBt; memset(&PBt, 0, sizeof(PBt)); PBt.n = nb;

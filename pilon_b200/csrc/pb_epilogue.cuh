@@ -52,8 +52,41 @@ __device__ __forceinline__ void finish_locus(const RegionDev& R, int64_t w, int 
     const int64_t qtot = (int64_t)(q[0] + q[1] + q[2] + q[3]);
     uint64_t call;
     int32_t ilen = 0;
+    // every quality sum below 2^30 (any ordinary depth: 2^30 / (127 * 256) = 33 k bases): the whole BaseCall in 32-bit arithmetic
+    const bool small = ((uint64_t)qtot >> 30) == 0;
     if (R.exp_flags & 16) { call = (uint64_t)(c[0] + mqSum); }
-    else if (r_ins <= 2 && r_del <= 2) {
+    else if (r_ins <= 2 && r_del <= 2 && small) {
+        // no indel can be called (PileUp.scala:183-191) and nothing needs 64 bits
+        const bool useq = qSum > 0;                                                         // :135
+        const uint32_t q0 = (uint32_t)q[0], q1 = (uint32_t)q[1], q2 = (uint32_t)q[2], q3 = (uint32_t)q[3];
+        const uint32_t s0 = useq ? q0 : c[0], s1 = useq ? q1 : c[1], s2 = useq ? q2 : c[2], s3 = useq ? q3 : c[3];
+        // BaseSum.order (BaseSum.scala:57-60): stable descending, ties keep A < C < G < T
+        int o0 = 0; uint32_t m0 = s0;
+        if (s1 > m0) { m0 = s1; o0 = 1; }
+        if (s2 > m0) { m0 = s2; o0 = 2; }
+        if (s3 > m0) { m0 = s3; o0 = 3; }
+        int o1 = o0 == 0 ? 1 : 0; uint32_t m1 = o0 == 0 ? s1 : s0;
+        if (o0 != 1 && o1 != 1 && s1 > m1) { m1 = s1; o1 = 1; }
+        if (o0 != 2 && s2 > m1) { m1 = s2; o1 = 2; }
+        if (o0 != 3 && s3 > m1) { m1 = s3; o1 = 3; }
+        const int32_t baseSum = (int32_t)(o0 == 0 ? q0 : o0 == 1 ? q1 : o0 == 2 ? q2 : q3);  // :139
+        const int32_t altSum = (int32_t)(o1 == 0 ? q0 : o1 == 1 ? q1 : o1 == 2 ? q2 : q3);   // :141
+        const int32_t total = (int32_t)qtot;
+        const int32_t homoScore = baseSum - (total - baseSum);                              // :144
+        const int32_t half = total >> 1;                                                    // :145 (total >= 0)
+        const int32_t hetero = total - abs(half - baseSum) - abs(half - altSum);            // :146
+        const int homo = homoScore >= hetero;                                               // :147
+        const uint32_t diff = (uint32_t)abs(homoScore - hetero);                            // |.| <= 2^31
+        uint64_t score = 0;
+        if (mqSum > 0) {                                                                    // :148
+            const uint64_t prod = (uint64_t)diff * (uint64_t)(uint32_t)n;
+            score = (prod >> 32) == 0 ? (uint64_t)((uint32_t)prod / (uint32_t)mqSum) : prod / (uint64_t)mqSum;
+        }
+        const int base = n > 0 ? o0 : 4;
+        const int hi = n > 0 && score >= 10ull * (uint64_t)n;                               // :166-167: score / n >= 10
+        call = (uint64_t)base | ((uint64_t)o1 << 3) | ((uint64_t)homo << 5) | (1ull << 8) |
+               ((uint64_t)(base != 4) << 9) | ((uint64_t)hi << 10) | (score << 16);
+    } else if (r_ins <= 2 && r_del <= 2) {
         // no indel can be called (PileUp.scala:183-191): the plain-base BaseCall with select-based ordering
         const bool useq = qSum > 0;                                                         // :135
         const int64_t s0 = useq ? (int64_t)q[0] : c[0], s1 = useq ? (int64_t)q[1] : c[1];
@@ -98,8 +131,13 @@ __device__ __forceinline__ void finish_locus(const RegionDev& R, int64_t w, int 
     R.o_clips[loc] = r_clips;
     R.o_cov[loc] = wrap32(depth);                                                           // GenomeRegion.scala:247
     R.o_frag[loc] = (int32_t)(fragN + (uint32_t)r_delfrag);                                 // GenomeRegion.scala:296-298
-    R.o_wq[loc] = (int8_t)(uint8_t)(mqSum > 0 ? udiv_fast((uint64_t)qtot + (uint64_t)(mqSum / 2), (uint64_t)mqSum) : 0);   // PileUp.scala:60-62
-    R.o_wmq[loc] = (int8_t)(uint8_t)(qSum > 0 ? udiv_fast((uint64_t)qtot + (uint64_t)(qSum / 2), (uint64_t)qSum) : 0);     // PileUp.scala:56-58
+    if (small) {                                                                            // numerators below 2^31
+        R.o_wq[loc] = (int8_t)(uint8_t)(mqSum > 0 ? ((uint32_t)qtot + (uint32_t)(mqSum / 2)) / (uint32_t)mqSum : 0u);      // PileUp.scala:60-62
+        R.o_wmq[loc] = (int8_t)(uint8_t)(qSum > 0 ? ((uint32_t)qtot + (uint32_t)(qSum / 2)) / (uint32_t)qSum : 0u);        // PileUp.scala:56-58
+    } else {
+        R.o_wq[loc] = (int8_t)(uint8_t)(mqSum > 0 ? udiv_fast((uint64_t)qtot + (uint64_t)(mqSum / 2), (uint64_t)mqSum) : 0);
+        R.o_wmq[loc] = (int8_t)(uint8_t)(qSum > 0 ? udiv_fast((uint64_t)qtot + (uint64_t)(qSum / 2), (uint64_t)qSum) : 0);
+    }
     R.o_flags[loc] = (uint8_t)fl;
     R.o_call[loc] = call;
     if ((fl & PB_FL_CHANGED) && ((fl >> PB_FL_KIND_SHIFT) & 3) == PB_KIND_DEL) {
