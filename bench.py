@@ -317,12 +317,13 @@ def run_gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    placement = bind_rank(local, world) if world > 1 else None      # each rank on the cores next to its GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    ncpu = os.cpu_count() or 1
-    wl, regions = build_workload(args.workload, args.scale, rank, max(1, ncpu // max(world, 1)))
+    ncpu = len(os.sched_getaffinity(0))
+    wl, regions = build_workload(args.workload, args.scale, rank, ncpu)
     total_aligned = sum(r.aligned for r in regions)
     total_loci = sum(r.size for r in regions)
 
@@ -580,11 +581,253 @@ def run_gpu_arm(args):
                             "algorithmic_bytes_per_launch": sum(r.alg_bytes for r in regions) / len(regions),
                             "algorithmic_bytes_per_base": alg / total_aligned,
                             "pileup_ms_per_step": pileup_ms, "pileup_share_of_sequential_step": pileup_ms / seq_step_ms},
-               "cpu_baseline": cpu, "parity": parity, "clocks": clocks}
+               "cpu_baseline": cpu, "parity": parity, "host_placement": placement, "clocks": clocks}
         print(json.dumps(out))
         if parity is not None and not parity["ok"]:
             print("PARITY MISMATCH: " + "; ".join(parity["mismatches"]), file=sys.stderr)
             sys.exit(3)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+
+# ---------------------------------------------------------------------------------------------
+# host placement: one rank per GPU, each on the cores (and memory) next to its GPU
+# ---------------------------------------------------------------------------------------------
+def _parse_cpulist(txt):
+    out = []
+    for part in txt.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        out += list(range(int(a), int(b or a) + 1))
+    return out
+
+
+def gpu_local_cpus(index):
+    """Cores the kernel reports as local to GPU `index` (sysfs local_cpulist of its PCI function)."""
+    try:
+        bus = subprocess.check_output(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                      text=True, stderr=subprocess.DEVNULL).strip().lower()
+        bus = bus[-12:] if len(bus) > 12 else bus                     # 00000000:1B:00.0 -> 0000:1b:00.0
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bus) as f:
+            cpus = _parse_cpulist(f.read())
+        return cpus or None
+    except Exception:
+        return None
+
+
+def bind_rank(local, world):
+    """Pin this rank (and the threads it starts later) to its share of the cores local to its GPU.  Returns a
+    description for the JSON line.  Ranks whose GPUs report the same core list split it evenly."""
+    allowed = sorted(os.sched_getaffinity(0))
+    lists = [gpu_local_cpus(i) for i in range(world)]
+    mine = lists[local] if local < len(lists) else None
+    if not mine:
+        mine, peers, k = allowed, world, local
+    else:
+        same = [i for i in range(world) if lists[i] == mine]
+        peers, k = len(same), same.index(local)
+    mine = [c for c in mine if c in allowed] or allowed
+    share = mine[k * len(mine) // peers:(k + 1) * len(mine) // peers] or mine
+    try:
+        os.sched_setaffinity(0, share)
+    except Exception:
+        share = allowed
+    os.environ["OMP_NUM_THREADS"] = str(max(1, len(share)))
+    return {"cores": len(share), "first_core": share[0], "gpu_local_cores": len(mine), "ranks_sharing_them": peers}
+
+
+# ---------------------------------------------------------------------------------------------
+# sharded arm (BASELINE config 4): ONE genome, its chunks distributed over the ranks, streamed in waves
+# ---------------------------------------------------------------------------------------------
+class StreamRegion:
+    """One chunk generated on its own: the reads of its +-10 kb window and the reference window the engine uploads.
+    Nothing of the genome outside the window is ever held (GenomeFile.scala:67-74 chunking, BamFile.scala:118-119)."""
+
+    def __init__(self, wl, index, chunk):
+        ci, a, b = chunk
+        self.index, self.ci, self.start, self.stop = index, ci, a, b
+        self.size = b + 1 - a
+        n = wl.contig_lens[ci]
+        self.contig_len = n
+        self.lo, self.hi = max(1, a - 16384), min(n, b + 16384)          # PB_REF_HALO on either side
+        self.window = wl.contig_bases(ci, self.lo, self.hi)
+        self.batches = wl.region_batches(ci, a, b)
+        self.aligned = sum(x.aligned_bases for x in self.batches)
+        self.n_reads = sum(x.n_reads for x in self.batches)
+        self.n_cigar = sum(x.c.n_cigar for x in self.batches)
+
+    def begin(self, eng):
+        from pilon_b200 import _capi as capi
+        # the engine reads contig[start - 16384 - 1 .. stop + 16384 - 1] only: hand it the window under the address
+        # the whole contig would have had
+        capi.check(eng.lib.pb_region_begin(eng._h, self.window.ctypes.data - (self.lo - 1), self.contig_len, self.start, self.stop))
+        eng._keep = [self.window]
+
+
+def plane_digest(res, planes):
+    """Order-sensitive 64-bit digest of a region's result planes and scalars (cheap: two reductions per plane).
+    The buffers may be larger than the region: only the first res.c.size loci are read."""
+    from pilon_b200 import _capi as capi
+    size = int(res.c.size)
+    per = {p[0]: p[2] for p in capi.RESULT_PLANES}
+    acc = [size, int(res.c.base_count), int(res.c.read_count), int(res.c.min_depth), int(res.c.n_indels)]
+    w = (np.arange(size, dtype=np.uint64) % np.uint64(65521)) + np.uint64(1)
+    for name in planes:
+        x = res.arrays[name][:size * per[name]].astype(np.uint64)
+        if per[name] > 1:
+            x = x.reshape(size, per[name]).sum(axis=1, dtype=np.uint64)
+        acc.append(int(x.sum(dtype=np.uint64)))
+        acc.append(int((x * w).sum(dtype=np.uint64)))
+    return acc
+
+
+def run_sharded_arm(args):
+    import zlib
+    import torch
+    import torch.distributed as dist
+    from pilon_b200 import build as pbuild
+    pbuild.build()
+    from pilon_b200 import sharding, synth
+    from pilon_b200.engine import Engine
+    from pilon_b200.packing import ResultBuffers
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    placement = bind_rank(local, world)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    wl = synth.workload(args.workload, args.scale)
+    chunks = wl.regions()
+    depth = sum(l.depth for l in wl.libraries)
+    mine = sharding.assign(chunks, world, [depth] * len(chunks))[rank]
+    from pilon_b200 import _capi as capi
+    planes = FIX_PLANES if args.planes == "fix" else [p[0] for p in capi.RESULT_PLANES]
+    max_size = max(b + 1 - a for _, a, b in chunks)
+    n_workers = args.e2e_workers
+    workers = [(Engine(local), ResultBuffers(max_size, planes, indels_cap=1 << 20, indel_bytes_cap=1 << 23, pinned=True))
+               for _ in range(n_workers)]
+    rt = torch.cuda.cudart()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    totals = dict(aligned=0, loci=0, reads=0, h2d=0, d2h=0, launches=0)
+    t_e2e = t_dev = t_pile = 0.0
+    digests = {}
+    per_locus = sum(np.dtype(dt).itemsize * per for name, dt, per in capi.RESULT_PLANES if name in planes)
+    wave_n = max(1, args.wave)
+    warm = True
+    for w0 in range(0, len(mine), wave_n):
+        regs = [StreamRegion(wl, i, chunks[i]) for i in mine[w0:w0 + wave_n]]       # generated now, dropped after the wave
+        pinned = []
+        for r in regs:
+            for b in r.batches:
+                totals["h2d"] += pin_batch(torch, b.c)
+                pinned.append(b.c)
+            totals["h2d"] += r.hi - r.lo + 1
+        # ---- end to end: host buffers -> C ABI -> pinned host planes, `n_workers` chunks in flight ----
+        def e2e_pass(keep_digests):
+            order = list(range(len(regs)))
+            lock = threading.Lock()
+
+            def work(slot):
+                eng, res = workers[slot]
+                while True:
+                    with lock:
+                        k = order.pop(0) if order else None
+                    if k is None:
+                        return
+                    r = regs[k]
+                    r.begin(eng)
+                    for b in r.batches:
+                        eng.add_batch(b, b.frag)
+                    eng.finish(res)
+                    assert int(res.c.aligned_bases) == r.aligned
+                    if keep_digests:
+                        digests[r.index] = plane_digest(res, planes)
+            ts = [threading.Thread(target=work, args=(s,)) for s in range(n_workers)]
+            [t.start() for t in ts]
+            [t.join() for t in ts]
+        if warm:                                   # first wave of the run: clocks, allocator pools, page faults
+            e2e_pass(False)
+            warm = False
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_pass(False)
+        torch.cuda.synchronize()
+        t_e2e += time.perf_counter() - t0
+        e2e_pass(True)                             # untimed: the digests of this wave's results
+        # ---- HBM-resident: batches uploaded (untimed), the pass timed with CUDA events on the engine's stream ----
+        eng = workers[0][0]
+        for r in regs:
+            r.begin(eng)
+            keep = []
+            for b in r.batches:
+                d, k = device_batch(torch, b.c, dev)
+                keep.append(k)
+                eng.add_batch(d, b.frag)
+            eng.compute_timed(1)                                   # sizes every buffer
+            a, p, n = eng.compute_timed(args.steps)
+            t_dev += a / args.steps * 1e-3
+            t_pile += p / args.steps * 1e-3
+            totals["launches"] += n // args.steps
+            res = workers[0][1]
+            eng.finish(res)
+            assert plane_digest(res, planes) == digests[r.index], "device-resident and host-fed results differ for chunk %d" % r.index
+            del keep
+        for r in regs:
+            totals["aligned"] += r.aligned; totals["loci"] += r.size; totals["reads"] += r.n_reads
+        for c in pinned:
+            for name, count, width in _BATCH_FIELDS:
+                nb = _field_bytes(c, count, width)
+                if name == "quals" and c.qual_codes:
+                    name = "qual_codes"
+                if nb:
+                    rt.cudaHostUnregister(getattr(c, name))
+        del regs, pinned
+    totals["d2h"] = per_locus * totals["loci"]
+    clocks = sampler.stop() if rank == 0 else None
+    for eng, _ in workers:
+        eng.close()
+    vals = torch.tensor([t_dev, t_pile, t_e2e], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(totals[k]) for k in ("aligned", "loci", "reads", "h2d", "d2h", "launches")], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    t_dev_max, t_pile_max, t_e2e_max = [float(x) for x in vals.tolist()]
+    aligned, loci, reads, h2d, d2h, launches = [float(x) for x in sums.tolist()]
+    ordered = sharding.gather_in_chunk_order(digests, world)     # host-side gather in chunk order (GenomeFile.scala:135-162)
+    if rank == 0:
+        assert len(ordered) == len(chunks)
+        digest = "%08x" % (zlib.crc32(repr(ordered).encode()) & 0xFFFFFFFF)
+        peak, peak_src = measured_peak_gbs()
+        out = {"metric": METRIC, "value": aligned / t_dev_max, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": 1,
+               "ms_per_step": 1e3 * t_dev_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64",
+               "data": "synthetic",
+               "config": {"workload": "%s: %s" % (wl.name, wl.description), "scale": args.scale, "chunks": len(chunks),
+                          "chunks_per_gpu_max": max(len(x) for x in sharding.assign(chunks, world, [depth] * len(chunks))),
+                          "loci": loci, "reads": reads, "aligned_bases": aligned, "mean_depth": aligned / loci,
+                          "streaming": "chunks generated and dropped in waves of %d per rank; no rank ever holds more than a wave" % wave_n,
+                          "sharding": "pilon_b200.sharding.assign (greedy by loci x depth), no data-path collective; per-chunk digests "
+                                      "gathered on the host in chunk order", "l2": "inputs_exceed_l2",
+                          "timing": "per rank: sum over its chunks of the device time of one pass (CUDA events on the engine's stream, "
+                                    "batches resident); job = max over ranks.  e2e: wall time of each wave through the C ABI from pinned "
+                                    "host buffers, %d chunks in flight, summed per rank, max over ranks" % n_workers,
+                          "e2e_planes": args.planes},
+               "digest": digest,
+               "e2e": {"value": aligned / t_e2e_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "ms_per_step": 1e3 * t_e2e_max},
+               "gpu_launches": int(launches),
+               "roofline": {"bound": "hbm", "kernel": "k_pileup", "achieved": algorithmic_bytes(aligned, reads, reads * 1.1, loci) / t_pile_max / world / 1e9,
+                            "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                            "frac": algorithmic_bytes(aligned, reads, reads * 1.1, loci) / t_pile_max / world / 1e9 / peak,
+                            "note": "per GPU: job algorithmic bytes / ranks / max-over-ranks pileup-kernel time"},
+               "cpu_baseline": None, "host_placement": placement, "clocks": clocks}
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -607,9 +850,14 @@ def main():
     ap.add_argument("--quals8", action="store_true", help="e2e arm: upload one quality byte per base even when the batch "
                     "offers the packed transport (pb_batch.qual_codes)")
     ap.add_argument("--host-threads", type=int, default=4, help="host threads feeding region passes to the GPU")
+    ap.add_argument("--sharded", action="store_true", help="ONE genome, its chunks distributed over the ranks and streamed in waves "
+                    "(strong scaling; the default for --workload C4): see run_sharded_arm")
+    ap.add_argument("--wave", type=int, default=4, help="sharded arm: chunks a rank generates, processes and drops at a time")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.sharded or args.workload == "C4":
+        run_sharded_arm(args)
     else:
         run_gpu_arm(args)
 
