@@ -298,6 +298,66 @@ int pb_packer_add_many(pb_packer* p, int64_t n_reads, const int32_t* pos, const 
  * reset / add / destroy. */
 int pb_packer_view(pb_packer* p, pb_batch* out);
 
+/* ---- consumers of the per-locus results (host side) -----------------------
+ * GenomeRegion.postProcess pass 2 (GenomeRegion.scala:275-283), identifyAndFixIssues for `--fix snps,indels`
+ * (:307-380,413), fixFixList / fixIssues (:557-621), writeChanges (:646-657), writeVcf (:623-643) with
+ * Vcf.writeRecord / writeDup (Vcf.scala:74-176,193-201), the wiggle tracks (Tracks.scala:56-186) and GenomeFile's
+ * naming / FASTA rules (GenomeFile.scala:79-82,137-141).  Gap filling and local reassembly stay the reference's
+ * CPU code (north_star): bigFixList is empty here. */
+typedef struct pb_output_config {      /* the `object Pilon` switches these consumers read (Pilon.scala:28-73) */
+    int32_t fix_snps;        /* Pilon.fixSnps    --fix snps                                            */
+    int32_t fix_indels;      /* Pilon.fixIndels  --fix indels                                          */
+    int32_t iupac;           /* Pilon.iupac      AMB fixes become IUPAC codes     GenomeRegion.scala:333 */
+    int32_t diploid;         /* Pilon.diploid    no Amb filter, one snp total     Vcf.scala:122         */
+    int32_t vcf_qe;          /* Pilon.vcfQE      QE= instead of QP=               Vcf.scala:145         */
+    int32_t longread;        /* Pilon.longread   AMB calls are not fixed          GenomeRegion.scala:332 */
+    int32_t reserved[2];
+} pb_output_config;
+
+typedef struct pb_out_stats {          /* the numbers of the region log lines (GenomeRegion.scala:358-370) */
+    int64_t confirmed, non_n, snps, amb, ins, dels, ins_bases, del_bases;
+    int64_t n_fixes;         /* entries of fixFixList(snpFixList ++ smallFixList)                        */
+    int64_t fix_mismatches;  /* "Fix mismatch" log lines (GenomeRegion.scala:605-606,614)                */
+    int64_t n_dups;          /* duplicationEvents (:735-741)                                             */
+} pb_out_stats;
+
+/* Tracks.scala track functions that are plain per-locus maps of the engine's planes */
+#define PB_TRACK_CHANGES            0   /* Tracks.scala:57-60   */
+#define PB_TRACK_UNCONFIRMED        1   /* :62-65               */
+#define PB_TRACK_COPY_NUMBER        2   /* :67-70               */
+#define PB_TRACK_COVERAGE           3   /* :77-80               */
+#define PB_TRACK_BAD_COVERAGE       4   /* :93-96               */
+#define PB_TRACK_PCT_BAD            5   /* :139-147             */
+#define PB_TRACK_DELTA_COVERAGE     6   /* :104-107             */
+#define PB_TRACK_DIP_COVERAGE       7   /* :109-112             */
+#define PB_TRACK_PHYSICAL_COVERAGE  8   /* :114-117             */
+#define PB_TRACK_CLIPPED            9   /* :163-166             */
+#define PB_TRACK_WEIGHTED_QUAL     10   /* :157-160             */
+#define PB_TRACK_WEIGHTED_MQ       11   /* :150-155             */
+
+typedef struct pb_region_out pb_region_out;
+
+const char* pb_out_last_error(void);
+/* One GenomeRegion downstream of postProcess pass 1.  `res` (with flags, call, frag_coverage and untruncated indel
+ * evidence) and `contig_bases` are referenced, not copied: both must outlive the handle. */
+int pb_out_create(const pb_region_result* res, const uint8_t* contig_bases, int64_t contig_len, const char* name,
+                  int32_t start, int32_t stop, const pb_output_config* cfg, pb_region_out** out);
+int pb_out_destroy(pb_region_out* o);
+int pb_out_stats_get(const pb_region_out* o, pb_out_stats* st);
+int pb_out_bases(const pb_region_out* o, const uint8_t** bases, int64_t* n);        /* GenomeRegion.bases after fixIssues    */
+int pb_out_copy_number(const pb_region_out* o, const int16_t** cn, int64_t* n);    /* GenomeRegion.copyNumber               */
+/* Text producers: *text points into a buffer owned by the handle, valid until the same function is called again. */
+int pb_out_log(pb_region_out* o, const char** text, int64_t* n);                    /* the region's log lines               */
+int pb_out_changes(pb_region_out* o, const char* new_name, int64_t offset, const char** text, int64_t* n);   /* writeChanges */
+int pb_out_vcf(pb_region_out* o, int threads, const char** text, int64_t* n);       /* writeVcf: needs every counter plane  */
+int pb_out_wig(pb_region_out* o, int track, const char** text, int64_t* n);         /* makeTrack body for this region       */
+/* GenomeFile-level helpers; buf == NULL only reports the size in *n. */
+int pb_pilon_name(const char* name, char* buf, int64_t cap, int64_t* n);
+int pb_fasta_element(const char* header, const uint8_t* bases, int64_t n_bases, char* buf, int64_t cap, int64_t* n);
+int pb_vcf_header(const pb_output_config* cfg, const char* date, const char* version, const char* command_args,
+                  const char* reference_uri, const char* const* contig_names, const int64_t* contig_sizes, int32_t n_contigs,
+                  char* buf, int64_t cap, int64_t* n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,12 +9,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libpilonb200.so")
-SOURCES = ["pb_engine.cu"]
+SOURCES = ["pb_engine.cu", "pb_output.cpp"]
 
 
 def deps():
     """Every source the library is compiled from: all of csrc/*.cu, csrc/*.cuh and the public header."""
-    out = [f for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    out = [f for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".cpp", ".hpp")) and f != "pb_synth.cpp"]
     return out + [os.path.join("..", "..", "include", "pilon_b200.h")]
 
 

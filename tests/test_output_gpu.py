@@ -1,0 +1,62 @@
+"""`--fix snps,indels --changes --vcf` end to end: CUDA engine through the C ABI -> pb_out_* -> .fasta / .changes / .vcf
+text, against the literal Python transliteration of the whole chain (oracle/pilon_oracle.py + pilon_output_oracle.py)."""
+import random
+
+import pytest
+
+from oracle import pilon_oracle as po
+from oracle import pilon_output_oracle as oo
+from pilon_b200 import output as out
+from pilon_b200.engine import Engine
+from pilon_b200.packing import pack_records
+from tests import helpers as H
+from tests.test_output_cpu import compare, oracle_outputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("seed", [1, 4, 9, 16])
+def test_engine_results_feed_the_consumers(seed):
+    contig, start, stop, reads = H.random_case(seed, contig_len=1200, n_reads=600)
+    groups = H.split_batches(reads, random.Random(seed))
+    ocfg = oo.OutConfig(vcfQE=seed % 2 == 0)
+    gr = oracle_outputs(contig, start, stop, groups, None, ocfg)
+    e = Engine(0)
+    try:
+        res, _ = e.run_region(contig, start, stop, [(pack_records(g), f) for g, f in groups])
+    finally:
+        e.close()
+    compare(res, contig, start, stop, gr, ocfg)
+
+
+def test_two_chunk_contig_fasta_changes_and_vcf():
+    """One contig cut into two chunks (GenomeFile.scala:67-74): the changes file carries the running offset of the fixed
+    sequence across chunks (:150-153), the FASTA is the concatenation of the fixed chunks 80 columns wide (:155-161)."""
+    contig, _, _, reads = H.clean_case(7, n=24000, start=1, stop=24000, depth=12, n_sites=30)
+    name = "scaffold_7"
+    chunks = [(1, 12000), (12001, 24000)]
+    ocfg = oo.OutConfig()
+    e = Engine(0)
+    outs, grs = [], []
+    try:
+        for a, b in chunks:
+            mine = [r for r in reads if a - 10000 <= r.pos <= b + 10000]          # BamFile.scala:118-119 window
+            gr = oo.GenomeRegionOut(contig, a, b, None, name, ocfg)
+            gr.initializePileUps(oob_drop=True)
+            gr.processBam(mine, "frags")
+            gr.postProcess()
+            gr.identifyAndFixIssues()
+            grs.append(gr)
+            res, _ = e.run_region(contig, a, b, [(pack_records(mine), True)], indels_cap=1 << 16, bytes_cap=1 << 20)
+            outs.append(out.RegionOutput(res, contig, name, a, b))
+        vcf = oo.Vcf(ocfg)
+        want_changes, want_fasta = oo.writeContig(name, grs, vcf, True)
+        got_changes, got_fasta, got_vcf = out.writeContig(name, outs, vcf=True, changes=True)
+        assert got_changes == want_changes and len(want_changes) > 10
+        assert got_fasta.splitlines() == want_fasta
+        assert got_vcf.splitlines() == vcf.lines
+        assert any(" ." in c for c in want_changes)                               # at least one indel moved the offset
+    finally:
+        for o in outs:
+            o.close()
+        e.close()
