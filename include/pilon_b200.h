@@ -358,6 +358,28 @@ int pb_vcf_header(const pb_output_config* cfg, const char* date, const char* ver
                   const char* reference_uri, const char* const* contig_names, const int64_t* contig_sizes, int32_t n_contigs,
                   char* buf, int64_t cap, int64_t* n);
 
+/* ---- BAM ingest and synthetic BAM / BAI / FASTA output (host side) ---------
+ * pb_bam_query_pack is BamFile.process's reader loop (BamFile.scala:117-139) without htsjdk: BGZF inflate, BAI
+ * linear-index seek, BAM record decode, validateRead (BamFile.scala:101-105) and pb_packer_add.  The writer produces
+ * coordinate-sorted BAM + BAI (+ FASTA / .fai) from pb_batch arrays so that synthetic inputs can also be fed to the
+ * reference JVM (tools/run_real_pilon.sh). */
+typedef struct pb_bam pb_bam;
+typedef struct pb_bam_writer pb_bam_writer;
+const char* pb_bam_last_error(void);
+int pb_bam_open(const char* bam_path, const char* bai_path /* NULL: bam_path + ".bai" */, pb_bam** out);
+int pb_bam_close(pb_bam* b);
+int pb_bam_n_refs(const pb_bam* b, int32_t* n);
+int pb_bam_ref(const pb_bam* b, int32_t i, const char** name, int64_t* len);
+/* records of reference ref_id overlapping [start, stop] (1-based inclusive: pass region.start - 10000, region.stop + 10000
+ * as BamFile.scala:118-119 does); non_pf = Pilon.nonPf, duplicates = Pilon.duplicates */
+int pb_bam_query_pack(pb_bam* b, int32_t ref_id, int32_t start, int32_t stop, int non_pf, int duplicates,
+                      pb_packer* packer, int64_t* n_records, int64_t* n_rejected);
+int pb_bam_writer_open(const char* path, const char* const* ref_names, const int64_t* ref_lens, int32_t n_refs,
+                       const char* program_line, pb_bam_writer** out);
+int pb_bam_writer_add_batch(pb_bam_writer* w, int32_t ref_id, const pb_batch* batch, const uint16_t* extra_flags);
+int pb_bam_writer_close(pb_bam_writer* w, const char* bai_path);
+int pb_fasta_write(const char* path, const char* const* names, const uint8_t* const* seqs, const int64_t* lens, int32_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -411,3 +411,26 @@ def clean_case(seed: int, n: int = 30000, start: int = 2001, stop: int = 26000, 
         reads += planted_snp_cluster(rng, contig, start, stop, depth_range=(2 * depth, 3 * depth))
     reads.sort(key=lambda r: r.pos)
     return contig, start, stop, reads
+
+
+def unpack_batch(rb: ReadBatch) -> List[po.Read]:
+    """The records a packed batch stands for, as the literal oracle wants them (inverse of pack_records)."""
+    out: List[po.Read] = []
+    exc = {int(i): (int(b), int(q)) for i, b, q in zip(rb.exc_idx, rb.exc_base, rb.exc_qual)}
+    for r in range(rb.n_reads):
+        L, s0, fl = int(rb.read_len[r]), int(rb.seq_off[r]), int(rb.flags[r])
+        bases, quals = bytearray(L), bytearray(L)
+        for j in range(L):
+            i = s0 + j
+            q = int(rb.quals[i])
+            if q & 0x80:
+                bases[j], quals[j] = exc[i]
+            else:
+                bases[j] = b"ACGT"[(int(rb.bases2[i >> 2]) >> (2 * (i & 3))) & 3]
+                quals[j] = q
+        cig = [(capi.CIGAR_OPS[int(e) & 15], int(e) >> 4) for e in rb.cigar[int(rb.cigar_off[r]):int(rb.cigar_off[r + 1])]]
+        out.append(po.Read(pos=int(rb.pos[r]), cigar=cig, bases=bytes(bases), quals=bytes(quals) if fl & capi.PB_F_HAS_QUALS else b"",
+                           mapq=int(rb.mapq[r]), paired=bool(fl & capi.PB_F_PAIRED), proper=bool(fl & capi.PB_F_PROPER),
+                           mate_same_ref=bool(fl & capi.PB_F_MATE_SAME_REF), tlen=int(rb.tlen[r]),
+                           unmapped=bool(fl & capi.PB_F_UNMAPPED), reverse=bool(fl & capi.PB_F_REVERSE)))
+    return out

@@ -60,3 +60,42 @@ def test_two_chunk_contig_fasta_changes_and_vcf():
         for o in outs:
             o.close()
         e.close()
+
+
+def test_fasta_and_bams_in_fasta_changes_vcf_out(tmp_path):
+    """The whole replaced chain on files: genome.fasta + frags.bam + jumps.bam (written by the synthetic generator) ->
+    native BAM ingest -> CUDA engine -> consumers -> pilon.fasta / .changes / .vcf, against the literal oracle chain fed with
+    the same records.  This is what tools/run_real_pilon.sh diffs against the JVM where one exists."""
+    import os
+    import subprocess
+    import sys
+    from pilon_b200 import bamio, synth
+    sys.path.insert(0, os.path.join(H.ROOT, "tools"))
+    import make_pilon_inputs
+    wl = synth.workload("C2", 0.0008)                      # 20 contigs of 20 kb: 60x frags + 10x jumps
+    wl.contig_lens = wl.contig_lens[:3]
+    names, paths = make_pilon_inputs.write_inputs(wl, str(tmp_path / "in"))
+    subprocess.check_call([sys.executable, os.path.join(H.ROOT, "tools", "pilon_b200_run.py"), "--genome", str(tmp_path / "in" / "genome.fasta"),
+                           "--frags", paths["frags"], "--jumps", paths["jumps"], "--changes", "--vcf", "--outdir", str(tmp_path / "out"),
+                           "--chunksize", "12000"], stdout=subprocess.DEVNULL)
+    want_fa, want_ch, vcf = [], [], oo.Vcf()
+    for ci, name in enumerate(names):
+        seq = wl.contig_bases(ci).tobytes()
+        grs = []
+        for a, b in synth.chunks_of(len(seq), 12000):
+            gr = oo.GenomeRegionOut(seq, a, b, None, name)
+            gr.initializePileUps(oob_drop=True)
+            for kind in ("frags", "jumps"):
+                bf = bamio.BamFile(paths[kind], kind)
+                gr.processBam(H.unpack_batch(bf.process(name, a, b)), kind)
+                bf.close()
+            gr.postProcess()
+            gr.identifyAndFixIssues()
+            grs.append(gr)
+        ch, fa = oo.writeContig(name, grs, vcf, True)
+        want_ch += ch
+        want_fa += fa
+    got = lambda ext: open(str(tmp_path / "out" / ("pilon." + ext))).read().splitlines()
+    assert got("fasta") == want_fa
+    assert got("changes") == want_ch and len(want_ch) > 5
+    assert [l for l in got("vcf") if not l.startswith("#")] == vcf.lines
