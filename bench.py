@@ -487,7 +487,7 @@ def run_gpu_arm(args):
         [t.join() for t in ts]
         return done[0]
 
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, args.steps)
     for _ in range(max(1, min(args.warmup, 3))):
         e2e_step()
     barrier()
@@ -501,6 +501,26 @@ def run_gpu_arm(args):
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     assert got == total_aligned * e2e_steps, (got, total_aligned)
+    # the same arm with one quality byte per base (what a BAM with unbinned qualities needs), a few steps
+    e2e8 = None
+    if q4 and not args.quals8 and world == 1:
+        saved = [(b, b.c.qual_codes) for r in regions for b in r.batches]
+        h2d8 = 0
+        for b, _ in saved:
+            b.c.qual_codes = None
+            _register(torch.cuda.cudart(), b.c.quals, int(b.c.n_seq))
+            h2d8 += int(b.c.n_seq) - (int(b.c.n_seq) * int(b.c.qual_code_bits) + 7) // 8
+        e2e_step()
+        torch.cuda.synchronize()
+        t8 = time.perf_counter()
+        n8 = max(1, min(args.steps, 3))
+        for _ in range(n8):
+            e2e_step()
+        torch.cuda.synchronize()
+        t8 = (time.perf_counter() - t8) / n8
+        e2e8 = {"value": total_aligned / t8, "unit": UNIT, "ms_per_step": 1e3 * t8, "h2d_bytes_per_step": h2d + h2d8, "steps": n8}
+        for b, qc in saved:
+            b.c.qual_codes = qc
     if trace is not None and rank == 0:
         for slot, t in enumerate(trace):
             print("e2e worker %d: begin %.1f ms, add_batch %.1f ms, finish %.1f ms per step" %
@@ -558,6 +578,20 @@ def run_gpu_arm(args):
                       "ok": not mismatches}
             if mismatches:
                 parity["mismatches"] = mismatches[:10]
+        from_bam = from_bam_leg(args, wl, regions, local) if (args.from_bam and world == 1) else None
+        # shared-memory reductions of the scatter kernel: one 32-bit RED lane-op per counted base (+ one per counted base of a
+        # batch outside fragCoverage); peak = 32 lanes x 1 wavefront per clock per SM.  Regions the engine gives to the gather
+        # kernel (deep and narrow: C5) accumulate in registers and issue no per-base atomics.
+        scatter = [r for r in regions if (r.size + 2047) // 2048 >= 256 and sum(int(b.c.n_seq) for b in r.batches) // r.size <= 1000]
+        sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
+        lane_ops = sum(b.aligned_bases * (1 if b.frag else 2) for r in scatter for b in r.batches) * (130.0 / 150.0)
+        atomic = {"kernel": "k_pileup7 (scatter)" if scatter else "k_pileup5 (gather: no per-base atomics)",
+                  "regions": len(scatter),
+                  "shared_red_lane_ops_per_s": (lane_ops / (pileup_ms * 1e-3)) if scatter else 0.0,
+                  "peak_lane_ops_per_s": 148 * 32 * sm_hz,
+                  "frac": (lane_ops / (pileup_ms * 1e-3)) / (148 * 32 * sm_hz) if scatter else 0.0,
+                  "note": "counted bases ~ aligned bases x 130/150 (trusted flank); ncu: profiles/r2_pileup7_raw.csv "
+                          "(smsp__inst_executed_op_shared_atom, l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom)"}
         out = {"metric": METRIC, "value": job_aligned / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "int64", "data": "synthetic",
@@ -573,21 +607,85 @@ def run_gpu_arm(args):
                                         if args.base_deltas else "2 bits per base")},
                "wall_ms_per_step": wall_step_ms, "sequential_ms_per_step": seq_step_ms,
                "e2e": {"value": job_aligned / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": job_h2d, "d2h_bytes_per_step": job_d2h,
-                       "ms_per_step": 1e3 * e2e_sec, "streams_per_gpu": n_workers * e2e_depth,
-                       "host_threads_per_gpu": n_workers, "passes_in_flight_per_thread": e2e_depth},
+                       "ms_per_step": 1e3 * e2e_sec, "steps": e2e_steps, "streams_per_gpu": n_workers * e2e_depth,
+                       "host_threads_per_gpu": n_workers, "passes_in_flight_per_thread": e2e_depth,
+                       "quals8": e2e8},
                "gpu_launches": int(job_launches),
                "roofline": {"bound": "hbm", "kernel": "k_pileup", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": sum(r.alg_bytes for r in regions) / len(regions),
                             "algorithmic_bytes_per_base": alg / total_aligned,
-                            "pileup_ms_per_step": pileup_ms, "pileup_share_of_sequential_step": pileup_ms / seq_step_ms},
-               "cpu_baseline": cpu, "parity": parity, "host_placement": placement, "clocks": clocks}
+                            "pileup_ms_per_step": pileup_ms, "pileup_share_of_sequential_step": pileup_ms / seq_step_ms,
+                            "atomic": atomic},
+               "cpu_baseline": cpu, "parity": parity, "e2e_from_bam": from_bam, "host_placement": placement, "clocks": clocks}
         print(json.dumps(out))
         if parity is not None and not parity["ok"]:
             print("PARITY MISMATCH: " + "; ".join(parity["mismatches"]), file=sys.stderr)
             sys.exit(3)
     if world > 1:
         dist.destroy_process_group()
+
+
+
+def from_bam_leg(args, wl, regions, local):
+    """End to end from BAM BYTES on a bounded sample: the sample contigs' reads are written as coordinate-
+    sorted BAM + BAI (untimed), then timed: native BGZF inflate + record decode + validateRead + packing (host threads, one
+    BAM handle each) -> C ABI -> per-locus results on the host.  What the reference does here is htsjdk + addRead."""
+    import tempfile
+    from pilon_b200 import bamio, synth
+    from pilon_b200.engine import Engine
+    from pilon_b200.packing import ResultBuffers
+    sample = [r for r in regions if r.size <= 3_000_000][:6] or regions[:1]
+    tmp = tempfile.mkdtemp(prefix="pb_bam_")
+    refs = [("contig%02d" % (r.ci + 1), len(r.contig)) for r in sample]
+    paths = []
+    for libr in wl.libraries:
+        p = os.path.join(tmp, libr.name + ".bam")
+        batches = [(k, synth.SynthBatch(wl.params(r.ci, libr), 1, len(r.contig), libr.counts_toward_frag_coverage)) for k, r in enumerate(sample)]
+        bamio.write_bam(p, refs, [(k, sb.c) for k, sb in batches])
+        paths.append((p, libr.name))
+        del batches
+    bam_bytes = sum(os.path.getsize(p) for p, _ in paths)
+    nthreads = max(1, min(len(sample), len(os.sched_getaffinity(0)), 6))
+    max_size = max(r.size for r in sample)
+    slots = [(Engine(local), ResultBuffers(max_size, FIX_PLANES, indels_cap=1 << 20, indel_bytes_cap=1 << 23, pinned=True),
+              [bamio.BamFile(p, t) for p, t in paths]) for _ in range(nthreads)]
+    order = list(range(len(sample)))
+    lock = threading.Lock()
+    t_ingest = [0.0] * nthreads
+    got = [0]
+
+    def work(slot):
+        eng, res, bams = slots[slot]
+        while True:
+            with lock:
+                k = order.pop(0) if order else None
+            if k is None:
+                return
+            r = sample[k]
+            t0 = time.perf_counter()
+            batches = [(b.process(refs[k][0], r.start, r.stop), b.countsTowardFragCoverage) for b in bams]
+            t_ingest[slot] += time.perf_counter() - t0
+            eng.region_begin(r.contig, r.start, r.stop)
+            for rb, frag in batches:
+                eng.add_batch(rb, frag)
+            eng.finish(res)
+            with lock:
+                got[0] += int(res.c.aligned_bases)
+    t0 = time.perf_counter()
+    ts = [threading.Thread(target=work, args=(s,)) for s in range(nthreads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    dt = time.perf_counter() - t0
+    for eng, _, bams in slots:
+        eng.close()
+        [b.close() for b in bams]
+    for p, _ in paths:
+        os.remove(p); os.remove(p + ".bai")
+    os.rmdir(tmp)
+    return {"value": got[0] / dt, "unit": UNIT, "regions": len(sample), "aligned_bases": got[0], "bam_bytes": bam_bytes,
+            "host_threads": nthreads, "seconds": dt, "ingest_seconds_per_thread": sum(t_ingest) / nthreads,
+            "note": "BGZF inflate + BAM decode + packing are inside the timed region (zlib, one stream per host thread)"}
 
 
 
@@ -850,6 +948,7 @@ def main():
     ap.add_argument("--quals8", action="store_true", help="e2e arm: upload one quality byte per base even when the batch "
                     "offers the packed transport (pb_batch.qual_codes)")
     ap.add_argument("--host-threads", type=int, default=4, help="host threads feeding region passes to the GPU")
+    ap.add_argument("--from-bam", action="store_true", help="also time a bounded sample end to end from BAM bytes (native BGZF/BAM ingest)")
     ap.add_argument("--sharded", action="store_true", help="ONE genome, its chunks distributed over the ranks and streamed in waves "
                     "(strong scaling; the default for --workload C4): see run_sharded_arm")
     ap.add_argument("--wave", type=int, default=4, help="sharded arm: chunks a rank generates, processes and drops at a time")

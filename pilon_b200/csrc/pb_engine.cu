@@ -14,11 +14,10 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
-#include "pb_pileup9.cuh"
+#include "pb_pileup7.cuh"
 
 using namespace pb;
 
-static_assert(2 * (sizeof(Tile9<P9_TILE>) + 1024) <= 228 * 1024, "two CTAs of k_pileup9 must fit one SM's shared memory");
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -123,11 +122,10 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
     e->cfg.min_qual = c->min_qual; e->cfg.min_mq = c->min_mq; e->cfg.flank = c->flank;
     e->cfg.default_qual = c->default_qual; e->cfg.min_min_depth = c->min_min_depth;
     e->cfg.old_indel = c->old_indel; e->cfg.fix_amb = c->fix_amb; e->cfg.min_depth = c->min_depth;
-    if (const char* v = getenv("PB_PILEUP")) { const int pv = atoi(v); if (pv == 5 || pv == 7 || pv == 9) e->pileup_version = pv; }
+    if (const char* v = getenv("PB_PILEUP")) { const int pv = atoi(v); if (pv == 5 || pv == 7) e->pileup_version = pv; }
     CK(cudaFuncSetAttribute(k_pileup7<false, P7_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile7<P7_TILE>)));
     CK(cudaFuncSetAttribute(k_pileup7<true, P7_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile7<P7_TILE>)));
-    CK(cudaFuncSetAttribute(k_pileup9<false, P9_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile9<P9_TILE>)));
-    CK(cudaFuncSetAttribute(k_pileup9<true, P9_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile9<P9_TILE>)));
+
     CK(cudaFuncSetAttribute(k_pileup5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_pileup5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -602,7 +600,7 @@ static int compute(pb_engine* e, bool time_pileup, bool full_cap = false) {
         const int64_t depth = R.size > 0 ? (int64_t)(total_seq / (size_t)R.size) : 0;      // stored bases per locus: >= depth
         pv = (tiles >= 256 && depth <= 1000) ? 7 : 5;
     }
-    if ((pv == 7 || pv == 9) && nb > PB_MAXB) pv = 5;   // the scatter kernel keeps its per-batch cursors in shared memory: <= PB_MAXB batches
+    if (pv == 7 && nb > PB_MAXB) pv = 5;   // the scatter kernel keeps its per-batch cursors in shared memory: <= PB_MAXB batches
     PileBatches PBt; memset(&PBt, 0, sizeof(PBt)); PBt.n = nb;
     {
         std::vector<PileBatch>& pile = e->pile_host;
@@ -622,10 +620,6 @@ static int compute(pb_engine* e, bool time_pileup, bool full_cap = false) {
         }
     }
     if (R.exp_flags & 256) {               // knock-out: everything but the pileup kernel (what the rest of the pass costs)
-    } else if (pv == 9) {
-        const unsigned grid = (unsigned)((R.n_win * 32 + P9_TILE - 1) / P9_TILE);
-        if (e->cfg.min_qual > 0) k_pileup9<true, P9_TILE><<<grid, P9_WARPS * 32, sizeof(Tile9<P9_TILE>), s>>>(R, PBt);
-        else k_pileup9<false, P9_TILE><<<grid, P9_WARPS * 32, sizeof(Tile9<P9_TILE>), s>>>(R, PBt);
     } else if (pv == 7) {
         const unsigned grid = (unsigned)((R.n_win * 32 + P7_TILE - 1) / P7_TILE);
         if (e->cfg.min_qual > 0) k_pileup7<true, P7_TILE><<<grid, P7_WARPS * 32, sizeof(Tile7<P7_TILE>), s>>>(R, PBt);

@@ -23,7 +23,7 @@ class kernel_choice:
     """PB_PILEUP is read by pb_create: engines made inside the block use the forced kernel (None = the engine's choice)."""
 
     def __init__(self, which):
-        self.val = {None: None, "auto": None, "gather": "5", "scatter": "7", "items": "9"}[which]
+        self.val = {None: None, "auto": None, "gather": "5", "scatter": "7"}[which]
 
     def __enter__(self):
         self.old = os.environ.get("PB_PILEUP")
@@ -122,7 +122,7 @@ def _eng_cfg(cfg):
                         cfg.oldIndel, cfg.iupac, cfg.fixAmb)
 
 
-@pytest.mark.parametrize("kernel", ["gather", "scatter", "items"])
+@pytest.mark.parametrize("kernel", ["gather", "scatter"])
 def test_deletion_shift_readds_bases_left_of_the_reads_pos(kernel):
     """PileUpRegion.scala:167-178: the shift walks read offsets backwards across earlier CIGAR elements; after a long
     insertion inside a homopolymer the re-added bases start LEFT of the read's alignment start.  No read of the batch
@@ -153,7 +153,7 @@ def test_deletion_shift_readds_bases_left_of_the_reads_pos(kernel):
         e.close()
 
 
-@pytest.mark.parametrize("kernel", ["gather", "scatter", "items"])
+@pytest.mark.parametrize("kernel", ["gather", "scatter"])
 def test_more_than_4064_descriptors_per_tile_with_mixed_mapq(kernel):
     """The scatter kernel folds its 12-bit tile counters into the output planes every 4064 descriptors; reads with
     five different mapping qualities make the folds carry Bq / C terms as well."""
@@ -184,7 +184,7 @@ def test_more_than_4064_descriptors_per_tile_with_mixed_mapq(kernel):
     assert int(res["base_count4"].sum(axis=1).max()) > 300
 
 
-@pytest.mark.parametrize("kernel", ["gather", "scatter", "items"])
+@pytest.mark.parametrize("kernel", ["gather", "scatter"])
 def test_int32_wrap_of_mqsum(kernel):
     """mqSum is a JVM Int (PileUp.scala:33): 8.5 M bases of MAPQ 255 at one locus push it past 2^31 and it wraps;
     BaseSum (qualSum) is 64-bit and does not.  score becomes 0 through `mqSum > 0` (PileUp.scala:148)."""
