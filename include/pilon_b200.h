@@ -241,8 +241,9 @@ int pb_region_begin(pb_engine* e, const uint8_t* contig_bases, int64_t contig_le
 
 /* The batched equivalent of the `for (read <- reads) ... addRead` loop (BamFile.scala:126-139).
  * counts_toward_frag_coverage = (bamType != "jumps")      (GenomeRegion.scala:291,296)
- * long_read_type              = BamFile.longReadType       (BamFile.scala:43-47); only 0 is
- *                               implemented in this round (PB_ERR_UNSUPPORTED otherwise).
+ * long_read_type              = BamFile.longReadType       (BamFile.scala:43-47): 0, 1 = nanopore, 2 = pacbio; the
+ *                               long-read branches of addRead (PileUpRegion.scala:120-134,142,160,180-181,190) apply
+ *                               to the reads of this batch.
  * The call is asynchronous on the engine's stream; host buffers must stay valid until
  * pb_region_finish returns. */
 int pb_region_add_batch(pb_engine* e, const pb_batch* batch,

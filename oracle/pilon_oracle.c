@@ -167,8 +167,23 @@ static void unpack_read(const pb_batch* b, int64_t rd, uint8_t* bases, uint8_t* 
     *exc_cursor = k;
 }
 
-/* PileUpRegion.addRead, PileUpRegion.scala:102-220 (longRead == 0 branches only) */
-static int32_t addRead(po_region* r, const pb_batch* b, int64_t rd, const uint8_t* bases, const uint8_t* qraw) {
+/* PileUpRegion.scala:120-134: both helpers index refBases (the whole contig, 0-based) with whatever they are handed -- a
+ * locus for insertions (:160), a REGION index for deletions and aligned bases (:180-181,190).  Outside the contig the JVM
+ * would throw; here such an index simply matches nothing. */
+static int refAt(const po_region* r, int64_t i0) { return (i0 >= 0 && i0 < r->contig_len) ? r->contig[i0] : 0; }
+static int homoRun(const po_region* r, int64_t i0) {
+    if (i0 < 0 || i0 >= r->contig_len) return 0;
+    int b = r->contig[i0];
+    for (int64_t i = i0 + 1; i < r->contig_len; i++) if (r->contig[i] != b) return (int)(i - i0 > 1000000 ? 1000000 : i - i0);
+    return (int)(r->contig_len - i0 > 1000000 ? 1000000 : r->contig_len - i0);
+}
+static int nanoporeExclude(const po_region* r, int64_t i0) {
+    return inRegion(r, r->start + i0 - 2) && inRegion(r, r->start + i0 + 2) &&
+           refAt(r, i0 - 2) == 'C' && refAt(r, i0 - 1) == 'C' && refAt(r, i0 + 1) == 'G' && refAt(r, i0 + 2) == 'G';
+}
+
+/* PileUpRegion.addRead, PileUpRegion.scala:102-220; longRead = BamFile.longReadType (0, 1 nanopore, 2 pacbio) */
+static int32_t addRead(po_region* r, const pb_batch* b, int64_t rd, const uint8_t* bases, const uint8_t* qraw, int longRead) {
     const pb_config* cfg = &r->cfg;
     const uint8_t* ref = r->contig;
     int32_t length = b->read_len[rd];
@@ -193,7 +208,7 @@ static int32_t addRead(po_region* r, const pb_batch* b, int64_t rd, const uint8_
     }
     int32_t aEnd = (fl & PB_F_UNMAPPED) ? 0 : wrap32((int64_t)aStart + reflen - 1);   /* getAlignmentEnd */
     int32_t adjMq = roundDivI(wrap32((int64_t)mq * (length - clipped)), length);      /* :141 */
-    int32_t indelMq = adjMq;                                                          /* :142, longRead == 0 */
+    int32_t indelMq = longRead > 0 ? (adjMq < 8 ? adjMq : 8) : adjMq;                 /* :142 */
     int64_t readOffset = 0, refOffset = 0;
     for (int32_t k = 0; k < ncig; k++) {
         int op = cig[k] & 15; int64_t len = cig[k] >> 4;
@@ -212,6 +227,7 @@ static int32_t addRead(po_region* r, const pb_batch* b, int64_t rd, const uint8_
                     if (iloc < r->start) break;   /* JVM would crash at pileups(index(iloc)) below */
                 }
                 if (iloc < r->start) { r->dropped_oob++; free(ins); break; }
+                if (longRead > 0 && homoRun(r, iloc) >= 4) { free(ins); break; }         /* :160 (the locus is used as an index) */
                 int64_t i = iloc - r->start;
                 /* PileUp.addInsertion, PileUp.scala:98-105 */
                 r->insQual[i] = wrap32((int64_t)r->insQual[i] + indelMq + 1);
@@ -238,6 +254,7 @@ static int32_t addRead(po_region* r, const pb_batch* b, int64_t rd, const uint8_
                     }
                 }
                 int64_t i = dloc - r->start;
+                if (longRead > 0 && (homoRun(r, i) >= 4 || (longRead == 1 && nanoporeExclude(r, i)))) break;   /* :180-181 */
                 /* PileUp.addDeletion, PileUp.scala:107-114 */
                 r->mqSum[i] = wrap32((int64_t)r->mqSum[i] + indelMq + 1);
                 r->delQual[i] = wrap32((int64_t)r->delQual[i] + indelMq + 1);
@@ -249,7 +266,10 @@ static int32_t addRead(po_region* r, const pb_batch* b, int64_t rd, const uint8_
         case 0: case 7: case 8: /* M = X, :184-193 */
             for (int64_t i = 0; i < len; i++) {
                 int64_t rOff = readOffset + i;
-                if (TRUSTED(rOff)) region_add(r, locus + i, bases[rOff], QUAL(rOff), adjMq, valid);
+                if (TRUSTED(rOff)) {
+                    int qual = (longRead == 1 && nanoporeExclude(r, locus + i - r->start)) ? 0 : QUAL(rOff);   /* :190 */
+                    region_add(r, locus + i, bases[rOff], qual, adjMq, valid);
+                }
             }
             break;
         case 4: { /* S, :194-206 */
@@ -276,7 +296,7 @@ static int32_t addRead(po_region* r, const pb_batch* b, int64_t rd, const uint8_
 
 /* BamFile.process loop (BamFile.scala:126-139) inside GenomeRegion.processBam (GenomeRegion.scala:287-300) */
 int po_region_add_batch(po_region* r, const pb_batch* b, int frag, int long_read, int32_t* insert_sizes_out) {
-    if (long_read != 0) return PB_ERR_UNSUPPORTED;
+    if (long_read < 0 || long_read > 2) return PB_ERR_INVALID;
     const int32_t readsBefore = r->readCount;                                           /* BamFile.scala:120 */
     const int64_t baseCountBefore = r->baseCount;                                       /* :121 */
     const int64_t covBeforeBam = roundDivL(r->baseCount, r->size);                      /* :122; PileUpRegion.scala:36 */
@@ -288,7 +308,7 @@ int po_region_add_batch(po_region* r, const pb_batch* b, int frag, int long_read
     int64_t cursor = 0;
     for (int64_t rd = 0; rd < b->n_reads; rd++) {
         unpack_read(b, rd, bases, quals, &cursor);
-        int32_t ins = addRead(r, b, rd, bases, quals);
+        int32_t ins = addRead(r, b, rd, bases, quals, long_read);
         if (insert_sizes_out) insert_sizes_out[rd] = ins;
     }
     free(bases); free(quals);

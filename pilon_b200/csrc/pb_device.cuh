@@ -25,6 +25,8 @@ namespace pb {
 struct __align__(16) Seg { int32_t loc0; int32_t len; uint32_t src; uint32_t w; };
 static constexpr uint32_t SEG_VALID = 1u << 16;   // valid read: PileUp.add + region baseCount; else badPair++
 static constexpr uint32_t SEG_HASQ  = 1u << 17;   // read has base qualities (else Pilon.defaultQual)
+static constexpr uint32_t SEG_READD = 1u << 18;   // bases a deletion's left shift re-adds (PileUpRegion.scala:170-178): they keep their
+                                                  // own quality even in a nanopore batch (:172 reads quals(rloc), not the :190 rule)
 
 // One insertion / deletion observation (PileUp.addInsertion / addDeletion, PileUp.scala:98-114).
 // `lk`  = locus index << 1 | (kind - 1); `h` identifies the string (exact 2-bit image for
@@ -39,6 +41,11 @@ struct __align__(8) Group {          // device image of pb_indel (+ the winning 
 };
 
 struct __align__(32) Rare { int32_t ins, insq, del, delq, q, mq, clips, delfrag; };
+
+// Per-locus contributions of long-read batches (--nanopore / --pacbio; PileUpRegion.scala:120-134,160,180-181,190): their
+// bases are added by k_long with global atomics into this plane, which the pileup epilogue merges and re-zeroes.  Only
+// allocated for regions that get such a batch: the short-read hot path never sees it.
+struct __align__(16) Extra { unsigned long long qs[4]; uint32_t cnt[4]; uint32_t mq, q, bp, frag; };
 
 // What the pileup kernel needs to know about a batch, passed BY VALUE in the kernel parameters
 // (constant bank): no dependent global load stands between a warp and its first descriptor.
@@ -66,7 +73,7 @@ struct DevBatch {
     int32_t* reach;         // [2] device scalars: max forward reach, max backward reach (loci)
     int32_t frag;           // counts toward fragCoverage (GenomeRegion.scala:291,296)
     int32_t fwd, back;      // host copy of reach[0..1], filled in after k_prep (saves a dependent load per tile)
-    int32_t pad;
+    int32_t long_read;      // BamFile.longReadType: 0, 1 = nanopore, 2 = pacbio (BamFile.scala:43-47)
 };
 
 // k_prep spreads its per-warp partial sums over SC_SLOTS slots (same-address L2 atomics serialise);
@@ -109,6 +116,10 @@ struct RegionDev {
     Rare* rare;
     uint32_t *r_gins, *r_gdel;  // group index + 1 of the locus' insertion / deletion evidence
     uint32_t* rare_bits;        // [n_win] bit l set = locus 32*w + l has any rare contribution
+    Extra* extra;               // [size] or nullptr: what long-read batches contributed (k_long)
+    const uint8_t* head;        // long-read mode: raw contig bytes [0, head_len) -- the reference indexes refBases with REGION
+    int64_t head_len;           //   indices in homoRun / nanoporeExclude (PileUpRegion.scala:120-134,180-181,190)
+    int64_t contig_len;
     int2* pc_diff;              // physCov / insertSize difference array (PileUpRegion.scala:62-88)
     // events
     EventKey* ev_key; Event* ev; uint32_t ev_cap;

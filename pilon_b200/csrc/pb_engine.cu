@@ -72,7 +72,8 @@ struct pb_engine {
     std::vector<HostBatch> batches;
     DBuf d_batches, d_pile;          // DevBatch[] image; PileBatch[] image (only for > PB_MAXB batches)
     // per-locus buffers
-    DBuf ref, rare, gplane[2], rare_bits, pc_diff, block_sums, scalars;
+    DBuf ref, rare, gplane[2], rare_bits, pc_diff, block_sums, scalars, extra, head;
+    const uint8_t* contig_host = nullptr;   // the caller's contig (valid until pb_region_finish): head upload of long-read regions
     DBuf o_cnt, o_qs, o_i32[12], o_wq, o_wmq, o_flags, o_call;
     // event buffers
     DBuf ev_key, ev, perm, sort_buf, groups, cand, work, spill_scratch, str_pool, cub_tmp;
@@ -151,7 +152,7 @@ extern "C" int pb_destroy(pb_engine* e) {
     cudaStreamSynchronize(e->stream);
     free_batches(e);
     cudaStreamSynchronize(e->stream);
-    DBuf* all[] = {&e->d_batches, &e->d_pile, &e->ref, &e->rare_bits, &e->pc_diff, &e->block_sums, &e->scalars,
+    DBuf* all[] = {&e->d_batches, &e->d_pile, &e->extra, &e->head, &e->ref, &e->rare_bits, &e->pc_diff, &e->block_sums, &e->scalars,
                    &e->o_cnt, &e->o_qs, &e->o_wq, &e->o_wmq, &e->o_flags, &e->o_call, &e->ev_key, &e->ev, &e->perm,
                    &e->groups, &e->cand, &e->work, &e->spill_scratch, &e->str_pool, &e->cub_tmp};
     for (DBuf* b : all) b->release();
@@ -186,6 +187,8 @@ extern "C" int pb_region_begin(pb_engine* e, const uint8_t* contig, int64_t cont
     CK(e->ref.ensure(ref_bytes + 8, false, s));                                     // k_rebuild_bases reads whole words
     CK(cudaMemcpyAsync(e->ref.p, contig + (R.ref_locus0 - 1), ref_bytes, cudaMemcpyHostToDevice, s));
     R.ref = e->ref.as<uint8_t>();
+    R.contig_len = contig_len; R.extra = nullptr; R.head = nullptr; R.head_len = 0;
+    e->contig_host = contig;
     if (e->unverified && e->scalars.p) {              // asynchronous passes since the last read-back: did one of them raise a flag?
         CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -407,12 +410,12 @@ __global__ void __launch_bounds__(256) k_unpack_quals3(const uint32_t* __restric
     out[2 * i + 1] = make_uint4(four((w1 >> 16) & 0xFFFu), four(__funnelshift_r(w1, w2, 28) & 0xFFFu), four((w2 >> 8) & 0xFFFu), four((w2 >> 20) & 0xFFFu));
 }
 
-static int stage_batch(pb_engine* e, const pb_batch* b, int frag);
+static int stage_batch(pb_engine* e, const pb_batch* b, int frag, int long_read_type);
 
 extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, int long_read_type) {
     if (!e || !b) return fail(PB_ERR_INVALID, "null argument");
     if (!e->in_region) return fail(PB_ERR_INVALID, "pb_region_begin has not been called");
-    if (long_read_type != 0) return fail(PB_ERR_UNSUPPORTED, "long-read branches (PileUpRegion.scala:120-134,160,180,190) are gated off");
+    if (long_read_type < 0 || long_read_type > 2) return fail(PB_ERR_INVALID, "long_read_type must be 0, 1 (nanopore) or 2 (pacbio)");
     if (b->n_seq >= (1ll << 32) || (b->n_seq & 3)) return fail(PB_ERR_INVALID, "n_seq must be a multiple of 4 and < 2^32");
     if (b->n_cigar >= (1ll << 32) || b->n_reads >= (1ll << 31)) return fail(PB_ERR_INVALID, "batch too large");
     if (b->n_reads < 0 || b->n_cigar < 0 || b->n_seq < 0 || b->n_exc < 0) return fail(PB_ERR_INVALID, "negative count in pb_batch");
@@ -430,7 +433,7 @@ extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, in
     drop_graph(e);                                   // the captured pass belongs to the previous batch set
     // every argument has been validated: from here on only CUDA calls can fail, and then the half-staged batch is withdrawn
     e->batches.emplace_back();
-    const int rc_stage = stage_batch(e, b, frag);
+    const int rc_stage = stage_batch(e, b, frag, long_read_type);
     if (rc_stage != PB_OK) {
         for (void* p : e->batches.back().owned) cudaFreeAsync(p, e->stream);
         e->batches.pop_back();
@@ -438,11 +441,26 @@ extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, in
     return rc_stage;
 }
 
-static int stage_batch(pb_engine* e, const pb_batch* b, int frag) {
+static int stage_batch(pb_engine* e, const pb_batch* b, int frag, int long_read_type) {
     HostBatch& hb = e->batches.back();
+    if (long_read_type != 0) {
+        // long-read batches are counted by k_long into the Extra plane (zero between regions, like the rare planes); the
+        // reference's homoRun / nanoporeExclude index the contig with REGION indices, so a region that does not start at
+        // locus 1 also needs the head of the contig on the device
+        RegionDev& R = e->R;
+        CK(e->extra.ensure((size_t)R.size * sizeof(Extra), true, e->stream));
+        R.extra = e->extra.as<Extra>();
+        if (R.start > 1 && !R.head) {
+            const size_t hl = (size_t)std::min<int64_t>(R.contig_len, R.size + 8);
+            CK(e->head.ensure(hl + 8, false, e->stream));
+            CK(cudaMemcpyAsync(e->head.p, e->contig_host, hl, cudaMemcpyHostToDevice, e->stream));
+            R.head = e->head.as<uint8_t>(); R.head_len = (int64_t)hl;
+        }
+    }
     DevBatch& d = hb.d;
     memset(&d, 0, sizeof(d));
     d.n_reads = b->n_reads; d.n_cigar = b->n_cigar; d.n_seq = b->n_seq; d.n_exc = b->n_exc; d.frag = frag ? 1 : 0;
+    d.long_read = long_read_type;
     const size_t n = (size_t)b->n_reads;
     int rc;
 #define ST(field, count) if ((rc = stage(e, hb, b->field, (size_t)(count), b->mem, &d.field)) != PB_OK) return rc
@@ -505,6 +523,7 @@ static int clean_sparse_planes(pb_engine* e) {   // a failed / abandoned pass ma
     for (auto& b : e->gplane) if (b.p) CK(cudaMemsetAsync(b.p, 0, b.cap, s));
     if (e->rare_bits.p) CK(cudaMemsetAsync(e->rare_bits.p, 0, e->rare_bits.cap, s));
     if (e->pc_diff.p) CK(cudaMemsetAsync(e->pc_diff.p, 0, e->pc_diff.cap, s));
+    if (e->extra.p) CK(cudaMemsetAsync(e->extra.p, 0, e->extra.cap, s));
     return PB_OK;
 }
 
@@ -610,7 +629,7 @@ static int compute(pb_engine* e, bool time_pileup, bool full_cap = false) {
             PileBatch& pb_ = pile[i];
             pb_.seg = d.seg; pb_.quals = d.quals; pb_.bases2 = d.bases2; pb_.win_first = d.win_first;
             pb_.n_cigar = (uint32_t)d.n_cigar; pb_.reach = d.reach;
-            pb_.flags = (d.frag ? 1u : 0u) | (d.n_reads ? 2u : 0u);
+            pb_.flags = (d.frag ? 1u : 0u) | ((d.n_reads && !d.long_read) ? 2u : 0u);     // long-read batches: k_long, not the tile kernels
             if (i < PB_MAXB) PBt.b[i] = pb_;
         }
         if (nb > PB_MAXB) {                // more BAMs than the by-value table holds: the kernel reads a device-side table
@@ -618,6 +637,10 @@ static int compute(pb_engine* e, bool time_pileup, bool full_cap = false) {
             CK(cudaMemcpyAsync(e->d_pile.p, pile.data(), sizeof(PileBatch) * (size_t)nb, cudaMemcpyHostToDevice, s));
             PBt.ext = e->d_pile.as<PileBatch>();
         }
+    }
+    for (int i = 0; i < nb; i++) {         // long-read batches: plain global-atomic accumulation, merged by the epilogue
+        const DevBatch& d = img[i];
+        if (d.long_read && d.n_cigar) { k_long<<<148 * 4, 256, 0, s>>>(R, d); e->launches++; }
     }
     if (R.exp_flags & 256) {               // knock-out: everything but the pileup kernel (what the rest of the pass costs)
     } else if (pv == 7) {

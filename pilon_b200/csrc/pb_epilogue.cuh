@@ -30,11 +30,20 @@ __device__ __forceinline__ int64_t udiv_fast(uint64_t n, uint64_t d) {      // d
 }
 
 __device__ __forceinline__ void finish_locus(const RegionDev& R, int64_t w, int lane, int32_t loc,
-                                             const uint32_t c[4], const uint64_t q[4],
+                                             const uint32_t c_in[4], const uint64_t q_in[4],
                                              uint32_t mqS, uint32_t qS, uint32_t bp, uint32_t fragN,
                                              uint32_t rb, uint8_t refb, int2 rc_md = make_int2(-1, 0)) {
     // rc_md = the region's {read count, minDepth} (k_fold's device scalars) when the caller already holds them
     const bool inr = loc < R.size;
+    uint32_t c[4] = {c_in[0], c_in[1], c_in[2], c_in[3]}; uint64_t q[4] = {q_in[0], q_in[1], q_in[2], q_in[3]};
+    if (R.extra != nullptr && inr) {             // (kernel-uniform) the region has long-read batches: add what k_long counted
+        Extra* xp = &R.extra[loc];
+        const Extra x = *xp;
+#pragma unroll
+        for (int b = 0; b < 4; b++) { c[b] += x.cnt[b]; q[b] += x.qs[b]; }
+        mqS += x.mq; qS += x.q; bp += x.bp; fragN += x.frag;
+        if (x.cnt[0] | x.cnt[1] | x.cnt[2] | x.cnt[3] | x.bp) *xp = Extra{};               // self-cleaning, like the rare plane
+    }
     int32_t r_ins = 0, r_insq = 0, r_del = 0, r_delq = 0, r_q = 0, r_mq = 0, r_clips = 0, r_delfrag = 0;
     uint32_t gi = 0, gd = 0;
     if (inr && ((rb >> lane) & 1) && !(R.exp_flags & 32)) {

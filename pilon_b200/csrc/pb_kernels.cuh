@@ -54,6 +54,25 @@ __device__ __forceinline__ int2 pc_unpack(int2 d) { d.y += d.x < 0 ? 1 : 0; retu
 
 __device__ __forceinline__ uint64_t fnv64(uint64_t h, uint8_t b) { return (h ^ b) * 1099511628211ull; }
 
+// ---- long-read helpers (PileUpRegion.scala:120-134).  Both index `refBases` -- the whole contig, 0-based -- with whatever
+// the caller passes: a 1-based locus for insertions (:160), a REGION index for deletions and aligned bases (:180-181,190).
+// They are restated with the same argument, so a region that does not start at locus 1 sees the same (odd) bases. ----
+__device__ __forceinline__ uint8_t contig_at(const RegionDev& R, int64_t i0) {          // refBases(i0); 0 outside the contig
+    if (i0 < 0 || i0 >= R.contig_len) return 0;
+    if (i0 < R.head_len) return R.head[i0];
+    const int64_t locus = i0 + 1;
+    return (locus >= R.ref_locus0 && locus <= R.ref_end) ? R.ref[locus - R.ref_locus0] : 0;
+}
+__device__ __forceinline__ bool homo_run_ge4(const RegionDev& R, int64_t i0) {          // homoRun(i0) >= 4  (:120-126)
+    if (i0 < 0 || i0 + 3 >= R.contig_len) return false;       // fewer than four bases left: the run cannot reach 4 (i0 outside: JVM AIOOBE)
+    const uint8_t b = contig_at(R, i0);
+    return contig_at(R, i0 + 1) == b && contig_at(R, i0 + 2) == b && contig_at(R, i0 + 3) == b;
+}
+__device__ __forceinline__ bool nanopore_exclude(const RegionDev& R, int64_t i0) {      // :128-134
+    return i0 - 2 >= 0 && i0 + 2 < R.size &&                    // inRegion(locus(i0 - 2)) && inRegion(locus(i0 + 2))
+           contig_at(R, i0 - 2) == 'C' && contig_at(R, i0 - 1) == 'C' && contig_at(R, i0 + 1) == 'G' && contig_at(R, i0 + 2) == 'G';
+}
+
 // number of 32-locus windows that start at or before `pos` (index into win_first)
 __device__ __forceinline__ int64_t kmin_of(const RegionDev& R, int32_t pos) {
     const int64_t d = (int64_t)pos - R.start;
@@ -241,7 +260,8 @@ __global__ void __launch_bounds__(128) k_indel(RegionDev R, const DevBatch* __re
         int64_t clipped = 0;
         for (uint32_t kk = c0; kk < c1; kk++) { const uint32_t e = B.cigar[kk]; if ((e & 15) == 4) clipped += e >> 4; }
         const int32_t adjMq = roundDivI(wrap32((int64_t)mq * (length - clipped)), length);       // :141
-        const int32_t indelMq = adjMq;                                                           // :142 (longRead == 0)
+        const int longRead = B.long_read;
+        const int32_t indelMq = longRead > 0 ? (adjMq < 8 ? adjMq : 8) : adjMq;                  // :142
         const uint32_t segw = (uint32_t)((adjMq + 1) & 0xFFFF) | (hasq ? SEG_HASQ : 0u);
         const int64_t tlo = cfg.flank, thi = (int64_t)length - cfg.flank;
         const uint32_t e = B.cigar[k]; const int op = e & 15; const int64_t len = e >> 4;
@@ -258,6 +278,7 @@ __global__ void __launch_bounds__(128) k_indel(RegionDev R, const DevBatch* __re
                         if (iloc < R.start) { dropped = true; break; }        // JVM: AIOOBE at pileups(index(iloc))
                     }
                     if (dropped) drop++;
+                    else if (longRead > 0 && homo_run_ge4(R, iloc)) {}         // :160 (homoRun is handed the LOCUS as an index)
                     else {
                         const int64_t i = iloc - R.start;
                         uint8_t b0, q0; read_base(B, src, &b0, &q0);
@@ -303,12 +324,15 @@ __global__ void __launch_bounds__(128) k_indel(RegionDev R, const DevBatch* __re
                         int64_t a = rloc > tlo ? rloc : tlo, b = readOffset < thi ? readOffset : thi;
                         if (b > a) {
                             sg.loc0 = (int32_t)(a + (locus + len - readOffset) - R.start); sg.len = (int32_t)(b - a);
-                            sg.src = seq0 + (uint32_t)a; sg.w = segw | SEG_VALID;
+                            sg.src = seq0 + (uint32_t)a; sg.w = segw | SEG_VALID | SEG_READD;
                             atomicAdd(&R.batch_bc[batch_id * BC_SPREAD + (wi & (BC_SPREAD - 1))], (unsigned long long)sg.len);   // :43 (rare)
                         }
                         const int64_t i = dloc - R.start;
+                        // :180-181: long reads drop deletions in homopolymers (and, nanopore, at CC.GG motifs)
+                        const bool lr_skip = longRead > 0 && (homo_run_ge4(R, i) || (longRead == 1 && nanopore_exclude(R, i)));
                         uint8_t b0, q0; read_base(B, seq0 + (uint32_t)readOffset, &b0, &q0);
                         const int qual = hasq ? (int)(int8_t)q0 : (int)(int8_t)cfg.default_qual;
+                        if (!lr_skip) {
                         atomicAdd(&R.rare[i].mq, indelMq + 1);                   // PileUp.addDeletion, PileUp.scala:107-114
                         atomicAdd(&R.rare[i].delq, indelMq + 1);
                         atomicAdd(&R.rare[i].q, qual);
@@ -321,6 +345,7 @@ __global__ void __launch_bounds__(128) k_indel(RegionDev R, const DevBatch* __re
                             Event ev; ev.src = 0; ev.len = (uint32_t)len; ev.rot = 0; ev.batch = batch_id;
                             R.ev[ei] = ev;
                         } else atomicOr(&R.sc->error, 2);
+                        }
                     }
                 }
             }
@@ -338,6 +363,47 @@ __global__ void __launch_bounds__(128) k_indel(RegionDev R, const DevBatch* __re
     }
     // few threads: plain atomics into the slots that the last k_fold folds
     if (drop) atomicAdd(&R.slots[threadIdx.x & (SC_SLOTS - 1)].dropped_oob, drop);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_long: the aligned bases of a LONG-READ batch (PileUpRegion.scala:184-193 with longRead > 0), warp per segment, lane per
+// base, global atomics into the Extra plane.  Not a hot path: no BASELINE config has long reads; it exists so that
+// --nanopore / --pacbio inputs are served instead of refused.  Nanopore: the quality of a base that lands on a CC.GG motif
+// (nanoporeExclude, region-index quirk included) counts as 0 (:190).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_long(RegionDev R, DevBatch B) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int min_qual = R.cfg.min_qual;
+    for (int64_t s = warp0; s < B.n_cigar; s += nwarps) {
+        const Seg sg = B.seg[s];
+        if (sg.len <= 0) continue;
+        const bool valid = sg.w & SEG_VALID, hasq = sg.w & SEG_HASQ;
+        const uint32_t mq1 = sg.w & 0xFFFFu;
+        for (int32_t j = lane; j < sg.len; j += 32) {
+            const int64_t i = (int64_t)sg.loc0 + j;
+            Extra& X = R.extra[i];
+            if (!valid) { atomicAdd(&X.bp, 1u); continue; }                                   // PileUpRegion.scala:45
+            const uint32_t idx = sg.src + (uint32_t)j;
+            const uint8_t qb = B.quals[idx];
+            const bool zeroed = B.long_read == 1 && !(sg.w & SEG_READD) && nanopore_exclude(R, i);    // :190: the quality counts as 0
+            uint32_t code = (B.bases2[idx >> 2] >> (2 * (idx & 3))) & 3u;
+            int q = hasq ? (int)qb : R.cfg.default_qual;
+            if (qb & 0x80) {
+                // marked uncountable: not A C G T (PileUp.scala:46-52), or a quality byte the JVM reads as negative (:77).  The
+                // second kind counts after all when the motif rule replaces its quality by 0
+                if (!zeroed) continue;
+                uint8_t letter, qraw; read_base(B, idx, &letter, &qraw);
+                if (letter == 'A') code = 0; else if (letter == 'C') code = 1; else if (letter == 'G') code = 2; else if (letter == 'T') code = 3; else continue;
+            }
+            if (zeroed) q = 0;
+            if (q < min_qual) continue;                                                       // PileUp.scala:77
+            atomicAdd(&X.cnt[code], 1u);
+            atomicAdd(&X.qs[code], (unsigned long long)((uint32_t)q * mq1));
+            atomicAdd(&X.mq, mq1); atomicAdd(&X.q, (uint32_t)q);
+            if (B.frag) atomicAdd(&X.frag, 1u);
+        }
+    }
 }
 
 // region coverage and minDepth (PileUpRegion.scala:36; GenomeRegion.scala:221-224)

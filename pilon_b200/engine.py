@@ -94,11 +94,12 @@ class Engine:
     def run_region(self, contig: bytes, start: int, stop: int, batches: Sequence[Tuple[ReadBatch, bool]],
                    planes: Optional[Sequence[str]] = None, indels_cap: int = 1 << 16,
                    bytes_cap: int = 1 << 20, pinned: bool = False):
-        """begin + add every (batch, counts_toward_frag_coverage) + finish."""
+        """begin + add every (batch, counts_toward_frag_coverage[, longReadType]) + finish."""
         self.region_begin(contig, start, stop)
         inserts = []
-        for rb, frag in batches:
-            self.add_batch(rb, frag)
+        for bt in batches:
+            rb, frag, long_read = bt if len(bt) == 3 else (bt[0], bt[1], 0)
+            self.add_batch(rb, frag, long_read)
             inserts.append(np.zeros(rb.n_reads, np.int32))
         res = ResultBuffers(stop + 1 - start, planes, indels_cap, bytes_cap, pinned)
         self.finish(res, inserts)
@@ -288,8 +289,7 @@ class PileUpRegion:
 
     def addRead(self, r, refBases=None, longRead: int = 0) -> int:
         """Buffers the record; returns what the reference returns (physCovIncr, PileUpRegion.scala:62-88)."""
-        if longRead:
-            raise capi.EngineError(capi.PB_ERR_UNSUPPORTED, "long-read branches are gated off")
+        self._pending_long = longRead                            # BamFile.longReadType: one value per BAM
         self._pending.append(r)
         valid = (r.mapq >= self.config.minMq) and ((not r.paired) or (r.proper and r.mate_same_ref))
         if (not valid) or (r.paired and r.tlen <= 0):
@@ -303,7 +303,7 @@ class PileUpRegion:
     def endBam(self, countsTowardFragCoverage: bool = True):
         """Marks the end of one BAM's reads (GenomeRegion.processBam, GenomeRegion.scala:287-300)."""
         if self._pending:
-            self._batches.append((pack_records(self._pending), countsTowardFragCoverage))
+            self._batches.append((pack_records(self._pending), countsTowardFragCoverage, getattr(self, "_pending_long", 0)))
             self._pending = []
 
     def addBatch(self, batch: ReadBatch, countsTowardFragCoverage: bool = True):
@@ -313,10 +313,10 @@ class PileUpRegion:
     def postProcess(self, planes: Optional[Sequence[str]] = None):
         """PileUpRegion.postProcess + GenomeRegion.postProcess pass 1 on the GPU."""
         self.endBam()
-        n_ops = sum(int(b.cigar.shape[0]) for b, _ in self._batches)
+        n_ops = sum(int(b[0].cigar.shape[0]) for b in self._batches)
         self.result, self.insertSizes = self.engine.run_region(
             self.contigBases, self.start, self.stop, self._batches, planes,
-            indels_cap=max(16, n_ops), bytes_cap=max(1024, sum(int(b.quals.shape[0]) for b, _ in self._batches)))
+            indels_cap=max(16, n_ops), bytes_cap=max(1024, sum(int(b[0].quals.shape[0]) for b in self._batches)))
         self._indel_map = {(e["locus_index"], e["kind"]): e for e in self.result.indels()}
         self._batches = []
 

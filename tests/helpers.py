@@ -52,10 +52,11 @@ def run_c_oracle(contig: bytes, start: int, stop: int, batches: Sequence[Tuple[R
     reg = lib.po_region_new(C.byref(ccfg), cbuf.ctypes.data, len(contig), start, stop)
     inserts = []
     try:
-        for rb, frag in batches:
+        for bt in batches:
+            rb, frag, long_read = bt if len(bt) == 3 else (bt[0], bt[1], 0)
             cb = rb.to_c()
             ins = np.zeros(rb.n_reads, np.int32)
-            rc = lib.po_region_add_batch(reg, C.byref(cb), int(frag), 0, ins.ctypes.data)
+            rc = lib.po_region_add_batch(reg, C.byref(cb), int(frag), int(long_read), ins.ctypes.data)
             assert rc == 0
             inserts.append(ins)
         res = ResultBuffers(stop + 1 - start, indels_cap=indels_cap, indel_bytes_cap=bytes_cap)
@@ -73,8 +74,9 @@ def run_py_oracle(contig: bytes, start: int, stop: int, batches: Sequence[Tuple[
     cfg = cfg or po.Config()
     gr = po.GenomeRegionHot(contig, start, stop, cfg)
     gr.initializePileUps(oob_drop=oob_drop)
-    for reads, frag in batches:
-        gr.processBam(reads, "frags" if frag else "jumps")
+    for bt in batches:
+        reads, frag, long_read = bt if len(bt) == 3 else (bt[0], bt[1], 0)
+        gr.processBam(reads, "frags" if frag else "jumps", long_read)
     gr.postProcess()
     pur = gr.pileUpRegion
     S = gr.size

@@ -363,3 +363,30 @@ def test_base_delta_transport_matches_byte_transport(engine, seed):
     engine.finish(res, ins)
     H.assert_results_equal(res, ref, "base-delta transport vs C oracle")
     assert np.array_equal(ins[0], ins_ref[0])
+
+
+@pytest.mark.parametrize("seed,long_read", [(s, 1 + s % 2) for s in range(10)])
+def test_long_read_batches_match_both_oracles(engine, seed, long_read):
+    """--nanopore / --pacbio batches (BamFile.longReadType 1 / 2) beside a short-read batch in the same region: k_long
+    accumulates them, the tile kernels the rest, the epilogue merges both (PileUpRegion.scala:120-134,142,160,180-181,190)."""
+    rng = random.Random(1000 + seed)
+    contig = bytearray(H.random_contig(rng, 900))
+    for _ in range(14):
+        p = rng.randrange(2, 890)
+        contig[p:p + 5] = b"CC" + bytes([rng.choice(b"ACGT")]) + b"GG"
+    contig = bytes(contig)
+    start = 1 if seed % 3 == 0 else rng.randint(2, 150)
+    stop = rng.randint(600, 900)
+    reads = [H.random_read(rng, contig, max(1, start - 40), min(900, stop + 20), max_len=150) for _ in range(400)]
+    reads += H.planted_indel_cluster(rng, contig, start, stop) + H.planted_snp_cluster(rng, contig, start, stop)
+    reads.sort(key=lambda r: r.pos)
+    groups = [([r for i, r in enumerate(reads) if i % 3 == 0], True, 0), ([r for i, r in enumerate(reads) if i % 3 == 1], False, long_read),
+              ([r for i, r in enumerate(reads) if i % 3 == 2], True, long_read)]
+    packed = [(pack_records(g), f, lr) for g, f, lr in groups]
+    res, ins = engine.run_region(contig, start, stop, packed)
+    ref, ins_ref = H.run_c_oracle(contig, start, stop, packed)
+    H.assert_results_equal(res, ref, "long reads, engine vs C oracle")
+    H.assert_matches_py(res, ins, H.run_py_oracle(contig, start, stop, groups), "long reads, engine vs python oracle")
+    # and the engine is clean afterwards: a plain short-read region on the same handle
+    c2, s2, e2, r2 = H.random_case(seed, contig_len=500, n_reads=150)
+    run_both(engine, c2, s2, e2, [(r2, True)])

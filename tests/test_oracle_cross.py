@@ -60,3 +60,27 @@ def test_c_oracle_matches_python_oracle_on_a_wide_region():
     for k in (0, 1, 2):
         assert (((fl & 2) != 0) & (kind == k)).any()
     assert (fl & 8).any() and (fl & 4).any()
+
+
+@pytest.mark.parametrize("seed,long_read", [(s, 1 + s % 2) for s in range(16)])
+def test_long_read_branches_c_oracle_matches_python_oracle(seed, long_read):
+    """--nanopore (1) / --pacbio (2): indelMq capped at 8, insertions / deletions in homopolymers dropped, nanopore CC.GG
+    motifs (PileUpRegion.scala:120-134,142,160,180-181,190), including the reference's habit of indexing the contig with
+    REGION indices there -- visible whenever the region does not start at locus 1."""
+    rng = random.Random(1000 + seed)
+    contig = bytearray(H.random_contig(rng, 700))
+    for _ in range(12):                                   # plant CC.GG motifs
+        p = rng.randrange(2, 690)
+        contig[p:p + 5] = b"CC" + bytes([rng.choice(b"ACGT")]) + b"GG"
+    contig = bytes(contig)
+    start = 1 if seed % 3 == 0 else rng.randint(2, 150)
+    stop = rng.randint(500, 700)
+    reads = [H.random_read(rng, contig, max(1, start - 40), min(700, stop + 20)) for _ in range(260)]
+    reads += H.planted_indel_cluster(rng, contig, start, stop)
+    reads.sort(key=lambda r: r.pos)
+    short = [r for i, r in enumerate(reads) if i % 3 == 0]
+    longs = [r for i, r in enumerate(reads) if i % 3 != 0]
+    groups = [(short, True, 0), (longs, True, long_read)]
+    py = H.run_py_oracle(contig, start, stop, groups)
+    res, ins = H.run_c_oracle(contig, start, stop, [(pack_records(g), f, lr) for g, f, lr in groups])
+    H.assert_matches_py(res, ins, py, "long read %d seed %d" % (long_read, seed))
