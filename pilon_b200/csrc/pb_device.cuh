@@ -79,7 +79,7 @@ struct DevBatch {
 // k_prep spreads its per-warp partial sums over SC_SLOTS slots (same-address L2 atomics serialise);
 // k_scalars folds them into the Scalars block.
 static constexpr int SC_SLOTS = 64;
-static constexpr int BC_SPREAD = 8;      // partial sums per batch of the region baseCount (RegionDev.batch_bc)
+static constexpr int BC_SPREAD = 64;     // partial sums per batch of the region baseCount (RegionDev.batch_bc): same-address atomics serialise (8 slots cost k_prep 2x)
 struct ScalarSlot { unsigned long long aligned_bases; int read_count, unknown_ops, dropped_oob; unsigned n_work; int fwd[8], back[8]; };
 
 struct Scalars {
