@@ -62,6 +62,7 @@ struct Bgzf {
         }
         if (bsize < 0) return false;
         const size_t csize = (size_t)bsize + 1;
+        if (csize < 12 + (size_t)xlen + 8) return false;                 // corrupt block header
         const size_t data_len = csize - 12 - xlen - 8;
         std::vector<uint8_t> cdata(data_len + 8);
         if (xlen <= 6) {                                     // part of the payload may already sit in hdr (never: xlen == 6 exactly)
@@ -69,6 +70,7 @@ struct Bgzf {
         }
         if (fread(cdata.data(), 1, data_len + 8, f) != data_len + 8) return false;
         const uint32_t isize = rd32(cdata.data() + data_len + 4);
+        if (isize > 65536u) return false;                                // a BGZF block inflates to at most 64 KiB
         block.resize(isize);
         if (isize) {
             z_stream zs; memset(&zs, 0, sizeof zs);
@@ -180,6 +182,7 @@ extern "C" int pb_bam_open(const char* bam_path, const char* bai_path, pb_bam** 
     auto bad = [&](const char* m) { fclose(b->z.f); delete b; return fail_bam(PB_ERR_INVALID, std::string(bam_path) + ": " + m); };
     if (!b->z.load(0) || !b->z.read(w, 8, &err) || memcmp(w, "BAM\1", 4) != 0) return bad("not a BAM file");
     const uint32_t l_text = rd32(w + 4);
+    if (l_text > (1u << 30)) return bad("implausible header length");
     std::vector<uint8_t> text(l_text);
     if (l_text && !b->z.read(text.data(), l_text, &err)) return bad("truncated header");
     if (!b->z.read(w, 4, &err)) return bad("truncated header");
@@ -187,6 +190,7 @@ extern "C" int pb_bam_open(const char* bam_path, const char* bai_path, pb_bam** 
     for (uint32_t i = 0; i < n_ref; i++) {
         if (!b->z.read(w, 4, &err)) return bad("truncated reference list");
         const uint32_t l_name = rd32(w);
+        if (l_name > (1u << 16)) return bad("implausible reference name length");
         std::vector<uint8_t> nm(l_name + 4);
         if (!b->z.read(nm.data(), l_name + 4, &err)) return bad("truncated reference list");
         b->ref_names.emplace_back(reinterpret_cast<const char*>(nm.data()), l_name ? l_name - 1 : 0);
@@ -252,7 +256,7 @@ extern "C" int pb_bam_query_pack(pb_bam* b, int32_t ref_id, int32_t start, int32
     uint8_t w4[4];
     while (b->z.read(w4, 4, &err)) {
         const uint32_t bs = rd32(w4);
-        if (bs < 32) return fail_bam(PB_ERR_INVALID, "corrupt BAM record");
+        if (bs < 32 || bs > (1u << 28)) return fail_bam(PB_ERR_INVALID, "corrupt BAM record");
         b->rec.resize(bs);
         if (!b->z.read(b->rec.data(), bs, &err)) return fail_bam(PB_ERR_INVALID, "truncated BAM record");
         const uint8_t* r = b->rec.data();

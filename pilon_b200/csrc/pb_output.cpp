@@ -298,6 +298,8 @@ extern "C" int pb_out_create(const pb_region_result* res, const uint8_t* contig,
     if (!res->flags || !res->call) return fail_out(PB_ERR_INVALID, "the result must carry the flags and call planes");
     if (res->n_indels > res->indels_cap || res->n_indel_bytes > res->indel_bytes_cap)
         return fail_out(PB_ERR_INVALID, "the result's indel evidence was truncated (indels_cap / indel_bytes_cap too small)");
+    if (res->n_indels > 0 && (!res->indels || (res->n_indel_bytes > 0 && !res->indel_bytes)))
+        return fail_out(PB_ERR_INVALID, "the result must carry the indel evidence (indels, indel_bytes): insertion / deletion fixes need the strings");
     pb_region_out* o = new pb_region_out();
     o->res = res; o->contig = contig; o->contig_len = contig_len; o->name = name; o->start = start; o->stop = stop;
     o->size = res->size; o->cfg = *cfg;
