@@ -327,29 +327,32 @@ extern "C" int pb_out_create(const pb_region_result* res, const uint8_t* contig,
         const std::string rBase(1, o->ref_base(loc)), cBase(1, "ACGTN"[PB_CALL_BASE(call)]);
         switch (kind) {
             case PB_KIND_SNP:
-                if (cfg->fix_snps) o->snp_fixes.insert(o->snp_fixes.begin(), Fix{loc, rBase, cBase});
+                if (cfg->fix_snps) o->snp_fixes.push_back(Fix{loc, rBase, cBase});
                 st.snps++;
                 break;
             case PB_KIND_AMB:
                 if (cfg->fix_snps && !cfg->longread) {
-                    if (cfg->iupac) o->small_fixes.insert(o->small_fixes.begin(), Fix{loc, rBase, std::string(1, iupac_of(cBase[0], "ACGT"[PB_CALL_ALT(call)]))});
-                    else o->snp_fixes.insert(o->snp_fixes.begin(), Fix{loc, rBase, cBase});
+                    if (cfg->iupac) o->small_fixes.push_back(Fix{loc, rBase, std::string(1, iupac_of(cBase[0], "ACGT"[PB_CALL_ALT(call)]))});
+                    else o->snp_fixes.push_back(Fix{loc, rBase, cBase});
                     st.amb++;
                 }
                 break;
             case PB_KIND_INS: {
                 const std::string ins = o->indel_string(i, 1);
-                if (cfg->fix_indels) o->small_fixes.insert(o->small_fixes.begin(), Fix{loc, std::string(), ins});
+                if (cfg->fix_indels) o->small_fixes.push_back(Fix{loc, std::string(), ins});
                 st.ins++; st.ins_bases += (int64_t)ins.size();
                 break;
             }
             default: {
                 const std::string del = o->indel_string(i, 2);
-                if (cfg->fix_indels) o->small_fixes.insert(o->small_fixes.begin(), Fix{loc, del, std::string()});
+                if (cfg->fix_indels) o->small_fixes.push_back(Fix{loc, del, std::string()});
                 st.dels++; st.del_bases += (int64_t)del.size();
             }
         }
     }
+    // the Scala lists are built by prepending (::=): newest first
+    std::reverse(o->snp_fixes.begin(), o->snp_fixes.end());
+    std::reverse(o->small_fixes.begin(), o->small_fixes.end());
     {
         char buf[160];
         snprintf(buf, sizeof buf, "Confirmed %lld of %lld bases (%.2f%%)\n", (long long)st.confirmed, (long long)st.non_n,
