@@ -94,14 +94,18 @@ __device__ __forceinline__ void scatter_chunk(const uint4 Q, uint32_t cw, uint32
 template <bool MINQ>
 __device__ __forceinline__ uint32_t chunk_mask(const uint4 Q, uint32_t k, uint32_t src, uint32_t last, uint32_t minq_add, uint32_t nohq_pass) {
     const uint32_t lo = k == (src >> 4) ? (src & 15u) : 0u, hi = k == (last >> 4) ? (last & 15u) + 1u : 16u;
-    uint32_t v0 = ~Q.x >> 7, v1 = ~Q.y >> 7, v2 = ~Q.z >> 7, v3 = ~Q.w >> 7;
-    if (MINQ) {                                                  // reads without qualities: default_qual decides
-        v0 &= (((Q.x & 0x7F7F7F7Fu) + minq_add) >> 7) | nohq_pass; v1 &= (((Q.y & 0x7F7F7F7Fu) + minq_add) >> 7) | nohq_pass;
-        v2 &= (((Q.z & 0x7F7F7F7Fu) + minq_add) >> 7) | nohq_pass; v3 &= (((Q.w & 0x7F7F7F7Fu) + minq_add) >> 7) | nohq_pass;
+    // bit 7 of every byte = "not counted": the 0x80 mark, or (MINQ) a quality below minQual unless default_qual decides
+    uint32_t u0 = Q.x, u1 = Q.y, u2 = Q.z, u3 = Q.w;
+    if (MINQ) {
+        u0 |= ~((((Q.x & 0x7F7F7F7Fu) + minq_add) | (nohq_pass << 7))); u1 |= ~((((Q.y & 0x7F7F7F7Fu) + minq_add) | (nohq_pass << 7)));
+        u2 |= ~((((Q.z & 0x7F7F7F7Fu) + minq_add) | (nohq_pass << 7))); u3 |= ~((((Q.w & 0x7F7F7F7Fu) + minq_add) | (nohq_pass << 7)));
     }
-    const uint32_t m0 = ((v0 & 0x01010101u) * 0x01020408u) >> 24, m1 = ((v1 & 0x01010101u) * 0x01020408u) >> 24;
-    const uint32_t m2 = ((v2 & 0x01010101u) * 0x01020408u) >> 24, m3 = ((v3 & 0x01010101u) * 0x01020408u) >> 24;
-    return ((1u << hi) - 1u) & ~((1u << lo) - 1u) & ((m0 & 15u) | ((m1 & 15u) << 4) | ((m2 & 15u) << 8) | ((m3 & 15u) << 12));
+    // the four bit-7s of a word gathered into its top nibble by one multiplication (partial products never collide:
+    // bit 7 -> 28, bit 15 -> 29, bit 23 -> 30, bit 31 -> 31)
+    const uint32_t n0 = ((u0 & 0x80808080u) * 0x00204081u) >> 28, n1 = ((u1 & 0x80808080u) * 0x00204081u) >> 28;
+    const uint32_t n2 = ((u2 & 0x80808080u) * 0x00204081u) >> 28, n3 = ((u3 & 0x80808080u) * 0x00204081u) >> 28;
+    const uint32_t bad = n0 | (n1 << 4) | (n2 << 8) | (n3 << 12);
+    return ((1u << hi) - 1u) & ~((1u << lo) - 1u) & ~bad;
 }
 
 // The same 16 bases for a segment whose (adjMq + 1) differs from the tile's reference value by dmq: Bq / C terms.
@@ -325,16 +329,26 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
             if (work) {
                 {
                     uint32_t sa = sA + 4u * (uint32_t)(col + (int32_t)(16u * k - src));      // A[0][locus of base 16 k] (virtual before col)
+                    // two register stages, used alternately: the loads of the next chunk are in flight while the reductions of
+                    // this one issue, and nothing is copied between the stages
+                    auto chunk = [&](const uint4& Qc, const uint32_t cwc) {
+                        const uint32_t okm = chunk_mask<MINQ>(Qc, k, src, last, minq_add, nohq_pass);
+                        if (allhq) { if (nf) scatter_chunk<true, true, T>(Qc, cwc, okm, sa, qand, qor); else scatter_chunk<false, true, T>(Qc, cwc, okm, sa, qand, qor); }
+                        else { if (nf) scatter_chunk<true, false, T>(Qc, cwc, okm, sa, qand, qor); else scatter_chunk<false, false, T>(Qc, cwc, okm, sa, qand, qor); }
+                        if (inl) scatter_chunk_dmq<T>(Qc, cwc, okm, sa, qand, qor, dmq);         // slow list full (deep pile-ups)
+                    };
+                    uint4 Q2 = make_uint4(0, 0, 0, 0); uint32_t cw2 = 0;
                     for (;;) {
-                        uint4 Qn = make_uint4(0, 0, 0, 0); uint32_t cwn = 0;
-                        const bool more = k < k1;
-                        if (more) { Qn = qp[1]; cwn = cp[1]; }                           // next chunk's loads in flight
-                        const uint32_t okm = chunk_mask<MINQ>(Q, k, src, last, minq_add, nohq_pass);
-                        if (allhq) { if (nf) scatter_chunk<true, true, T>(Q, cw, okm, sa, qand, qor); else scatter_chunk<false, true, T>(Q, cw, okm, sa, qand, qor); }
-                        else { if (nf) scatter_chunk<true, false, T>(Q, cw, okm, sa, qand, qor); else scatter_chunk<false, false, T>(Q, cw, okm, sa, qand, qor); }
-                        if (inl) scatter_chunk_dmq<T>(Q, cw, okm, sa, qand, qor, dmq);           // slow list full (deep pile-ups)
+                        bool more = k < k1;
+                        if (more) { Q2 = qp[1]; cw2 = cp[1]; }
+                        chunk(Q, cw);
                         if (!more) break;
-                        Q = Qn; cw = cwn; k++; qp++; cp++; sa += 64;
+                        k++; sa += 64;
+                        more = k < k1;
+                        if (more) { Q = qp[2]; cw = cp[2]; }
+                        chunk(Q2, cw2);
+                        if (!more) break;
+                        k++; sa += 64; qp += 2; cp += 2;
                     }
                 }
             }
