@@ -65,7 +65,8 @@ struct HostBatch {
 struct pb_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr, ev_sc = nullptr;
+    cudaStream_t stream2 = nullptr;  // side stream: the physCov scans run beside the indel / sort / group chain (fork-join inside a pass)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr, ev_sc = nullptr, ev_fork = nullptr, ev_join = nullptr;
     Cfg cfg{};
     bool in_region = false;
     RegionDev R{};
@@ -130,6 +131,9 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
     CK(cudaFuncSetAttribute(k_pileup5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_pileup5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     if (getenv("PB_PHASE_TIMING")) { e->phase_timing = true; for (auto& ev : e->ph) CK(cudaEventCreate(&ev)); }
     CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
     CK(cudaEventCreate(&e->evp0)); CK(cudaEventCreate(&e->evp1));
@@ -160,7 +164,8 @@ extern "C" int pb_destroy(pb_engine* e) {
     for (auto& b : e->o_i32) b.release();
     if (e->h_sc) cudaFreeHost(e->h_sc);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->evp0); cudaEventDestroy(e->evp1);
-    cudaEventDestroy(e->ev_sc);
+    cudaEventDestroy(e->ev_sc); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join);
+    cudaStreamDestroy(e->stream2);
     cudaStreamDestroy(e->stream);
     delete e;
     return PB_OK;
@@ -585,14 +590,29 @@ static int compute(pb_engine* e, bool time_pileup, bool full_cap = false) {
             k_prep<<<(unsigned)((d.n_reads + 127) / 128), 128, 0, s>>>(R, d, (uint32_t)i);      // also builds win_first
             e->launches += 1;
         }
-        if (i1 == nb) { k_indel<<<148 * 4, 128, 0, s>>>(R, dB); e->launches++; }     // queued I / D ops of every batch
+        if (i1 == nb) {
+            // every k_prep has run: the physCov scans only need its difference array, so they go to the side stream and
+            // run beside k_indel -> k_fold -> sort -> k_groups -> pileup (joined before the deletion spill)
+            CK(cudaEventRecord(e->ev_fork, s));
+            CK(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
+            const int nblocks = (int)((R.size + SCAN_TILE - 1) / SCAN_TILE);
+            k_scan1<<<nblocks, SCAN_THREADS, 0, e->stream2>>>(R, e->block_sums.as<uint2>());
+            k_scan2<<<1, 1024, 0, e->stream2>>>(R, e->block_sums.as<uint2>(), nblocks);
+            k_scan3<<<nblocks, SCAN_THREADS, 0, e->stream2>>>(R, e->block_sums.as<uint2>());
+            e->launches += 3;
+            CK(cudaEventRecord(e->ev_join, e->stream2));
+            k_indel<<<148 * 4, 128, 0, s>>>(R, dB); e->launches++;     // queued I / D ops of every batch
+        }
         k_fold<<<1, 32, 0, s>>>(R, reach_base + 2 * i0, i1 - i0, i1 == nb, nb); e->launches++;
     }
-    const int nblocks = (int)((R.size + SCAN_TILE - 1) / SCAN_TILE);
-    k_scan1<<<nblocks, SCAN_THREADS, 0, s>>>(R, e->block_sums.as<uint2>());
-    k_scan2<<<1, 1024, 0, s>>>(R, e->block_sums.as<uint2>(), nblocks);
-    k_scan3<<<nblocks, SCAN_THREADS, 0, s>>>(R, e->block_sums.as<uint2>());
-    e->launches += 3;
+    const bool forked = nb > 0;
+    if (!forked) {              // no batch at all: the scans still have to produce (zero) planes
+        const int nblocks = (int)((R.size + SCAN_TILE - 1) / SCAN_TILE);
+        k_scan1<<<nblocks, SCAN_THREADS, 0, s>>>(R, e->block_sums.as<uint2>());
+        k_scan2<<<1, 1024, 0, s>>>(R, e->block_sums.as<uint2>(), nblocks);
+        k_scan3<<<nblocks, SCAN_THREADS, 0, s>>>(R, e->block_sums.as<uint2>());
+        e->launches += 3;
+    }
     if (evcap) {
         // events -> (locus, kind) groups: radix sort of `evcap` 32-bit keys (the unused slots carry the largest key), k_groups
         uint32_t* keys_in = e->sort_buf.as<uint32_t>();
@@ -656,6 +676,7 @@ static int compute(pb_engine* e, bool time_pileup, bool full_cap = false) {
     }
     e->launches++;
     if (time_pileup) CK(cudaEventRecord(e->evp1, s));
+    if (forked) CK(cudaStreamWaitEvent(s, e->ev_join, 0));          // join: the scans are part of the pass
     // deletion spill: candidates are bounded by the number of deletion groups
     uint32_t p2 = 1; while (p2 < evcap) p2 <<= 1;
     CK(e->spill_scratch.ensure((size_t)p2 * sizeof(int4) + 16, false, s));
@@ -712,22 +733,40 @@ extern "C" int pb_region_compute_timed(pb_engine* e, int iters, float* total_ms,
     CK(cudaSetDevice(e->device));
     const int64_t l0 = e->launches;
     float tot = 0.f, pil = 0.f;
+    static const bool use_graph = getenv("PB_NOGRAPH") == nullptr && getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") == nullptr;
+    auto check_pass = [&]() -> int {
+        CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->unverified = false;
+        if (e->h_sc->error) { e->dirty = true; return pass_error((uint32_t)e->h_sc->error); }
+        return PB_OK;
+    };
     for (int it = 0; it < iters; it++) {
+        // (1) plain launches with events around the pileup kernel (events recorded inside a captured graph cannot be
+        // timed): the kernel's own duration, and the pass's when no graph is in use
         CK(cudaEventRecord(e->ev0, e->stream));
         int rc = compute(e, true);
         if (rc != PB_OK) return rc;
-        // leave the sparse group planes clean for the next iteration
-        CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaStreamSynchronize(e->stream));
-        if (e->h_sc->error) return pass_error((uint32_t)e->h_sc->error);
-        if (e->h_sc->n_groups) { k_groups_clear<<<(e->h_sc->n_groups + 127) / 128, 128, 0, e->stream>>>(e->R, e->h_sc->n_groups); e->launches++; }
+        k_groups_clear_dev<<<64, 128, 0, e->stream>>>(e->R); e->launches++;
         CK(cudaEventRecord(e->ev1, e->stream));
-        CK(cudaEventSynchronize(e->ev1));
+        if ((rc = check_pass()) != PB_OK) return rc;
+        e->dirty = false;
         float a = 0, b = 0;
         CK(cudaEventElapsedTime(&a, e->ev0, e->ev1));
         CK(cudaEventElapsedTime(&b, e->evp0, e->evp1));
-        tot += a; pil += b;
-        e->dirty = false;
+        pil += b;
+        // (2) the pass the way pb_region_compute runs it -- replayed as one CUDA graph once it has been captured: its duration
+        if (use_graph) {
+            while (e->graph_state < 2) { if ((rc = pb_region_compute(e)) != PB_OK) return rc; if ((rc = check_pass()) != PB_OK) return rc; }
+            if (e->graph_state == 2) {
+                CK(cudaEventRecord(e->ev0, e->stream));
+                if ((rc = pb_region_compute(e)) != PB_OK) return rc;
+                CK(cudaEventRecord(e->ev1, e->stream));
+                if ((rc = check_pass()) != PB_OK) return rc;
+                CK(cudaEventElapsedTime(&a, e->ev0, e->ev1));
+            }
+        }
+        tot += a;
     }
     if (total_ms) *total_ms = tot;
     if (pileup_ms) *pileup_ms = pil;
