@@ -56,7 +56,8 @@ struct PileBatch {
 };
 static constexpr int PB_MAXB = 20;
 // `ext` != nullptr (more than PB_MAXB batches): the table lives in device memory instead
-struct PileBatches { int32_t n; int32_t pad; const PileBatch* ext; PileBatch b[PB_MAXB]; };
+// `spread` (scatter kernels): a grab takes every ng-th descriptor of the position-sorted list instead of 16 neighbours (deep pile-ups)
+struct PileBatches { int32_t n; int32_t spread; const PileBatch* ext; PileBatch b[PB_MAXB]; };
 __device__ __forceinline__ const PileBatch& pile_batch(const PileBatches& PB, int i) { return PB.ext ? PB.ext[i] : PB.b[i]; }
 
 struct DevBatch {

@@ -15,6 +15,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "pb_pileup7.cuh"
+#include "pb_pileup7c.cuh"
 
 using namespace pb;
 
@@ -90,6 +91,10 @@ struct pb_engine {
     std::vector<DevBatch> img_host;  // image of the batch table; a captured H2D copy reads it at every replay
     // PB_PHASE_TIMING=1 (diagnostics): device time of upload / pass / download per region, printed by pb_destroy
     bool phase_timing = false; cudaEvent_t ph[4] = {}; double ph_ms[3] = {0, 0, 0}; int64_t ph_regions = 0;
+    int ctile = P7C_TILE;            // tile of the cluster scatter kernel (PB_CTILE: A/B runs)
+    int spread_order = -1;           // -1 = by depth
+    int64_t deep_depth = 1000;       // mean depth above which a region goes to the cluster scatter kernel ...
+    int64_t spread_depth = 1000;     // ... and above which a grab spreads its descriptors over the tile (measured: profiles/README.md, r2q)
     int pileup_version = 0;          // 0 = choose per region (k_pileup7 scatter / k_pileup5 gather); PB_PILEUP=5 or 7 forces one (A/B runs)
     std::vector<PileBatch> pile_host; // image of the pileup kernels' batch table (device-side copy when there are more than PB_MAXB batches)
 };
@@ -124,10 +129,17 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
     e->cfg.min_qual = c->min_qual; e->cfg.min_mq = c->min_mq; e->cfg.flank = c->flank;
     e->cfg.default_qual = c->default_qual; e->cfg.min_min_depth = c->min_min_depth;
     e->cfg.old_indel = c->old_indel; e->cfg.fix_amb = c->fix_amb; e->cfg.min_depth = c->min_depth;
-    if (const char* v = getenv("PB_PILEUP")) { const int pv = atoi(v); if (pv == 5 || pv == 7) e->pileup_version = pv; }
+    if (const char* v = getenv("PB_SPREAD")) e->spread_order = atoi(v);           // A/B runs: 0 / 1 forces the descriptor order of a grab
+    if (const char* v = getenv("PB_DEEP")) e->deep_depth = atoi(v);
+    if (const char* v = getenv("PB_PILEUP")) { const int pv = atoi(v); if (pv == 5 || pv == 7 || pv == 8) e->pileup_version = pv; }
     CK(cudaFuncSetAttribute(k_pileup7<false, P7_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile7<P7_TILE>)));
     CK(cudaFuncSetAttribute(k_pileup7<true, P7_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile7<P7_TILE>)));
 
+    CK(cudaFuncSetAttribute(k_pileup7c<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile7c<512>)));
+    CK(cudaFuncSetAttribute(k_pileup7c<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile7c<512>)));
+    CK(cudaFuncSetAttribute(k_pileup7c<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile7c<1024>)));
+    CK(cudaFuncSetAttribute(k_pileup7c<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile7c<1024>)));
+    if (const char* v = getenv("PB_CTILE")) e->ctile = atoi(v) == 1024 ? 1024 : 512;
     CK(cudaFuncSetAttribute(k_pileup5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_pileup5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -631,16 +643,18 @@ static int compute(pb_engine* e, bool time_pileup, bool full_cap = false) {
     }
     if (const char* xf = getenv("PB_EXP")) R.exp_flags = atoi(xf);
     if (time_pileup) CK(cudaEventRecord(e->evp0, s));
-    // The scatter kernel needs enough 2048-locus tiles to fill the GPU and shallow enough pile-ups that its 12-bit tile
-    // counters rarely fold; deep, narrow regions (amplicons, BASELINE config 5) go to the gather kernel.
+    // Three formulations of the same arithmetic: pile-ups deeper than ~1000x go to the cluster scatter kernel
+    // (wide counters in shared memory, a cluster per 512-locus tile); shallower regions with enough 2048-locus tiles to
+    // fill the GPU to the scatter kernel; narrow shallow ones to the gather kernel.
     int pv = e->pileup_version;
+    const int64_t depth = R.size > 0 ? (int64_t)(total_seq / (size_t)R.size) : 0;          // stored bases per locus: >= depth
     if (pv == 0) {
         const int64_t tiles = (R.size + P7_TILE - 1) / P7_TILE;
-        const int64_t depth = R.size > 0 ? (int64_t)(total_seq / (size_t)R.size) : 0;      // stored bases per locus: >= depth
-        pv = (tiles >= 256 && depth <= 1000) ? 7 : 5;
+        pv = depth > e->deep_depth ? 8 : tiles >= 256 ? 7 : 5;
     }
-    if (pv == 7 && nb > PB_MAXB) pv = 5;   // the scatter kernel keeps its per-batch cursors in shared memory: <= PB_MAXB batches
+    if ((pv == 7 || pv == 8) && nb > PB_MAXB) pv = 5;   // the scatter kernels keep their per-batch cursors in shared memory: <= PB_MAXB batches
     PileBatches PBt; memset(&PBt, 0, sizeof(PBt)); PBt.n = nb;
+    PBt.spread = e->spread_order >= 0 ? e->spread_order : (depth > e->spread_depth ? 1 : 0);
     {
         std::vector<PileBatch>& pile = e->pile_host;
         pile.resize((size_t)std::max(nb, 1));
@@ -667,6 +681,25 @@ static int compute(pb_engine* e, bool time_pileup, bool full_cap = false) {
         const unsigned grid = (unsigned)((R.n_win * 32 + P7_TILE - 1) / P7_TILE);
         if (e->cfg.min_qual > 0) k_pileup7<true, P7_TILE><<<grid, P7_WARPS * 32, sizeof(Tile7<P7_TILE>), s>>>(R, PBt);
         else k_pileup7<false, P7_TILE><<<grid, P7_WARPS * 32, sizeof(Tile7<P7_TILE>), s>>>(R, PBt);
+    } else if (pv == 8) {
+        // a cluster per 512-locus tile; the cluster grows until the grid fills the GPU's 148 x 2 CTA slots a few times over
+        const unsigned T = (unsigned)e->ctile;
+        const unsigned tiles = (unsigned)((R.n_win * 32 + T - 1) / T);
+        unsigned cl = 1;
+        if (const char* cs = getenv("PB_CLUSTER")) cl = (unsigned)atoi(cs);
+        else while (cl < (unsigned)P7C_MAX_CLUSTER && (uint64_t)tiles * cl < 148u * 2u * 4u) cl <<= 1;
+        if (cl < 1 || cl > (unsigned)P7C_MAX_CLUSTER || (cl & (cl - 1))) cl = P7C_MAX_CLUSTER;
+        cudaLaunchConfig_t lc; memset(&lc, 0, sizeof(lc));
+        lc.gridDim = dim3(tiles * cl); lc.blockDim = dim3(P7_WARPS * 32); lc.stream = s;
+        lc.dynamicSmemBytes = T == 1024 ? sizeof(Tile7c<1024>) : sizeof(Tile7c<512>);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        if (tiles) {
+            const bool mq = e->cfg.min_qual > 0;
+            if (T == 1024) { if (mq) CK(cudaLaunchKernelEx(&lc, k_pileup7c<true, 1024>, R, PBt)); else CK(cudaLaunchKernelEx(&lc, k_pileup7c<false, 1024>, R, PBt)); }
+            else { if (mq) CK(cudaLaunchKernelEx(&lc, k_pileup7c<true, 512>, R, PBt)); else CK(cudaLaunchKernelEx(&lc, k_pileup7c<false, 512>, R, PBt)); }
+        }
     } else {
         const unsigned grid = (unsigned)((R.n_win + P5_WARPS - 1) / P5_WARPS);
         size_t smem = sizeof(Warp5) * P5_WARPS;

@@ -85,7 +85,7 @@ __device__ __forceinline__ void scatter_chunk(const uint4 Q, uint32_t cw, uint32
                                 : ((__byte_perm(Qw, 0, 0x4440 | (b & 3)) & qand) | qor);   // 1 << 20 | q
         const int pos = b < 7 ? 2 * b : b < 14 ? 2 * (b - 7) : 2 * (b - 14);   // bit position of the code in its copy
         const uint32_t code = (b < 7 ? cw : b < 14 ? cwm : cwh) & (3u << pos);
-        const uint32_t a = code * (1u << (LOG - pos)) + sa;                    // + letter * 4 T
+        const uint32_t a = (LOG >= pos ? code * (1u << (LOG >= pos ? LOG - pos : 0)) : code >> (pos > LOG ? pos - LOG : 0)) + sa;   // + letter * 4 T
         red_counted<NF>(okm, 1u << b, a + 4u * b, val, sa + 4u * b + OFF_X);
     }
 }
@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(P7_WARPS * 32, 2) k_pileup7(const RegionDev R,
             int b = 0;
             while (g >= S.grab0[b + 1]) b++;                      // batch of this grab (grab0 is non-decreasing)
             b_nx = b;
-            const uint32_t di = (g - S.grab0[b]) * P7_GRAB + (uint32_t)(lane >> 1);   // two lanes per descriptor
+            const uint32_t gl = g - S.grab0[b], ngb = S.grab0[b + 1] - S.grab0[b];
+            const uint32_t di = PB.spread ? (uint32_t)(lane >> 1) * ngb + gl : gl * P7_GRAB + (uint32_t)(lane >> 1);   // two lanes per descriptor
             sidx_nx = S.slo[b] + di;
             if (di < S.nseg[b]) seg_nx = PB.b[b].seg[sidx_nx];
         };

@@ -182,7 +182,9 @@ def workload(name: str, scale: float = 1.0) -> Workload:
     """The five BASELINE.json configs; `scale` shrinks the genome (not the depth) for quick runs."""
     s = lambda n: max(20_000, int(n * scale))   # noqa: E731
     if name == "C1":
-        return Workload("C1", 1, [s(5_000_000)], [FRAGS(100)], description="5 Mb bacterial-like, 100x 2x150")
+        d = int(os.environ.get("PB_SYNTH_DEPTH", "100"))      # kernel-selection experiments only (tools/ab_kernels.sh): says so in the name
+        return Workload("C1", 1, [s(5_000_000)], [FRAGS(d)],
+                        description="5 Mb bacterial-like, 100x 2x150" if d == 100 else "NOT A BASELINE CONFIG: C1 genome at %dx" % d)
     if name == "C2":
         return Workload("C2", 2, [s(n) for n in _C2_CONTIGS], [FRAGS(60), JUMPS(10)],
                         description="50 Mb fungal-scale, 20 contigs, 60x frags + 10x jumps")

@@ -27,12 +27,12 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
-@pytest.fixture(scope="module", params=["gather", "scatter", "auto"])
+@pytest.fixture(scope="module", params=["gather", "scatter", "cluster", "auto"])
 def pileup_kernel(request):
-    """Every engine test runs against both hot-kernel formulations (k_pileup5 gather, k_pileup7 scatter) and the
+    """Every engine test runs against both hot-kernel formulations (k_pileup5 gather, k_pileup7 scatter, k_pileup7c cluster scatter) and the
     engine's own per-region choice.  PB_PILEUP is read by pb_create, so engines made inside the module see it."""
     old = os.environ.get("PB_PILEUP")
-    val = {"gather": "5", "scatter": "7", "auto": None}[request.param]
+    val = {"gather": "5", "scatter": "7", "cluster": "8", "auto": None}[request.param]
     if val is None:
         os.environ.pop("PB_PILEUP", None)
     else:

@@ -23,7 +23,7 @@ class kernel_choice:
     """PB_PILEUP is read by pb_create: engines made inside the block use the forced kernel (None = the engine's choice)."""
 
     def __init__(self, which):
-        self.val = {None: None, "auto": None, "gather": "5", "scatter": "7"}[which]
+        self.val = {None: None, "auto": None, "gather": "5", "scatter": "7", "cluster": "8"}[which]
 
     def __enter__(self):
         self.old = os.environ.get("PB_PILEUP")
@@ -39,12 +39,12 @@ class kernel_choice:
             os.environ["PB_PILEUP"] = self.old
 
 
-def _region_vs_c_oracle(wl, ci, a, b):
+def _region_vs_c_oracle(wl, ci, a, b, which=None):
     contig = wl.contig_bases(ci).tobytes()
     sbs = wl.region_batches(ci, a, b)
     batches = [(sb.as_read_batch(), sb.frag) for sb in sbs]
     n_ops = sum(int(rb.cigar.shape[0]) for rb, _ in batches)
-    with kernel_choice(None):
+    with kernel_choice(which):
         e = Engine(0)
     try:
         res, ins = e.run_region(contig, a, b, batches, indels_cap=max(1 << 16, n_ops // 8), bytes_cap=1 << 24)
@@ -86,11 +86,12 @@ def test_c3_interior_chunk_with_halo_on_both_sides():
     _region_vs_c_oracle(wl, ci, a, b)
 
 
-def test_c5_whole_amplicon_200kb_5000x():
+@pytest.mark.parametrize("kernel", [None, "cluster"])
+def test_c5_whole_amplicon_200kb_5000x(kernel):
     wl = synth.workload("C5")
     (ci, a, b), = wl.regions()
     assert b - a + 1 == 200_000
-    res = _region_vs_c_oracle(wl, ci, a, b)
+    res = _region_vs_c_oracle(wl, ci, a, b, kernel)
     assert res.c.coverage > 4000
 
 
@@ -122,7 +123,7 @@ def _eng_cfg(cfg):
                         cfg.oldIndel, cfg.iupac, cfg.fixAmb)
 
 
-@pytest.mark.parametrize("kernel", ["gather", "scatter"])
+@pytest.mark.parametrize("kernel", ["gather", "scatter", "cluster"])
 def test_deletion_shift_readds_bases_left_of_the_reads_pos(kernel):
     """PileUpRegion.scala:167-178: the shift walks read offsets backwards across earlier CIGAR elements; after a long
     insertion inside a homopolymer the re-added bases start LEFT of the read's alignment start.  No read of the batch
@@ -153,7 +154,7 @@ def test_deletion_shift_readds_bases_left_of_the_reads_pos(kernel):
         e.close()
 
 
-@pytest.mark.parametrize("kernel", ["gather", "scatter"])
+@pytest.mark.parametrize("kernel", ["gather", "scatter", "cluster"])
 def test_more_than_4064_descriptors_per_tile_with_mixed_mapq(kernel):
     """The scatter kernel folds its 12-bit tile counters into the output planes every 4064 descriptors; reads with
     five different mapping qualities make the folds carry Bq / C terms as well."""
@@ -184,7 +185,7 @@ def test_more_than_4064_descriptors_per_tile_with_mixed_mapq(kernel):
     assert int(res["base_count4"].sum(axis=1).max()) > 300
 
 
-@pytest.mark.parametrize("kernel", ["gather", "scatter"])
+@pytest.mark.parametrize("kernel", ["gather", "scatter", "cluster"])
 def test_int32_wrap_of_mqsum(kernel):
     """mqSum is a JVM Int (PileUp.scala:33): 8.5 M bases of MAPQ 255 at one locus push it past 2^31 and it wraps;
     BaseSum (qualSum) is 64-bit and does not.  score becomes 0 through `mqSum > 0` (PileUp.scala:148)."""
