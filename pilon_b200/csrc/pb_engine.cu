@@ -140,6 +140,7 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
     CK(cudaFuncSetAttribute(k_pileup7c<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile7c<1024>)));
     CK(cudaFuncSetAttribute(k_pileup7c<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile7c<1024>)));
     if (const char* v = getenv("PB_CTILE")) e->ctile = atoi(v) == 1024 ? 1024 : 512;
+    CK(cudaFuncSetAttribute(k_spill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SPILL_SMEM_CAP * sizeof(int4))));
     CK(cudaFuncSetAttribute(k_pileup5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_pileup5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -613,7 +614,7 @@ static int compute(pb_engine* e, bool time_pileup, bool full_cap = false) {
             k_scan3<<<nblocks, SCAN_THREADS, 0, e->stream2>>>(R, e->block_sums.as<uint2>());
             e->launches += 3;
             CK(cudaEventRecord(e->ev_join, e->stream2));
-            k_indel<<<148 * 4, 128, 0, s>>>(R, dB); e->launches++;     // queued I / D ops of every batch
+            k_indel<<<148 * 12, 128, 0, s>>>(R, dB); e->launches++;    // queued I / D ops of every batch; a chain of dependent loads per op: as many threads in flight as 40 registers allow
         }
         k_fold<<<1, 32, 0, s>>>(R, reach_base + 2 * i0, i1 - i0, i1 == nb, nb); e->launches++;
     }
@@ -713,7 +714,7 @@ static int compute(pb_engine* e, bool time_pileup, bool full_cap = false) {
     // deletion spill: candidates are bounded by the number of deletion groups
     uint32_t p2 = 1; while (p2 < evcap) p2 <<= 1;
     CK(e->spill_scratch.ensure((size_t)p2 * sizeof(int4) + 16, false, s));
-    if (evcap) { k_spill<<<1, 1024, 2048 * sizeof(int4), s>>>(R, e->spill_scratch.as<int4>(), p2); e->launches++; }
+    if (evcap) { k_spill<<<SPILL_CTAS, 1024, (size_t)std::min(p2, SPILL_SMEM_CAP) * sizeof(int4), s>>>(R, e->spill_scratch.as<int4>(), p2); e->launches++; }
     CK(cudaGetLastError());
     return PB_OK;
 }

@@ -231,10 +231,22 @@ __global__ void __launch_bounds__(128) k_prep(RegionDev R, DevBatch B, uint32_t 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_indel(RegionDev R, const DevBatch* __restrict__ batches) {
     __shared__ uint32_t pre[SC_SLOTS + 1];                    // flat item index -> (sub-queue, entry)
-    if (threadIdx.x == 0) {
-        uint32_t acc = 0;
-        for (uint32_t q = 0; q < (uint32_t)SC_SLOTS; q++) { pre[q] = acc; if (q < R.work_slots) acc += min(R.slots[q].n_work, R.work_sub); }
-        pre[SC_SLOTS] = acc;
+    static_assert(SC_SLOTS == 64, "two warps load the sub-queue counts");
+    if (threadIdx.x < 64) {                                   // exclusive scan of the 64 sub-queue lengths: one load latency, not 64
+        const uint32_t q = threadIdx.x, ln = threadIdx.x & 31;
+        const uint32_t cnt = q < R.work_slots ? min(R.slots[q].n_work, R.work_sub) : 0u;
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, inc, o); if (ln >= (uint32_t)o) inc += v; }
+        if (q == 31) pre[SC_SLOTS] = inc;                     // first half's total, parked in the last slot for a moment
+        pre[q] = inc - cnt;
+    }
+    __syncthreads();
+    const uint32_t half = pre[SC_SLOTS];
+    __syncthreads();
+    if (threadIdx.x >= 32 && threadIdx.x < 64) {
+        pre[threadIdx.x] += half;
+        if (threadIdx.x == 63) pre[SC_SLOTS] = pre[63] + (63u < R.work_slots ? min(R.slots[63].n_work, R.work_sub) : 0u);
     }
     __syncthreads();
     const uint32_t n_work = pre[SC_SLOTS];
@@ -512,6 +524,9 @@ __device__ __forceinline__ void emit_group(const RegionDev& R, const DevBatch* b
 // thread: Boyer-Moore vote, recount, record.  Longer groups (a 5000x pile-up has thousands of events per indel) are
 // worked on by the whole warp: each lane votes over its strided share -- a strict majority of the group is a strict
 // majority of at least one share -- and the distinct surviving candidates are counted exactly.
+// Evidence lists up to this long are voted by the thread that finds their start (two dependent loads per entry, one after
+// the other); longer ones -- a real indel at depth 70 has 30-70 entries -- by the whole warp, a few load latencies in all.
+static constexpr uint32_t GROUP_SERIAL_MAX = 8;
 __global__ void __launch_bounds__(256) k_groups(RegionDev R, const DevBatch* batches, const uint32_t* keys,
                                                 const uint32_t* perm, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -522,11 +537,11 @@ __global__ void __launch_bounds__(256) k_groups(RegionDev R, const DevBatch* bat
     if (is_start) {
         const uint32_t key = keys[i];
         uint64_t h = 0; uint32_t votes = 0, ge = i;
-        for (; ge < n && ge < i + 65 && keys[ge] == key; ge++) {
+        for (; ge < n && ge < i + GROUP_SERIAL_MAX + 1 && keys[ge] == key; ge++) {
             const uint64_t hj = R.ev_key[perm[ge]].h;
             if (votes == 0) { h = hj; votes = 1; } else if (hj == h) votes++; else votes--;
         }
-        big = ge == i + 65;                                              // longer than 64: the warp takes it below
+        big = ge == i + GROUP_SERIAL_MAX + 1;                            // longer: the warp takes it below
         if (!big) {
             uint32_t cnt = 0, rep = 0xFFFFFFFFu;
             for (uint32_t j = i; j < ge; j++) {
@@ -743,9 +758,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan3(RegionDev R, const uint2
 // k_spill: GenomeRegion.scala:259-264.  Pass 1 walks loci in ascending order; a homozygous
 // deletion called at locus i marks i+1 .. i+len-1 deleted and adds its `deletions` to theirs;
 // deleted loci make no calls.  Candidates (computed in parallel, ignoring `deleted`) are sorted
-// by locus, accepted/rejected with a sequential watermark, then applied in parallel.
-// Single CTA; the candidate list is tiny (one entry per homozygous deletion call).
+// by locus and accepted/rejected by the reference's watermark rule, then applied in parallel.
+// The watermark is sequential only inside a CHAIN of overlapping candidates: a candidate that
+// starts right of the end of every earlier candidate (a prefix maximum) is accepted whatever
+// happened before it, and the rule restarts there -- so one thread per chain head walks its
+// chain (chains are one or two entries long).  The list is small (one entry per homozygous
+// deletion call): every CTA sorts its own copy in shared memory (up to SPILL_SMEM_CAP entries;
+// beyond that one CTA works in a global scratch) and applies its share of the accepted ones.
 // ---------------------------------------------------------------------------------------------
+static constexpr uint32_t SPILL_SMEM_CAP = 8192;      // 128 KB of int4
+static constexpr uint32_t SPILL_CTAS = 37;            // every CTA sorts its own copy of the list, then applies its share
 __device__ __forceinline__ void bitonic_sort_by_x(int4* a, uint32_t npow2) {
     for (uint32_t k = 2; k <= npow2; k <<= 1)
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
@@ -766,28 +788,54 @@ __global__ void __launch_bounds__(1024) k_spill(RegionDev R, int4* scratch, uint
     const uint32_t n = min(R.sc->n_cand, R.cand_cap);
     if (n == 0) return;
     uint32_t p2 = 1; while (p2 < n) p2 <<= 1;
-    int4* a = (p2 <= 2048) ? sm4 : scratch;           // 32 KB of shared memory, else the global scratch
+    int4* a = (p2 <= SPILL_SMEM_CAP) ? sm4 : scratch;     // else the global scratch, and one CTA does it all
+    if (a == scratch && blockIdx.x) return;
     if (p2 > scratch_cap && a == scratch) { if (threadIdx.x == 0) atomicOr(&R.sc->error, 2); return; }
     for (uint32_t t = threadIdx.x; t < p2; t += blockDim.x) a[t] = t < n ? R.cand[t] : make_int4(0x7fffffff, 0, 0, 0);
     __syncthreads();
     bitonic_sort_by_x(a, p2);
-    // sequential watermark over (locus, deletions, length): w = 1 marks a rejected candidate
-    if (threadIdx.x == 0) {
-        int64_t deleted_until = -1;
-        for (uint32_t t = 0; t < n; t++) {
-            const int4 c = a[t];
-            if (c.x <= deleted_until) { a[t].w = 1; continue; }             // it is deleted: makes no call
-            const int64_t end = (int64_t)c.x + c.z - 1;
-            if (end > deleted_until) deleted_until = end;
+    // chain heads: x > max over ALL earlier candidates of their last deleted locus (thread t owns entries [t*per, t*per+per))
+    __shared__ long long s_max[1024];
+    const uint32_t per = (n + blockDim.x - 1) / blockDim.x, b0 = threadIdx.x * per, b1 = min(b0 + per, n);
+    auto end_of = [&](const int4& c) { return (long long)c.x + c.z - 1; };
+    long long m = -1;
+    for (uint32_t t = b0; t < b1; t++) m = max(m, end_of(a[t]));
+    s_max[threadIdx.x] = m;
+    __syncthreads();
+    for (uint32_t o = 1; o < blockDim.x; o <<= 1) {           // inclusive max-scan of the per-thread maxima
+        const long long v = threadIdx.x >= o ? s_max[threadIdx.x - o] : -1;
+        __syncthreads();
+        s_max[threadIdx.x] = max(s_max[threadIdx.x], v);
+        __syncthreads();
+    }
+    m = threadIdx.x ? s_max[threadIdx.x - 1] : -1;            // everything left of my entries
+    for (uint32_t t = b0; t < b1; t++) {
+        const int4 c = a[t];
+        a[t].w = (long long)c.x > m ? 2 : 0;                  // w: 2 = chain head, 1 = rejected
+        m = max(m, end_of(c));
+    }
+    __syncthreads();
+    // the reference's watermark over (locus, length), restarted at every chain head
+    for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
+        if (a[t].w != 2) continue;
+        long long deleted_until = end_of(a[t]);
+        for (uint32_t u = t + 1; u < n; u++) {
+            const int4 c = a[u];
+            if (c.w == 2) break;                              // the next chain: somebody else's
+            if ((long long)c.x <= deleted_until) { a[u].w = 1; continue; }      // it is deleted: makes no call
+            deleted_until = max(deleted_until, end_of(c));
         }
     }
     __syncthreads();
-    // apply: every deleted locus belongs to exactly one accepted deletion
-    for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
+    // apply: every deleted locus belongs to exactly one accepted deletion.  Warp per candidate, lane per deleted locus --
+    // the per-locus work is a chain of dependent loads and a BaseCall (~2 us): a thread per candidate made the kernel as
+    // slow as the longest deletion -- and the candidates are dealt to all CTAs of the grid (each has sorted its own copy).
+    const uint32_t lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (uint32_t t = blockIdx.x * wpb + (threadIdx.x >> 5); t < n; t += gridDim.x * wpb) {
         const int4 cd = a[t];
-        if (cd.w) continue;
+        if (cd.w == 1) continue;
         const int32_t loc = cd.x, d = cd.y, L = cd.z;
-        for (int32_t j = 1; j < L; j++) {
+        for (int32_t j = 1 + (int32_t)lane; j < L; j += 32) {
             const int64_t i = (int64_t)loc + j;
             const int32_t nd = wrap32((int64_t)R.o_del[i] + d);                                  // :263
             R.o_del[i] = nd;

@@ -225,3 +225,48 @@ def test_int32_wrap_of_mqsum(kernel):
 
 def capi_score(c):
     return int(c) >> 16
+
+
+@pytest.mark.parametrize("kernel", ["gather", "scatter", "cluster"])
+def test_deletion_spill_chain_of_overlapping_candidates(kernel):
+    """GenomeRegion.scala:259-264 is sequential: a deletion called INSIDE a deleted span makes no call, so the span it would
+    have deleted stays callable.  Three homozygous deletions in a chain: A = 100 (+10) is accepted, B = 105 (+8) lies inside A
+    and is rejected, C = 112 (+5) lies inside B's span only and must be accepted.  k_spill resolves chains in parallel from
+    their heads; a candidate far to the right is a chain of its own."""
+    rng = random.Random(5)
+    ref = bytearray(rng.choice(b"ACGT") for _ in range(400))
+    for start, dlen in ((100, 10), (105, 8), (112, 5), (300, 6)):
+        while ref[start - 2] == ref[start + dlen - 2]:      # base before != last deleted base: nothing shifts left (PileUpRegion.scala:167-178)
+            ref[start - 2] = rng.choice(b"ACGT")
+    ref = bytes(ref)
+
+    def del_read(pos, left, dlen, right):
+        bases = ref[pos - 1:pos - 1 + left] + ref[pos - 1 + left + dlen:pos - 1 + left + dlen + right]
+        return po.Read(pos=pos, cigar=[("M", left), ("D", dlen), ("M", right)], bases=bases, quals=bytes([35]) * len(bases), mapq=60)
+
+    reads = []
+    reads += [del_read(70, 30, 10, 2) for _ in range(20)]       # A: loci 100..109 deleted, reads end at 111
+    reads += [del_read(103, 2, 8, 2) for _ in range(20)]        # B: 105..112, reads cover 103,104 and 113,114
+    reads += [del_read(111, 1, 5, 40) for _ in range(20)]       # C: 112..116
+    reads += [del_read(270, 30, 6, 30) for _ in range(20)]      # far away: its own chain
+    reads.sort(key=lambda r: r.pos)
+    cfg = po.Config(flank=0)
+    groups = [(reads, True)]
+    py = H.run_py_oracle(ref, 1, 400, groups, cfg)
+    fl = py["flags"]
+    is_del = lambda l: bool(fl[l - 1] & capi.PB_FL_CHANGED) and ((fl[l - 1] >> capi.PB_FL_KIND_SHIFT) & 3) == capi.PB_KIND_DEL   # noqa: E731
+    deleted = lambda l: bool(fl[l - 1] & capi.PB_FL_DELETED)                                                                   # noqa: E731
+    assert is_del(100) and all(deleted(l) for l in range(101, 110))
+    assert not is_del(105) and not deleted(110) and not deleted(111)
+    assert is_del(112) and all(deleted(l) for l in range(113, 117)) and not deleted(117)
+    assert is_del(300) and deleted(301)
+    with kernel_choice(kernel):
+        e = Engine(0, _eng_cfg(cfg))
+    try:
+        packed = [(pack_records(g), f) for g, f in groups]
+        res, ins = e.run_region(ref, 1, 400, packed)
+        H.assert_matches_py(res, ins, py, "deletion spill chain (%s)" % kernel)
+        ref_c, _ = H.run_c_oracle(ref, 1, 400, packed, cfg)
+        H.assert_results_equal(res, ref_c, "deletion spill chain, C oracle (%s)" % kernel)
+    finally:
+        e.close()
