@@ -37,6 +37,12 @@ UNIT = "bases/s"
 # flags + call record for the change list); --vcf needs every counter
 FIX_PLANES = ["coverage_arr", "bad_pair", "phys_cov", "insert_size", "weighted_qual", "weighted_mq", "clips",
               "frag_coverage", "flags", "call"]
+# what the fix path itself consumes (pb_out_create: pass 2 + identifyAndFixIssues, GenomeRegion.scala:275-283, 307-380):
+# flags, fragCoverage and the call records of the changed / ambiguous loci (pb_region_result.calls) -- the other
+# per-locus arrays of :247-253 only feed --tracks and --vcf.  tests/test_output_cpu.py / test_output_gpu.py check that the
+# FASTA, the change list and the log from this set equal those from every plane.
+FIXMIN_PLANES = ["flags", "frag_coverage"]
+CALLS_CAP = 1 << 20
 
 
 def algorithmic_bytes(aligned: int, n_reads: int, n_cigar: int, loci: int) -> float:
@@ -425,15 +431,26 @@ def run_gpu_arm(args):
         if os.environ.get("PB_BENCH_PIN_CONTIG") != "1":     # measured: pinning them costs ~10 % (profiles/README.md)
             break
         _register(torch.cuda.cudart(), np.frombuffer(cbuf, np.uint8).ctypes.data, len(cbuf))
-    planes = FIX_PLANES if args.planes == "fix" else None
+    from pilon_b200 import _capi as capi
     n_workers = args.e2e_workers
     max_size = max(r.size for r in regions)
     e2e_depth = max(1, args.e2e_depth)                       # passes in flight per host thread (one engine + result set each)
-    workers = [[(Engine(local), ResultBuffers(max_size, planes, indels_cap=1 << 20, indel_bytes_cap=1 << 23, pinned=True))
-                for _ in range(e2e_depth)] for _ in range(n_workers)]
-    from pilon_b200 import _capi as capi
-    per_locus = sum(np.dtype(dt).itemsize * per for name, dt, per in capi.RESULT_PLANES if planes is None or name in planes)
-    d2h = per_locus * total_loci
+
+    def plane_set(which):
+        return {"fixmin": FIXMIN_PLANES, "fix": FIX_PLANES, "vcf": None}[which]
+
+    def make_workers(which):
+        pl = plane_set(which)
+        return [[(Engine(local), ResultBuffers(max_size, pl, indels_cap=1 << 20, indel_bytes_cap=1 << 23, pinned=True,
+                                                calls_cap=CALLS_CAP if which == "fixmin" else 0))
+                 for _ in range(e2e_depth)] for _ in range(n_workers)]
+
+    def d2h_bytes(which, n_calls):
+        pl = plane_set(which)
+        per_locus = sum(np.dtype(dt).itemsize * per for name, dt, per in capi.RESULT_PLANES if pl is None or name in pl)
+        return per_locus * total_loci + 16 * n_calls
+    workers = make_workers(args.planes)
+    calls_seen = [0]
 
     trace = [[0.0, 0.0, 0.0] for _ in range(n_workers)] if os.environ.get("PB_E2E_TRACE") else None
 
@@ -457,6 +474,9 @@ def run_gpu_arm(args):
         eng.finish(res)
         if trace is not None:
             trace[slot][2] += time.perf_counter() - t_c
+        if res.calls_cap:
+            assert res.c.n_calls <= res.calls_cap, "CALLS_CAP too small for this region"
+            calls_seen[0] += int(res.c.n_calls)              # (GIL-protected; only used for the byte count)
         return int(res.c.aligned_bases)
 
     def e2e_step():
@@ -487,7 +507,18 @@ def run_gpu_arm(args):
         [t.join() for t in ts]
         return done[0]
 
+    def prime():
+        """Every engine takes the largest region once: which host thread gets which region varies from step to step, and an
+        engine that met its largest region only in a timed step would grow its buffers there (cudaFree + cudaMalloc: a
+        device-wide synchronisation; seen as 60 ms vs 100 ms steps before this was here)."""
+        big = max(regions, key=lambda r: r.aligned)
+        for slot in range(n_workers):
+            for k in range(e2e_depth):
+                e2e_submit(slot, k, big)
+                e2e_collect(slot, k)
+        calls_seen[0] = 0
     e2e_steps = max(1, args.steps)
+    prime()
     for _ in range(max(1, min(args.warmup, 3))):
         e2e_step()
     barrier()
@@ -501,6 +532,42 @@ def run_gpu_arm(args):
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     assert got == total_aligned * e2e_steps, (got, total_aligned)
+    d2h = d2h_bytes(args.planes, calls_seen[0] // (e2e_steps + max(1, min(args.warmup, 3))))
+
+    def timed_variant(n):
+        prime()
+        e2e_step()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(n):
+            e2e_step()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t) / n
+    # the same arm as round 1 ran it: every array of GenomeRegion.scala:247-253 + the call plane down (35 B per locus) and the
+    # bases up as 2-bit codes -- what the minimal result set and the reference deltas bought
+    e2e_classic = None
+    if args.planes == "fixmin" and args.base_deltas and world == 1:
+        for w in workers:
+            for eng, _ in w:
+                eng.close()
+        workers = make_workers("fix")
+        saved_d = [(b, b.c.base_delta_idx, b.c.base_delta_code, b.c.n_base_delta) for r in regions for b in r.batches]
+        h2d_c = h2d
+        for b, _, _, _ in saved_d:
+            h2d_c += int(b.c.n_seq) // 4 - 5 * int(b.c.n_base_delta)
+            b.c.base_delta_idx = None; b.c.base_delta_code = None; b.c.n_base_delta = 0
+            _register(torch.cuda.cudart(), b.c.bases2, int(b.c.n_seq) // 4)
+        nc = max(1, min(args.steps, 3))
+        tc = timed_variant(nc)
+        e2e_classic = {"value": total_aligned / tc, "unit": UNIT, "ms_per_step": 1e3 * tc, "h2d_bytes_per_step": h2d_c,
+                       "d2h_bytes_per_step": d2h_bytes("fix", 0), "steps": nc,
+                       "what": "round-1 transport: 2-bit bases up, the ten per-locus arrays of the fix + tracks path down"}
+        for b, di, dc, nd in saved_d:
+            b.c.base_delta_idx = di; b.c.base_delta_code = dc; b.c.n_base_delta = nd
+        for w in workers:
+            for eng, _ in w:
+                eng.close()
+        workers = make_workers(args.planes)
     # the same arm with one quality byte per base (what a BAM with unbinned qualities needs), a few steps
     e2e8 = None
     if q4 and not args.quals8 and world == 1:
@@ -510,14 +577,8 @@ def run_gpu_arm(args):
             b.c.qual_codes = None
             _register(torch.cuda.cudart(), b.c.quals, int(b.c.n_seq))
             h2d8 += int(b.c.n_seq) - (int(b.c.n_seq) * int(b.c.qual_code_bits) + 7) // 8
-        e2e_step()
-        torch.cuda.synchronize()
-        t8 = time.perf_counter()
         n8 = max(1, min(args.steps, 3))
-        for _ in range(n8):
-            e2e_step()
-        torch.cuda.synchronize()
-        t8 = (time.perf_counter() - t8) / n8
+        t8 = timed_variant(n8)
         e2e8 = {"value": total_aligned / t8, "unit": UNIT, "ms_per_step": 1e3 * t8, "h2d_bytes_per_step": h2d + h2d8, "steps": n8}
         for b, qc in saved:
             b.c.qual_codes = qc
@@ -600,7 +661,8 @@ def run_gpu_arm(args):
                           "aligned_bases_per_gpu": total_aligned, "mean_depth": depth, "l2": "inputs_exceed_l2 (%.1f GB per step)" % (h2d / 1e9),
                           "timing": "CUDA events: first launch of the timed steps -> last engine stream done, regions launched by %d host threads onto one stream per region; "
                                     "sequential_ms_per_step = sum of per-region event intervals with one region at a time (the pileup kernel's launches are timed in that pass)" % args.host_threads,
-                          "e2e_planes": args.planes,
+                          "e2e_planes": {"fixmin": "flags + frag_coverage + sparse call records (pb_region_result.calls) + indel evidence: what pb_out_create consumes for --fix snps,indels --changes",
+                                         "fix": "the ten per-locus arrays of the fix + tracks path (35 B per locus)", "vcf": "every plane"}[args.planes],
                           "e2e_quals": ("%d-bit codes + table (the workload has <= %d distinct quality bytes), expanded on the device"
                                         % (qbits, 1 << qbits) if q4 else "1 byte per base"),
                           "e2e_bases": ("deltas against the reference (5 B per differing base), bases2 rebuilt on the device"
@@ -609,7 +671,7 @@ def run_gpu_arm(args):
                "e2e": {"value": job_aligned / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": job_h2d, "d2h_bytes_per_step": job_d2h,
                        "ms_per_step": 1e3 * e2e_sec, "steps": e2e_steps, "streams_per_gpu": n_workers * e2e_depth,
                        "host_threads_per_gpu": n_workers, "passes_in_flight_per_thread": e2e_depth,
-                       "quals8": e2e8},
+                       "quals8": e2e8, "classic": e2e_classic},
                "gpu_launches": int(job_launches),
                "roofline": {"bound": "hbm", "kernel": "k_pileup", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -804,7 +866,8 @@ def run_sharded_arm(args):
     depth = sum(l.depth for l in wl.libraries)
     mine = sharding.assign(chunks, world, [depth] * len(chunks))[rank]
     from pilon_b200 import _capi as capi
-    planes = FIX_PLANES if args.planes == "fix" else [p[0] for p in capi.RESULT_PLANES]
+    # (the sharded arm keeps the ten fix + tracks planes also for --planes fixmin: its chunk digests are taken over them)
+    planes = FIX_PLANES if args.planes in ("fix", "fixmin") else [p[0] for p in capi.RESULT_PLANES]
     max_size = max(b + 1 - a for _, a, b in chunks)
     n_workers = args.e2e_workers
     workers = [(Engine(local), ResultBuffers(max_size, planes, indels_cap=1 << 20, indel_bytes_cap=1 << 23, pinned=True))
@@ -915,7 +978,7 @@ def run_sharded_arm(args):
                           "timing": "per rank: sum over its chunks of the device time of one pass (CUDA events on the engine's stream, "
                                     "batches resident); job = max over ranks.  e2e: wall time of each wave through the C ABI from pinned "
                                     "host buffers, %d chunks in flight, summed per rank, max over ranks" % n_workers,
-                          "e2e_planes": args.planes},
+                          "e2e_planes": "fix" if args.planes in ("fix", "fixmin") else args.planes},
                "digest": digest,
                "e2e": {"value": aligned / t_e2e_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": 1e3 * t_e2e_max},
@@ -938,13 +1001,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrinks the genome (not the depth); 1.0 = the BASELINE config")
-    ap.add_argument("--planes", default="fix", choices=["fix", "vcf"], help="per-locus results copied back in the e2e arm")
+    ap.add_argument("--planes", default="fixmin", choices=["fixmin", "fix", "vcf"],
+                    help="results copied back in the e2e arm: fixmin = what the fix path consumes (flags, fragCoverage, sparse call "
+                    "records), fix = the ten per-locus arrays of the fix + tracks path, vcf = every plane")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-workers", type=int, default=3, help="host threads per GPU in the e2e arm")
     ap.add_argument("--e2e-depth", type=int, default=1, help="regions in flight per host thread in the e2e arm (one engine "
                     "and one result set each): the next region uploads while the previous one computes and downloads")
-    ap.add_argument("--base-deltas", action="store_true", help="e2e arm: upload the 2-bit bases as their deltas against the "
-                    "reference (pb_batch.base_delta_idx) instead of as they are; fewer bytes, no measured gain")
+    ap.add_argument("--no-base-deltas", dest="base_deltas", action="store_false", help="e2e arm: upload the bases as 2-bit codes "
+                    "instead of their deltas against the reference (pb_base_delta_encode; 5 B per differing base)")
     ap.add_argument("--quals8", action="store_true", help="e2e arm: upload one quality byte per base even when the batch "
                     "offers the packed transport (pb_batch.qual_codes)")
     ap.add_argument("--host-threads", type=int, default=4, help="host threads feeding region passes to the GPU")

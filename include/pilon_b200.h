@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB_ABI_VERSION 5
+#define PB_ABI_VERSION 6
 
 /* ---- status codes ---------------------------------------------------------------------- */
 #define PB_OK                 0
@@ -169,6 +169,12 @@ typedef struct pb_indel {
 /* ---- region results ------------------------------------------------------------------------
  * All array pointers are HOST memory owned by the caller, each `size` elements long unless noted;
  * a NULL pointer means "not wanted" (no device->host copy is made for it). */
+typedef struct pb_call_entry {
+    int32_t  locus_index;    /* 0-based in the region                                          */
+    uint32_t flags;          /* PB_FL_* of the locus                                           */
+    uint64_t call;           /* packed BaseCall record, as in the `call` plane                 */
+} pb_call_entry;
+
 typedef struct pb_region_result {
     /* scalars, always filled */
     int64_t size;            /* stop + 1 - start                               Region.scala:27 */
@@ -220,6 +226,16 @@ typedef struct pb_region_result {
     int64_t* batch_coverage;
     int64_t  batch_cap;
     int64_t  n_batches;
+
+    /* The call plane, sparse: one entry per locus whose pass-1 call changes or questions the reference
+     * (flags & (PB_FL_CHANGED | PB_FL_AMBIGUOUS)), ascending locus_index -- the only loci whose call record
+     * identifyAndFixIssues reads (GenomeRegion.scala:307-380).  A `--fix snps,indels --changes` caller asks for
+     * `flags`, `frag_coverage` (pass 2, :275-283) and these entries instead of the 8-byte-per-locus `call` plane.
+     * calls_cap is an input (NULL / 0 = not wanted); n_calls comes back and counts every such locus, also the
+     * ones beyond the capacity (which are not written).  */
+    pb_call_entry* calls;
+    int64_t  calls_cap;
+    int64_t  n_calls;
 } pb_region_result;
 
 typedef struct pb_engine pb_engine;

@@ -505,6 +505,17 @@ int po_region_finish(po_region* r, pb_region_result* res) {
     if (res->call) for (int64_t i = 0; i < S; i++) {   /* final-state BaseCall: what Vcf.writeRecord recomputes, Vcf.scala:78-79 */
         po_call c; baseCall(r, i, g, ng, &c); res->call[i] = pack_call(&c);
     }
+    /* the sparse form of the call plane: the loci identifyAndFixIssues looks at (GenomeRegion.scala:307-380) */
+    res->n_calls = 0;
+    if (res->calls && res->calls_cap > 0) for (int64_t i = 0; i < S; i++) {
+        if (!(flags[i] & (PB_FL_CHANGED | PB_FL_AMBIGUOUS))) continue;
+        if (res->n_calls < res->calls_cap) {
+            po_call c; baseCall(r, i, g, ng, &c);
+            pb_call_entry* en = &res->calls[res->n_calls];
+            en->locus_index = (int32_t)i; en->flags = flags[i]; en->call = pack_call(&c);
+        }
+        res->n_calls++;
+    }
     int64_t nb = 0, ni = 0;
     for (int64_t k = 0; k < ng; k++) {
         if (res->indels && ni < res->indels_cap) {

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libpilonb200.so")
 
 PB_OK = 0
-ABI_VERSION = 5
+ABI_VERSION = 6
 PB_ERR_INVALID, PB_ERR_CUDA, PB_ERR_UNSORTED, PB_ERR_UNSUPPORTED, PB_ERR_OOM, PB_ERR_HASH = -1, -2, -3, -4, -5, -6
 
 PB_F_PAIRED, PB_F_PROPER, PB_F_MATE_SAME_REF, PB_F_HAS_QUALS, PB_F_UNMAPPED, PB_F_REVERSE = 1, 2, 4, 8, 16, 32
@@ -61,7 +61,12 @@ class pb_region_result(C.Structure):
                 ("indels", C.c_void_p), ("indels_cap", C.c_int64),
                 ("indel_bytes", C.c_void_p), ("indel_bytes_cap", C.c_int64),
                 ("batch_read_count", C.c_void_p), ("batch_base_count", C.c_void_p), ("batch_coverage", C.c_void_p),
-                ("batch_cap", C.c_int64), ("n_batches", C.c_int64)]
+                ("batch_cap", C.c_int64), ("n_batches", C.c_int64),
+                ("calls", C.c_void_p), ("calls_cap", C.c_int64), ("n_calls", C.c_int64)]
+
+
+# pb_call_entry as a numpy record
+CALL_ENTRY_DTYPE = [("locus_index", "<i4"), ("flags", "<u4"), ("call", "<u8")]
 
 
 # name -> numpy dtype, elements per locus; order follows the struct

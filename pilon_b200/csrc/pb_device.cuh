@@ -92,6 +92,7 @@ struct Scalars {
     int phys_cov_start, insert_size_start;   // PileUpRegion.scala:59-60
     int unknown_ops, dropped_oob;
     unsigned n_events, n_groups, n_cand, n_work;
+    int n_calls;                        // loci with a changing / ambiguous call (pb_region_result.calls), written by the select
     int error;
     int min_depth;
 };

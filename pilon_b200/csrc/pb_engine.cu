@@ -10,9 +10,12 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <chrono>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include "pb_pileup7.cuh"
 #include "pb_pileup7c.cuh"
@@ -78,7 +81,7 @@ struct pb_engine {
     const uint8_t* contig_host = nullptr;   // the caller's contig (valid until pb_region_finish): head upload of long-read regions
     DBuf o_cnt, o_qs, o_i32[12], o_wq, o_wmq, o_flags, o_call;
     // event buffers
-    DBuf ev_key, ev, perm, sort_buf, groups, cand, work, spill_scratch, str_pool, cub_tmp;
+    DBuf ev_key, ev, perm, sort_buf, groups, cand, work, spill_scratch, str_pool, cub_tmp, call_idx, call_entries;
     Scalars* h_sc = nullptr;         // pinned
     int64_t launches = 0;
     float last_pileup_ms = 0.f;
@@ -91,6 +94,11 @@ struct pb_engine {
     std::vector<DevBatch> img_host;  // image of the batch table; a captured H2D copy reads it at every replay
     // PB_PHASE_TIMING=1 (diagnostics): device time of upload / pass / download per region, printed by pb_destroy
     bool phase_timing = false; cudaEvent_t ph[4] = {}; double ph_ms[3] = {0, 0, 0}; int64_t ph_regions = 0;
+    uint8_t* ref_stage = nullptr; size_t ref_stage_cap = 0;     // pinned staging for the reference window of a pageable contig
+    cudaEvent_t ev_stage = nullptr;
+    bool host_trace = false;         // PB_HOST_TRACE=1: host microseconds per section of pb_region_begin, printed by pb_destroy
+    double ht[6] = {0, 0, 0, 0, 0, 0}; long ht_n = 0;
+    double hf[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long hf_n = 0, ht_calls = 0, hf_calls = 0;
     int ctile = P7C_TILE;            // tile of the cluster scatter kernel (PB_CTILE: A/B runs)
     int spread_order = -1;           // -1 = by depth
     int64_t deep_depth = 1000;       // mean depth above which a region goes to the cluster scatter kernel ...
@@ -129,6 +137,7 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
     e->cfg.min_qual = c->min_qual; e->cfg.min_mq = c->min_mq; e->cfg.flank = c->flank;
     e->cfg.default_qual = c->default_qual; e->cfg.min_min_depth = c->min_min_depth;
     e->cfg.old_indel = c->old_indel; e->cfg.fix_amb = c->fix_amb; e->cfg.min_depth = c->min_depth;
+    if (const char* v = getenv("PB_HOST_TRACE")) e->host_trace = atoi(v) != 0;
     if (const char* v = getenv("PB_SPREAD")) e->spread_order = atoi(v);           // A/B runs: 0 / 1 forces the descriptor order of a grab
     if (const char* v = getenv("PB_DEEP")) e->deep_depth = atoi(v);
     if (const char* v = getenv("PB_PILEUP")) { const int pv = atoi(v); if (pv == 5 || pv == 7 || pv == 8) e->pileup_version = pv; }
@@ -147,6 +156,7 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
     CK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_stage, cudaEventDisableTiming));
     if (getenv("PB_PHASE_TIMING")) { e->phase_timing = true; for (auto& ev : e->ph) CK(cudaEventCreate(&ev)); }
     CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
     CK(cudaEventCreate(&e->evp0)); CK(cudaEventCreate(&e->evp1));
@@ -165,19 +175,28 @@ extern "C" int pb_destroy(pb_engine* e) {
         fprintf(stderr, "pilon_b200 phases over %lld regions: upload %.2f ms, pass %.2f ms, download %.2f ms per region\n",
                 (long long)e->ph_regions, e->ph_ms[0] / e->ph_regions, e->ph_ms[1] / e->ph_regions, e->ph_ms[2] / e->ph_regions);
     if (!e) return PB_OK;
+    if (e->host_trace && e->ht_n)
+        fprintf(stderr, "pilon_b200 pb_region_begin over %ld calls, host us per call: free_batches %.0f, reference window copy %.0f, flag read-back %.0f, buffers %.0f\n",
+                e->ht_n, e->ht[0] / e->ht_n, e->ht[1] / e->ht_n, e->ht[2] / e->ht_n, e->ht[3] / e->ht_n);
+    if (e->host_trace && e->hf_n)
+        fprintf(stderr, "pilon_b200 pb_region_finish over %ld calls, host us per call: enqueue pass %.0f, wait pass %.0f, indel groups (copy, strings) %.0f, "
+                "enqueue download %.0f, wait download %.0f, scalars + string pool %.0f, sort + fill indels %.0f, free batches %.0f\n",
+                e->hf_n, e->hf[0] / e->hf_n, e->hf[1] / e->hf_n, e->hf[2] / e->hf_n, e->hf[3] / e->hf_n, e->hf[4] / e->hf_n, e->hf[5] / e->hf_n,
+                e->hf[6] / e->hf_n, e->hf[7] / e->hf_n);
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     free_batches(e);
     cudaStreamSynchronize(e->stream);
     DBuf* all[] = {&e->d_batches, &e->d_pile, &e->extra, &e->head, &e->ref, &e->rare_bits, &e->pc_diff, &e->block_sums, &e->scalars,
                    &e->o_cnt, &e->o_qs, &e->o_wq, &e->o_wmq, &e->o_flags, &e->o_call, &e->ev_key, &e->ev, &e->perm,
-                   &e->groups, &e->cand, &e->work, &e->spill_scratch, &e->str_pool, &e->cub_tmp};
+                   &e->groups, &e->cand, &e->work, &e->spill_scratch, &e->str_pool, &e->cub_tmp, &e->call_idx, &e->call_entries};
     for (DBuf* b : all) b->release();
     e->rare.release(); for (auto& b : e->gplane) b.release();
     for (auto& b : e->o_i32) b.release();
     if (e->h_sc) cudaFreeHost(e->h_sc);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->evp0); cudaEventDestroy(e->evp1);
-    cudaEventDestroy(e->ev_sc); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join);
+    cudaEventDestroy(e->ev_sc); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); cudaEventDestroy(e->ev_stage);
+    if (e->ref_stage) cudaFreeHost(e->ref_stage);
     cudaStreamDestroy(e->stream2);
     cudaStreamDestroy(e->stream);
     delete e;
@@ -193,7 +212,11 @@ extern "C" int pb_region_begin(pb_engine* e, const uint8_t* contig, int64_t cont
     if (S >= (1ll << 30)) return fail(PB_ERR_INVALID, "region too large (size must be < 2^30)");
     CK(cudaSetDevice(e->device));
     cudaStream_t s = e->stream;
+    auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_prev = e->host_trace ? now() : 0.0;
+    auto lap = [&](int k) { if (e->host_trace) { const double t = now(); if (e->ht_calls >= 8) e->ht[k] += t - t_prev; t_prev = t; } };   // (the first calls grow buffers)
     if (free_batches(e) != PB_OK) return PB_ERR_CUDA;
+    lap(0);
     if (e->phase_timing) CK(cudaEventRecord(e->ph[0], s));
     RegionDev& R = e->R;
     R = RegionDev{};
@@ -203,7 +226,30 @@ extern "C" int pb_region_begin(pb_engine* e, const uint8_t* contig, int64_t cont
     R.cfg = e->cfg;
     const size_t ref_bytes = (size_t)(R.ref_end - R.ref_locus0 + 1);
     CK(e->ref.ensure(ref_bytes + 8, false, s));                                     // k_rebuild_bases reads whole words
-    CK(cudaMemcpyAsync(e->ref.p, contig + (R.ref_locus0 - 1), ref_bytes, cudaMemcpyHostToDevice, s));
+    {
+        // A cudaMemcpyAsync from PAGEABLE memory is synchronous and waits its turn on the copy engine -- behind the other host
+        // threads' batch uploads (measured: 1.5-3.8 ms per call, 20 calls per C2 step).  Unless the caller's contig is pinned,
+        // the window goes through a pinned staging buffer of the engine's own: a host memcpy, then a truly asynchronous copy.
+        const uint8_t* src = contig + (R.ref_locus0 - 1);
+        cudaPointerAttributes at;
+        const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        if (!pinned) {
+            cudaGetLastError();
+            if (ref_bytes > e->ref_stage_cap) {
+                if (e->ref_stage) { CK(cudaEventSynchronize(e->ev_stage)); CK(cudaFreeHost(e->ref_stage)); e->ref_stage = nullptr; e->ref_stage_cap = 0; }
+                const size_t want = ref_bytes + ref_bytes / 8 + 4096;
+                CK(cudaHostAlloc((void**)&e->ref_stage, want, cudaHostAllocDefault));
+                e->ref_stage_cap = want;
+            } else {
+                CK(cudaEventSynchronize(e->ev_stage));        // the previous region's copy out of the staging buffer is done
+            }
+            memcpy(e->ref_stage, src, ref_bytes);
+            src = e->ref_stage;
+        }
+        CK(cudaMemcpyAsync(e->ref.p, src, ref_bytes, cudaMemcpyHostToDevice, s));
+        if (!pinned) CK(cudaEventRecord(e->ev_stage, s));
+    }
+    lap(1);
     R.ref = e->ref.as<uint8_t>();
     R.contig_len = contig_len; R.extra = nullptr; R.head = nullptr; R.head_len = 0;
     e->contig_host = contig;
@@ -213,6 +259,7 @@ extern "C" int pb_region_begin(pb_engine* e, const uint8_t* contig, int64_t cont
         if (e->h_sc->error) e->dirty = true;
     }
     e->unverified = false;
+    lap(2);
     if (e->dirty) { int rcc = clean_sparse_planes(e); if (rcc != PB_OK) return rcc; e->dirty = false; }
     const size_t n4 = (size_t)S * 4;
     CK(e->rare.ensure((size_t)S * sizeof(Rare), true, s));
@@ -227,6 +274,7 @@ extern "C" int pb_region_begin(pb_engine* e, const uint8_t* contig, int64_t cont
     CK(e->o_flags.ensure((size_t)S, false, s)); CK(e->o_call.ensure((size_t)S * 8, false, s));
     const int nblocks = (int)((S + SCAN_TILE - 1) / SCAN_TILE);
     CK(e->block_sums.ensure((size_t)nblocks * 8, false, s));
+    lap(3); if (e->ht_calls++ >= 8) e->ht_n++;
     R.sc = e->scalars.as<Scalars>();
     R.slots = reinterpret_cast<ScalarSlot*>(static_cast<uint8_t*>(e->scalars.p) + sizeof(Scalars));
     R.batch_bc = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(e->scalars.p) + SC_BC_OFF);
@@ -808,18 +856,61 @@ extern "C" int pb_region_compute_timed(pb_engine* e, int iters, float* total_ms,
     return PB_OK;
 }
 
+// pb_region_result.calls: the loci whose call changes or questions the reference, in locus order -- an ordered stream
+// compaction over the flags plane (1 byte per locus), then a gather of (locus, flags, call).  The count goes into the
+// region scalars and comes back with them: no extra synchronisation.
+namespace {
+struct ChangedOrAmbiguous {
+    const uint8_t* fl;
+    __device__ bool operator()(int32_t i) const { return (fl[i] & (PB_FL_CHANGED | PB_FL_AMBIGUOUS)) != 0; }
+};
+__global__ void __launch_bounds__(256) k_call_entries(RegionDev R, const int32_t* __restrict__ idx, pb_call_entry* __restrict__ out, int64_t cap) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = R.sc->n_calls < cap ? R.sc->n_calls : cap;
+    if (t >= n) return;
+    const int32_t i = idx[t];
+    pb_call_entry en; en.locus_index = i; en.flags = R.o_flags[i]; en.call = R.o_call[i];
+    out[t] = en;
+}
+}  // namespace
+
+static int select_calls(pb_engine* e, int64_t cap) {
+    cudaStream_t s = e->stream;
+    RegionDev& R = e->R;
+    const int S = (int)R.size;
+    CK(e->call_idx.ensure((size_t)S * 4 + 16, false, s));
+    CK(e->call_entries.ensure((size_t)cap * sizeof(pb_call_entry) + 16, false, s));
+    thrust::counting_iterator<int32_t> it(0);
+    ChangedOrAmbiguous pred{R.o_flags};
+    size_t tmp = 0;
+    CK(cub::DeviceSelect::If(nullptr, tmp, it, e->call_idx.as<int32_t>(), &R.sc->n_calls, S, pred, s));
+    CK(e->cub_tmp.ensure(tmp + 16, false, s));
+    CK(cub::DeviceSelect::If(e->cub_tmp.p, tmp, it, e->call_idx.as<int32_t>(), &R.sc->n_calls, S, pred, s));
+    if (cap) k_call_entries<<<(unsigned)((cap + 255) / 256), 256, 0, s>>>(R, e->call_idx.as<int32_t>(), e->call_entries.as<pb_call_entry>(), cap);
+    e->launches += 3;
+    return PB_OK;
+}
+
 extern "C" int pb_region_finish(pb_engine* e, pb_region_result* res, int32_t* const* insert_sizes_out) {
     if (!e || !res) return fail(PB_ERR_INVALID, "null argument");
     if (!e->in_region) return fail(PB_ERR_INVALID, "pb_region_begin has not been called");
     CK(cudaSetDevice(e->device));
     cudaStream_t s = e->stream;
     RegionDev& R = e->R;
+    if (res->calls_cap < 0) return fail(PB_ERR_INVALID, "calls_cap < 0");
+    auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_prev = e->host_trace ? now() : 0.0;
+    auto lap = [&](int k) { if (e->host_trace) { const double t = now(); if (e->hf_calls >= 8) e->hf[k] += t - t_prev; t_prev = t; } };
+    const int64_t calls_cap = res->calls ? std::min<int64_t>(res->calls_cap, R.size) : 0;
     for (int attempt = 0;; attempt++) {
         if (e->phase_timing && attempt == 0) CK(cudaEventRecord(e->ph[1], s));
         int rc = compute(e, false, attempt > 0);
+        if (rc == PB_OK && calls_cap) rc = select_calls(e, calls_cap);
         if (rc != PB_OK) { cudaStreamSynchronize(s); return rc; }
+        lap(0);
         CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
+        lap(1);
         if (e->h_sc->error == 2 && attempt == 0) {       // the I/D bound did not hold (I/D-only CIGARs): once more, full capacity
             if ((rc = clean_sparse_planes(e)) != PB_OK) return rc;
             continue;
@@ -842,6 +933,7 @@ extern "C" int pb_region_finish(pb_engine* e, pb_region_result* res, int32_t* co
         k_groups_clear<<<(ng + 127) / 128, 128, 0, s>>>(R, ng); e->launches++;
         CK(cudaMemcpyAsync(groups.data(), R.groups, sizeof(Group) * ng, cudaMemcpyDeviceToHost, s));
     }
+    lap(2);
     const size_t S = (size_t)R.size;
 #define D2H(dst, src, bytes) if (res->dst) CK(cudaMemcpyAsync(res->dst, src, (bytes), cudaMemcpyDeviceToHost, s))
     D2H(base_count4, R.o_cnt, S * 16); D2H(qual_sum4, R.o_qs, S * 32);
@@ -851,13 +943,18 @@ extern "C" int pb_region_finish(pb_engine* e, pb_region_result* res, int32_t* co
     D2H(coverage_arr, R.o_cov, S * 4); D2H(frag_coverage, R.o_frag, S * 4);
     D2H(weighted_qual, R.o_wq, S); D2H(weighted_mq, R.o_wmq, S); D2H(flags, R.o_flags, S); D2H(call, R.o_call, S * 8);
 #undef D2H
+    res->n_calls = calls_cap ? (int64_t)e->h_sc->n_calls : 0;
+    if (calls_cap && res->n_calls)
+        CK(cudaMemcpyAsync(res->calls, e->call_entries.p, (size_t)std::min(res->n_calls, calls_cap) * sizeof(pb_call_entry), cudaMemcpyDeviceToHost, s));
     if (insert_sizes_out)
         for (size_t i = 0; i < e->batches.size(); i++)
             if (insert_sizes_out[i] && e->batches[i].d.n_reads)
                 CK(cudaMemcpyAsync(insert_sizes_out[i], e->batches[i].d.insert_out, (size_t)e->batches[i].d.n_reads * 4, cudaMemcpyDeviceToHost, s));
     std::vector<uint8_t> pool;
     if (e->phase_timing) CK(cudaEventRecord(e->ph[3], s));
+    lap(3);
     CK(cudaStreamSynchronize(s));
+    lap(4);
     if (e->phase_timing) {
         for (int i = 0; i < 3; i++) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, e->ph[i], e->ph[i + 1])); e->ph_ms[i] += ms; }
         e->ph_regions++;
@@ -871,6 +968,7 @@ extern "C" int pb_region_finish(pb_engine* e, pb_region_result* res, int32_t* co
     const size_t nbytes = (size_t)e->h_sc->str_bytes;
     if (nbytes) { pool.resize(nbytes); CK(cudaMemcpy(pool.data(), R.str_pool, nbytes, cudaMemcpyDeviceToHost)); }
     e->dirty = false;
+    lap(5);
     // scalars
     const Scalars& sc = *e->h_sc;
     res->size = R.size; res->base_count = (int64_t)sc.base_count; res->coverage = sc.coverage;
@@ -903,7 +1001,9 @@ extern "C" int pb_region_finish(pb_engine* e, pb_region_result* res, int32_t* co
         ni++; nbo += g.win_len;
     }
     res->n_indels = ni; res->n_indel_bytes = nbo;
+    lap(6);
     if (free_batches(e) != PB_OK) return PB_ERR_CUDA;
+    lap(7); if (e->hf_calls++ >= 8) e->hf_n++;
     e->in_region = false;
     return PB_OK;
 }

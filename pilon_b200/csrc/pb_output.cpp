@@ -295,7 +295,9 @@ extern "C" int pb_out_create(const pb_region_result* res, const uint8_t* contig,
     if (!res || !contig || !name || !cfg || !out) return fail_out(PB_ERR_INVALID, "null argument");
     if (start < 1 || stop < start || stop > contig_len || res->size != (int64_t)stop + 1 - start)
         return fail_out(PB_ERR_INVALID, "region does not match the result");
-    if (!res->flags || !res->call) return fail_out(PB_ERR_INVALID, "the result must carry the flags and call planes");
+    const bool sparse = !res->call && res->calls;      // the call plane in sparse form: changed / ambiguous loci only
+    if (!res->flags || (!res->call && !res->calls)) return fail_out(PB_ERR_INVALID, "the result must carry the flags plane and the call plane or its sparse form (calls)");
+    if (sparse && res->n_calls > res->calls_cap) return fail_out(PB_ERR_INVALID, "the result's sparse call entries were truncated (calls_cap too small)");
     if (res->n_indels > res->indels_cap || res->n_indel_bytes > res->indel_bytes_cap)
         return fail_out(PB_ERR_INVALID, "the result's indel evidence was truncated (indels_cap / indel_bytes_cap too small)");
     if (res->n_indels > 0 && (!res->indels || (res->n_indel_bytes > 0 && !res->indel_bytes)))
@@ -316,6 +318,7 @@ extern "C" int pb_out_create(const pb_region_result* res, const uint8_t* contig,
     }
     // ---- identifyAndFixIssues (:307-380, 413) ----
     pb_out_stats& st = o->stats;
+    int64_t next_call = 0;
     for (int64_t i = 0; i < o->size; i++) {
         const uint8_t fl = res->flags[i];
         if (fl & PB_FL_CONFIRMED) st.confirmed++;
@@ -323,7 +326,17 @@ extern "C" int pb_out_create(const pb_region_result* res, const uint8_t* contig,
         if (!(fl & (PB_FL_CHANGED | PB_FL_AMBIGUOUS))) continue;
         const int kind = (fl >> PB_FL_KIND_SHIFT) & 3;
         const int32_t loc = (int32_t)(start + i);
-        const uint64_t call = res->call[i];
+        uint64_t call;
+        if (sparse) {
+            while (next_call < res->n_calls && (int64_t)res->calls[next_call].locus_index < i) next_call++;
+            if (next_call >= res->n_calls || (int64_t)res->calls[next_call].locus_index != i) {
+                delete o;
+                return fail_out(PB_ERR_INVALID, "sparse call entries do not match the flags plane");
+            }
+            call = res->calls[next_call].call;
+        } else {
+            call = res->call[i];
+        }
         const std::string rBase(1, o->ref_base(loc)), cBase(1, "ACGTN"[PB_CALL_BASE(call)]);
         switch (kind) {
             case PB_KIND_SNP:
@@ -425,8 +438,8 @@ extern "C" int pb_out_vcf(pb_region_out* o, int threads, const char** text, int6
     if (!o || !text || !n) return fail_out(PB_ERR_INVALID, "null argument");
     const pb_region_result* r = o->res;
     if (!r->base_count4 || !r->qual_sum4 || !r->mq_sum || !r->phys_cov || !r->bad_pair || !r->deletions || !r->del_qual ||
-        !r->insertions || !r->ins_qual || !r->clips)
-        return fail_out(PB_ERR_INVALID, "pb_out_vcf needs every PileUp counter plane in the result");
+        !r->insertions || !r->ins_qual || !r->clips || !r->call)
+        return fail_out(PB_ERR_INVALID, "pb_out_vcf needs every PileUp counter plane and the call plane in the result");
     const auto dups = duplication_events(*o);
     const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(threads > 0 ? threads : 1, o->size / 4096 + 1));
     std::vector<std::string> parts((size_t)nt);

@@ -93,15 +93,17 @@ class Engine:
 
     def run_region(self, contig: bytes, start: int, stop: int, batches: Sequence[Tuple[ReadBatch, bool]],
                    planes: Optional[Sequence[str]] = None, indels_cap: int = 1 << 16,
-                   bytes_cap: int = 1 << 20, pinned: bool = False):
-        """begin + add every (batch, counts_toward_frag_coverage[, longReadType]) + finish."""
+                   bytes_cap: int = 1 << 20, pinned: bool = False, calls_cap: Optional[int] = None):
+        """begin + add every (batch, counts_toward_frag_coverage[, longReadType]) + finish.  calls_cap: entries of the
+        sparse call list (pb_region_result.calls) to make room for; default = one per locus up to 2^20."""
         self.region_begin(contig, start, stop)
         inserts = []
         for bt in batches:
             rb, frag, long_read = bt if len(bt) == 3 else (bt[0], bt[1], 0)
             self.add_batch(rb, frag, long_read)
             inserts.append(np.zeros(rb.n_reads, np.int32))
-        res = ResultBuffers(stop + 1 - start, planes, indels_cap, bytes_cap, pinned)
+        size = stop + 1 - start
+        res = ResultBuffers(size, planes, indels_cap, bytes_cap, pinned, calls_cap=min(size, 1 << 20) if calls_cap is None else calls_cap)
         self.finish(res, inserts)
         return res, inserts
 

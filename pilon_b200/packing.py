@@ -235,7 +235,7 @@ class ResultBuffers:
     """Caller-owned host arrays behind a `pb_region_result`."""
 
     def __init__(self, size: int, planes: Optional[Sequence[str]] = None, indels_cap: int = 0,
-                 indel_bytes_cap: int = 0, pinned: bool = False, batch_cap: int = 256):
+                 indel_bytes_cap: int = 0, pinned: bool = False, batch_cap: int = 256, calls_cap: int = 0):
         self.size = size
         self.arrays = {}
         self.c = capi.pb_region_result()
@@ -262,6 +262,19 @@ class ResultBuffers:
         self.c.batch_base_count = self.batch_base_count.ctypes.data
         self.c.batch_coverage = self.batch_coverage.ctypes.data
         self.c.batch_cap = batch_cap
+        # the call plane in sparse form (pb_region_result.calls): changed / ambiguous loci only
+        self.calls_cap = calls_cap
+        if calls_cap:
+            self._calls = _alloc(calls_cap, np.dtype(capi.CALL_ENTRY_DTYPE), pinned)
+            self.c.calls = self._calls.ctypes.data
+            self.c.calls_cap = calls_cap
+
+    def calls(self) -> np.ndarray:
+        """The entries written (locus_index, flags, call); raises if the capacity was too small."""
+        n = int(self.c.n_calls)
+        if n > self.calls_cap:
+            raise ValueError("calls_cap %d < %d changed / ambiguous loci" % (self.calls_cap, n))
+        return self._calls[:n]
 
     def __getitem__(self, name: str) -> np.ndarray:
         a = self.arrays[name]

@@ -59,7 +59,7 @@ def run_c_oracle(contig: bytes, start: int, stop: int, batches: Sequence[Tuple[R
             rc = lib.po_region_add_batch(reg, C.byref(cb), int(frag), int(long_read), ins.ctypes.data)
             assert rc == 0
             inserts.append(ins)
-        res = ResultBuffers(stop + 1 - start, indels_cap=indels_cap, indel_bytes_cap=bytes_cap)
+        res = ResultBuffers(stop + 1 - start, indels_cap=indels_cap, indel_bytes_cap=bytes_cap, calls_cap=min(stop + 1 - start, 1 << 20))
         assert lib.po_region_finish(reg, C.byref(res.c)) == 0
     finally:
         lib.po_region_free(reg)
@@ -154,6 +154,24 @@ def assert_results_equal(a: ResultBuffers, b: ResultBuffers, what: str = ""):
     for ea, eb in zip(ia, ib):
         assert (ea["locus_index"], ea["kind"], ea["list_len"]) == (eb["locus_index"], eb["kind"], eb["list_len"]), (ea, eb)
         assert _winner(ea) == _winner(eb), (ea, eb)
+    # the call plane in sparse form: against the other side's entries and against the planes it abbreviates
+    for r in (a, b):
+        if r.calls_cap and "flags" in r.arrays and "call" in r.arrays:
+            assert_calls_match_planes(r, r, what)
+    if a.calls_cap and b.calls_cap:
+        assert a.c.n_calls == b.c.n_calls, "%s n_calls: %d != %d" % (what, a.c.n_calls, b.c.n_calls)
+        assert np.array_equal(a.calls(), b.calls()), "%s sparse call entries differ" % what
+
+
+def assert_calls_match_planes(sparse: ResultBuffers, full: ResultBuffers, what: str = ""):
+    """pb_region_result.calls == [(i, flags[i], call[i]) for the loci with a changing / ambiguous call], in locus order."""
+    fl = full["flags"]
+    idx = np.flatnonzero(fl & (capi.PB_FL_CHANGED | capi.PB_FL_AMBIGUOUS))
+    got = sparse.calls()
+    assert int(sparse.c.n_calls) == len(idx), "%s n_calls %d != %d flagged loci" % (what, sparse.c.n_calls, len(idx))
+    assert np.array_equal(got["locus_index"], idx.astype(np.int32)), "%s sparse call loci differ" % what
+    assert np.array_equal(got["flags"], fl[idx].astype(np.uint32)), "%s sparse call flags differ" % what
+    assert np.array_equal(got["call"], full["call"][idx]), "%s sparse call records differ" % what
 
 
 def _winner(e):

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 15
     for n in names:
         assert hasattr(lib, n), "libpilonb200.so does not export %s" % n
-    assert lib.pb_abi_version() == capi.ABI_VERSION == 5
+    assert lib.pb_abi_version() == capi.ABI_VERSION == 6
 
 
 def test_struct_sizes_match_header():
@@ -34,7 +34,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(capi.pb_config) == 40
     assert C.sizeof(capi.pb_batch) == 4 * 8 + 13 * 8 + 8 + 8 + 16 + 24
     assert C.sizeof(capi.pb_indel) == 32
-    assert C.sizeof(capi.pb_region_result) == 4 * 8 + 4 * 4 + 2 * 8 + 18 * 8 + 4 * 8 + 5 * 8
+    assert C.sizeof(capi.pb_region_result) == 4 * 8 + 4 * 4 + 2 * 8 + 18 * 8 + 4 * 8 + 5 * 8 + 3 * 8
 
 
 def test_engine_rejects_bad_arguments_without_a_gpu():

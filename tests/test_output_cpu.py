@@ -133,3 +133,63 @@ def test_wiggle_tracks_are_per_locus_maps_of_the_planes():
             assert [int(x) for x in lines[1:]] == [int(x) for x in want]
     finally:
         ro.close()
+
+
+def minimal_fix_result(res):
+    """What a `--fix snps,indels --changes` caller downloads: flags, frag_coverage, the sparse call entries and the
+    indel evidence -- the same pb_region_result with every other plane NULL."""
+    from pilon_b200.packing import ResultBuffers
+    m = ResultBuffers(res.size, ["flags", "frag_coverage"], indels_cap=res.indels_cap, indel_bytes_cap=res.indel_bytes_cap,
+                      calls_cap=max(1, int(res.c.n_calls)))
+    m["flags"][:] = res["flags"]
+    m["frag_coverage"][:] = res["frag_coverage"]
+    m._calls[:int(res.c.n_calls)] = res.calls()
+    m.c.n_calls = res.c.n_calls
+    m._indels = res._indels if res.indels_cap else None
+    if res.indels_cap:
+        import ctypes as C
+        m.c.indels = C.addressof(res._indels)
+    if res.indel_bytes_cap:
+        m.indel_bytes = res.indel_bytes
+        m.c.indel_bytes = res.indel_bytes.ctypes.data
+    for f in ("size", "base_count", "coverage", "aligned_bases", "read_count", "min_depth", "unknown_ops", "dropped_oob", "n_indels",
+              "n_indel_bytes", "n_batches"):
+        setattr(m.c, f, getattr(res.c, f))
+    return m
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fix_outputs_from_the_minimal_result_equal_those_from_every_plane(seed):
+    """flags + frag_coverage + sparse call entries are all the fix path reads (GenomeRegion.scala:275-283, 307-380): the
+    FASTA bases, the change list, the statistics and the log are identical to what the full planes give."""
+    if seed < 4:
+        contig, start, stop, reads = H.random_case(seed, contig_len=900, n_reads=400)
+        groups = H.split_batches(reads, random.Random(seed))
+    else:
+        contig, start, stop, reads = H.clean_case(seed, n=20000, start=1001, stop=18000, depth=12, n_sites=30)
+        groups = [(reads, True)]
+    cfg = po.Config(iupac=seed % 2 == 1)
+    res, _ = H.run_c_oracle(contig, start, stop, [(pack_records(g), f) for g, f in groups], cfg, indels_cap=1 << 18, bytes_cap=1 << 22)
+    H.assert_calls_match_planes(res, res)
+    ocfg = out.OutputConfig(iupac=cfg.iupac)
+    full = out.RegionOutput(res, contig, "c|1", start, stop, ocfg)
+    m = minimal_fix_result(res)
+    mini = out.RegionOutput(m, contig, "c|1", start, stop, ocfg)
+    try:
+        assert mini.stats == full.stats and mini.bases == full.bases and mini.log() == full.log()
+        assert np.array_equal(mini.copyNumber, full.copyNumber)
+        assert mini.writeChanges() == full.writeChanges()
+        if seed >= 4:
+            assert full.stats["n_fixes"] > 10
+    finally:
+        full.close(); mini.close()
+
+
+def test_truncated_sparse_calls_are_refused():
+    contig, start, stop, reads = H.clean_case(4, n=20000, start=1001, stop=18000, depth=12, n_sites=30)
+    res, _ = H.run_c_oracle(contig, start, stop, [(pack_records(reads), True)], indels_cap=1 << 18, bytes_cap=1 << 22)
+    m = minimal_fix_result(res)
+    assert m.c.n_calls > 2
+    m.c.calls_cap = int(m.c.n_calls) - 1
+    with pytest.raises(Exception):
+        out.RegionOutput(m, contig, "c|1", start, stop)

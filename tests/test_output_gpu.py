@@ -99,3 +99,48 @@ def test_fasta_and_bams_in_fasta_changes_vcf_out(tmp_path):
     assert got("fasta") == want_fa
     assert got("changes") == want_ch and len(want_ch) > 5
     assert [l for l in got("vcf") if not l.startswith("#")] == vcf.lines
+
+
+@pytest.mark.parametrize("seed", [2, 5])
+def test_fix_outputs_from_the_minimal_download(seed):
+    """The e2e arm's default result set (bench.py FIXMIN_PLANES): flags + frag_coverage + the sparse call entries the
+    engine compacts on the device.  FASTA bases, change list, statistics and log are those of the literal oracle chain."""
+    contig, start, stop, reads = H.clean_case(seed, n=30000, start=1501, stop=28000, depth=12, n_sites=40)
+    ocfg = oo.OutConfig()
+    gr = oracle_outputs(contig, start, stop, [(reads, True)], None, ocfg)
+    e = Engine(0)
+    try:
+        packed = [(pack_records(reads), True)]
+        full, _ = e.run_region(contig, start, stop, packed, indels_cap=1 << 18, bytes_cap=1 << 22)
+        mini, _ = e.run_region(contig, start, stop, packed, planes=["flags", "frag_coverage"], indels_cap=1 << 18, bytes_cap=1 << 22)
+    finally:
+        e.close()
+    assert mini.c.call is None and mini.c.n_calls > 20
+    H.assert_calls_match_planes(mini, full, "minimal download")
+    ro = out.RegionOutput(mini, contig, "ctg|1", start, stop)
+    try:
+        st = ro.stats
+        for k, v in gr.stats.items():
+            key = {"nonN": "non_n", "insBases": "ins_bases", "delBases": "del_bases"}.get(k, k)
+            assert st[key] == v, (k, st[key], v)
+        assert ro.bases == bytes(gr.bases)
+        assert [l for l in ro.log() if not l.startswith("Fix mismatch")] == [l for l in gr.loglines if not l.startswith("Fix mismatch")]
+        assert ro.writeChanges() == gr.writeChanges()
+        assert st["n_fixes"] > 20
+    finally:
+        ro.close()
+
+
+def test_sparse_calls_beyond_the_capacity_are_counted_not_written():
+    contig, start, stop, reads = H.clean_case(6, n=20000, start=1, stop=20000, depth=12, n_sites=40)
+    e = Engine(0)
+    try:
+        packed = [(pack_records(reads), True)]
+        full, _ = e.run_region(contig, start, stop, packed)
+        small, _ = e.run_region(contig, start, stop, packed, calls_cap=5)
+    finally:
+        e.close()
+    assert small.c.n_calls == full.c.n_calls > 5
+    assert (small._calls == full.calls()[:5]).all()
+    with pytest.raises(ValueError):
+        small.calls()
