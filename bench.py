@@ -1006,7 +1006,7 @@ def main():
                     "records), fix = the ten per-locus arrays of the fix + tracks path, vcf = every plane")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-workers", type=int, default=3, help="host threads per GPU in the e2e arm")
-    ap.add_argument("--e2e-depth", type=int, default=1, help="regions in flight per host thread in the e2e arm (one engine "
+    ap.add_argument("--e2e-depth", type=int, default=2, help="regions in flight per host thread in the e2e arm (one engine "
                     "and one result set each): the next region uploads while the previous one computes and downloads")
     ap.add_argument("--no-base-deltas", dest="base_deltas", action="store_false", help="e2e arm: upload the bases as 2-bit codes "
                     "instead of their deltas against the reference (pb_base_delta_encode; 5 B per differing base)")

@@ -59,9 +59,48 @@ struct DBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Device memory of one region's batches (uploaded arrays, segment tables, ...): bump allocation out of blocks the engine
+// keeps.  The stream-ordered allocator it replaces cost ~30 calls per region and, with several regions in flight, grew its
+// pool in the middle of timed steps (an implicit device synchronisation: add_batch calls of 70-560 ms, profiles/README.md
+// r2q).  Everything that used the arena is stream-ordered before the next region's uploads, so reset() is just a rewind;
+// when a region needed more than one block the blocks are merged into one (cudaFree / cudaMalloc: warm-up only).
+struct Arena {
+    struct Block { void* p; size_t cap; };
+    std::vector<Block> blocks;
+    size_t cur = 0, off = 0, used = 0, high = 0;
+    cudaError_t alloc(size_t bytes, void** out) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        while (cur < blocks.size() && off + bytes > blocks[cur].cap) { cur++; off = 0; }
+        if (cur == blocks.size()) {
+            const size_t cap = std::max(bytes, (size_t)64 << 20);
+            void* p = nullptr;
+            cudaError_t e = cudaMalloc(&p, cap);
+            if (e != cudaSuccess) return e;
+            blocks.push_back({p, cap}); off = 0;
+        }
+        *out = static_cast<uint8_t*>(blocks[cur].p) + off;
+        off += bytes; used += bytes;
+        return cudaSuccess;
+    }
+    cudaError_t reset() {
+        high = std::max(high, used);
+        if (blocks.size() > 1) {                     // (cudaFree waits for the device: nothing is using the blocks afterwards)
+            for (auto& b : blocks) { cudaError_t e = cudaFree(b.p); if (e != cudaSuccess) return e; }
+            blocks.clear();
+            const size_t cap = high + high / 8 + ((size_t)1 << 20);
+            void* p = nullptr;
+            cudaError_t e = cudaMalloc(&p, cap);
+            if (e != cudaSuccess) return e;
+            blocks.push_back({p, cap});
+        }
+        cur = off = used = 0;
+        return cudaSuccess;
+    }
+    void release() { for (auto& b : blocks) cudaFree(b.p); blocks.clear(); cur = off = used = 0; }
+};
+
 struct HostBatch {
     DevBatch d;                      // device view
-    std::vector<void*> owned;        // device allocations owned by this batch (cudaMallocAsync)
 };
 
 }  // namespace
@@ -75,6 +114,7 @@ struct pb_engine {
     bool in_region = false;
     RegionDev R{};
     std::vector<HostBatch> batches;
+    Arena arena;                     // device memory of the current region's batches
     DBuf d_batches, d_pile;          // DevBatch[] image; PileBatch[] image (only for > PB_MAXB batches)
     // per-locus buffers
     DBuf ref, rare, gplane[2], rare_bits, pc_diff, block_sums, scalars, extra, head;
@@ -114,9 +154,8 @@ static void drop_graph(pb_engine* e) {
 }
 static int free_batches(pb_engine* e) {
     drop_graph(e);
-    for (auto& hb : e->batches)
-        for (void* p : hb.owned) CK(cudaFreeAsync(p, e->stream));
     e->batches.clear();
+    CK(e->arena.reset());
     return PB_OK;
 }
 
@@ -191,6 +230,7 @@ extern "C" int pb_destroy(pb_engine* e) {
                    &e->o_cnt, &e->o_qs, &e->o_wq, &e->o_wmq, &e->o_flags, &e->o_call, &e->ev_key, &e->ev, &e->perm,
                    &e->groups, &e->cand, &e->work, &e->spill_scratch, &e->str_pool, &e->cub_tmp, &e->call_idx, &e->call_entries};
     for (DBuf* b : all) b->release();
+    e->arena.release();
     e->rare.release(); for (auto& b : e->gplane) b.release();
     for (auto& b : e->o_i32) b.release();
     if (e->h_sc) cudaFreeHost(e->h_sc);
@@ -214,7 +254,7 @@ extern "C" int pb_region_begin(pb_engine* e, const uint8_t* contig, int64_t cont
     cudaStream_t s = e->stream;
     auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_prev = e->host_trace ? now() : 0.0;
-    auto lap = [&](int k) { if (e->host_trace) { const double t = now(); if (e->ht_calls >= 8) e->ht[k] += t - t_prev; t_prev = t; } };   // (the first calls grow buffers)
+    auto lap = [&](int k) { if (e->host_trace) { const double t = now(); if (e->ht_calls >= 8) { e->ht[k] += t - t_prev; if (t - t_prev > 30e3) fprintf(stderr, "pilon_b200 slow: pb_region_begin section %d took %.1f ms (call %ld, size %lld)\n", k, (t - t_prev) / 1e3, e->ht_calls, (long long)S); } t_prev = t; } };   // (the first calls grow buffers)
     if (free_batches(e) != PB_OK) return PB_ERR_CUDA;
     lap(0);
     if (e->phase_timing) CK(cudaEventRecord(e->ph[0], s));
@@ -293,13 +333,12 @@ extern "C" int pb_region_begin(pb_engine* e, const uint8_t* contig, int64_t cont
 }
 
 // Make one batch array visible to the device: device pointers are used in place, host arrays are
-// copied asynchronously into stream-ordered allocations owned by the batch.
+// copied asynchronously into the engine's batch arena.
 template <class T>
 static int stage(pb_engine* e, HostBatch& hb, const T* src, size_t n, int mem, const T** dst) {
     if (mem == PB_MEM_DEVICE) { *dst = src; return PB_OK; }
     void* p = nullptr;
-    CK(cudaMallocAsync(&p, n * sizeof(T) + 64, e->stream));   // kernels fetch aligned 16-byte blocks
-    hb.owned.push_back(p);
+    CK(e->arena.alloc(n * sizeof(T) + 64, &p));               // kernels fetch aligned 16-byte blocks
     if (n) CK(cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
     *dst = (const T*)p;
     return PB_OK;
@@ -496,13 +535,15 @@ extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, in
         return fail(PB_ERR_INVALID, "null per-read array in pb_batch");
     if ((b->n_cigar && !b->cigar) || (b->n_exc && (!b->exc_idx || !b->exc_base || !b->exc_qual))) return fail(PB_ERR_INVALID, "null array in pb_batch");
     CK(cudaSetDevice(e->device));
+    const double t_ab = e->host_trace ? std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count() : 0.0;
     drop_graph(e);                                   // the captured pass belongs to the previous batch set
     // every argument has been validated: from here on only CUDA calls can fail, and then the half-staged batch is withdrawn
     e->batches.emplace_back();
     const int rc_stage = stage_batch(e, b, frag, long_read_type);
-    if (rc_stage != PB_OK) {
-        for (void* p : e->batches.back().owned) cudaFreeAsync(p, e->stream);
-        e->batches.pop_back();
+    if (rc_stage != PB_OK) e->batches.pop_back();      // (its arena space comes back with the region's)
+    if (e->host_trace) {
+        const double dt = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_ab;
+        if (dt > 30e3 && e->ht_calls >= 8) fprintf(stderr, "pilon_b200 slow: pb_region_add_batch took %.1f ms (%lld reads)\n", dt / 1e3, (long long)b->n_reads);
     }
     return rc_stage;
 }
@@ -535,9 +576,9 @@ static int stage_batch(pb_engine* e, const pb_batch* b, int frag, int long_read_
     if (b->mem == PB_MEM_HOST && b->base_delta_idx) {   // compact transport: upload the deltas, rebuild bases2 on the device
         void *pi = nullptr, *pc = nullptr, *pout = nullptr;
         const size_t nd = (size_t)b->n_base_delta;
-        CK(cudaMallocAsync(&pi, nd * 4 + 64, e->stream)); hb.owned.push_back(pi);
-        CK(cudaMallocAsync(&pc, nd + 64, e->stream)); hb.owned.push_back(pc);
-        CK(cudaMallocAsync(&pout, (size_t)b->n_seq / 4 + 64, e->stream)); hb.owned.push_back(pout);
+        CK(e->arena.alloc(nd * 4 + 64, &pi));
+        CK(e->arena.alloc(nd + 64, &pc));
+        CK(e->arena.alloc((size_t)b->n_seq / 4 + 64, &pout));
         if (nd) {
             CK(cudaMemcpyAsync(pi, b->base_delta_idx, nd * 4, cudaMemcpyHostToDevice, e->stream));
             CK(cudaMemcpyAsync(pc, b->base_delta_code, nd, cudaMemcpyHostToDevice, e->stream));
@@ -556,8 +597,8 @@ static int stage_batch(pb_engine* e, const pb_batch* b, int frag, int long_read_
         const size_t groups = ((size_t)b->n_seq + per - 1) / per;
         const size_t in_bytes = ((size_t)b->n_seq * bits + 7) / 8;
         void *pin = nullptr, *pout = nullptr;
-        CK(cudaMallocAsync(&pin, groups * (bits == 4 ? 8 : 12) + 64, e->stream)); hb.owned.push_back(pin);
-        CK(cudaMallocAsync(&pout, groups * per + 64, e->stream)); hb.owned.push_back(pout);
+        CK(e->arena.alloc(groups * (bits == 4 ? 8 : 12) + 64, &pin));
+        CK(e->arena.alloc(groups * per + 64, &pout));
         if (b->n_seq) {
             CK(cudaMemcpyAsync(pin, b->qual_codes, in_bytes, cudaMemcpyHostToDevice, e->stream));
             uint32_t l[4]; memcpy(l, b->qual_lut, 16);
@@ -572,9 +613,9 @@ static int stage_batch(pb_engine* e, const pb_batch* b, int frag, int long_read_
     ST(exc_idx, b->n_exc); ST(exc_base, b->n_exc); ST(exc_qual, b->n_exc);
 #undef ST
     void* p = nullptr;
-    CK(cudaMallocAsync(&p, ((size_t)b->n_cigar + 1) * sizeof(Seg), e->stream)); hb.owned.push_back(p); d.seg = (Seg*)p;
-    CK(cudaMallocAsync(&p, ((size_t)e->R.n_win + 2) * 4, e->stream)); hb.owned.push_back(p); d.win_first = (uint32_t*)p;
-    CK(cudaMallocAsync(&p, (n + 1) * 4, e->stream)); hb.owned.push_back(p); d.insert_out = (int32_t*)p;
+    CK(e->arena.alloc(((size_t)b->n_cigar + 1) * sizeof(Seg), &p)); d.seg = (Seg*)p;
+    CK(e->arena.alloc(((size_t)e->R.n_win + 2) * 4, &p)); d.win_first = (uint32_t*)p;
+    CK(e->arena.alloc((n + 1) * 4, &p)); d.insert_out = (int32_t*)p;
     d.reach = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(e->scalars.p) + SC_REACH_OFF) + 2 * (e->batches.size() - 1);
     return PB_OK;
 }
@@ -900,7 +941,7 @@ extern "C" int pb_region_finish(pb_engine* e, pb_region_result* res, int32_t* co
     if (res->calls_cap < 0) return fail(PB_ERR_INVALID, "calls_cap < 0");
     auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_prev = e->host_trace ? now() : 0.0;
-    auto lap = [&](int k) { if (e->host_trace) { const double t = now(); if (e->hf_calls >= 8) e->hf[k] += t - t_prev; t_prev = t; } };
+    auto lap = [&](int k) { if (e->host_trace) { const double t = now(); if (e->hf_calls >= 8) { e->hf[k] += t - t_prev; if (t - t_prev > 60e3) fprintf(stderr, "pilon_b200 slow: pb_region_finish section %d took %.1f ms (call %ld, size %lld)\n", k, (t - t_prev) / 1e3, e->hf_calls, (long long)R.size); } t_prev = t; } };
     const int64_t calls_cap = res->calls ? std::min<int64_t>(res->calls_cap, R.size) : 0;
     for (int attempt = 0;; attempt++) {
         if (e->phase_timing && attempt == 0) CK(cudaEventRecord(e->ph[1], s));
