@@ -151,11 +151,24 @@ class BaseSumView:
         return ",".join(str(x) for x in self.sums)
 
 
+def _call_record(res, i: int) -> int:
+    """The packed call record of locus index i: from the `call` plane, or -- when only the sparse form was downloaded
+    (pb_region_result.calls: changed / ambiguous loci, the ones GenomeRegion.scala:321-351 looks at) -- from there."""
+    if "call" in res.arrays:
+        return int(res["call"][i])
+    ent = res.calls()
+    k = int(np.searchsorted(ent["locus_index"], i))
+    if k < len(ent) and int(ent["locus_index"][k]) == i:
+        return int(ent["call"][k])
+    raise KeyError("locus index %d has no call record in the sparse list (its call neither changes nor questions the reference); "
+                   "download the `call` plane to read every locus" % i)
+
+
 class BaseCall:
     """PileUp.BaseCall (PileUp.scala:132-173) decoded from the engine's packed call record."""
 
     def __init__(self, pu: "PileUp"):
-        c = int(pu._r["call"][pu._i])
+        c = _call_record(pu._r, pu._i)
         self._pu = pu
         b = c & 7
         self.base = "ACGTN"[b]

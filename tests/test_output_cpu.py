@@ -193,3 +193,18 @@ def test_truncated_sparse_calls_are_refused():
     m.c.calls_cap = int(m.c.n_calls) - 1
     with pytest.raises(Exception):
         out.RegionOutput(m, contig, "c|1", start, stop)
+
+
+def test_facade_reads_call_records_from_the_sparse_list():
+    from pilon_b200.engine import _call_record
+    contig, start, stop, reads = H.clean_case(4, n=20000, start=1001, stop=18000, depth=12, n_sites=30)
+    res, _ = H.run_c_oracle(contig, start, stop, [(pack_records(reads), True)], indels_cap=1 << 18, bytes_cap=1 << 22)
+    m = minimal_fix_result(res)
+    ent = res.calls()
+    assert len(ent) > 10
+    for k in (0, len(ent) // 2, len(ent) - 1):
+        i = int(ent["locus_index"][k])
+        assert _call_record(m, i) == _call_record(res, i) == int(res["call"][i])
+    quiet = int(np.flatnonzero((res["flags"] & 6) == 0)[0])
+    with pytest.raises(KeyError):
+        _call_record(m, quiet)
