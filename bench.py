@@ -150,6 +150,9 @@ _BATCH_FIELDS = [("pos", "n_reads", 4), ("tlen", "n_reads", 4), ("read_len", "n_
                  ("exc_idx", "n_exc", 4), ("exc_base", "n_exc", 1), ("exc_qual", "n_exc", 1)]
 
 
+_META_FIELDS = ("pos", "tlen", "read_len", "mapq", "flags", "cigar_off", "cigar", "seq_off")
+
+
 def _field_bytes(c, count, width):
     n = {"n_reads": c.n_reads, "n_reads+1": c.n_reads + 1, "n_cigar": c.n_cigar, "n_seq": c.n_seq,
          "n_seq/4": c.n_seq // 4, "n_exc": c.n_exc}[count]
@@ -179,8 +182,15 @@ def pin_batch(torch, c):
     DMA; returns the bytes uploaded per pass (4-bit quality codes replace the quality bytes when the batch has them)."""
     rt = torch.cuda.cudart()
     n = 0
+    if c.meta_codes:                                       # compact per-read metadata instead of the eight plain arrays
+        for nm, nb in (("meta_codes", int(c.n_reads) * 8), ("meta_cigar", int(c.n_meta_cigar) * 4), ("meta_esc", int(c.n_meta_esc) * 12)):
+            if nb:
+                _register(rt, getattr(c, nm), nb)
+                n += nb
     for name, count, width in _BATCH_FIELDS:
         nb = _field_bytes(c, count, width)
+        if c.meta_codes and name in _META_FIELDS:
+            continue
         if name == "bases2" and c.base_delta_idx:
             for nm, w in (("base_delta_idx", 4), ("base_delta_code", 1)):
                 if c.n_base_delta:
@@ -423,6 +433,17 @@ def run_gpu_arm(args):
                 b.c.base_delta_idx = b.delta_idx.ctypes.data
                 b.c.base_delta_code = b.delta_code.ctypes.data
                 b.c.n_base_delta = int(b.delta_idx.shape[0]) - 16
+    meta_on = False
+    if args.compact_meta:                                  # 8 bytes per read instead of 22 + 4 per CIGAR op (pb_meta_encode)
+        from pilon_b200.packing import meta_encode
+        encs = [(b, meta_encode(b.c)) for r in regions for b in r.batches]
+        if all(m is not None for _, m in encs):
+            meta_on = True
+            for b, m in encs:
+                b.meta = m
+                codes, cigar, esc, ng, ne, pos0, stride = m
+                b.c.meta_codes, b.c.meta_cigar, b.c.meta_esc = codes.ctypes.data, cigar.ctypes.data, esc.ctypes.data
+                b.c.n_meta_cigar, b.c.n_meta_esc, b.c.meta_pos0, b.c.meta_seq_stride = ng, ne, pos0, stride
     qbits = max([int(b.c.qual_code_bits) for r in regions for b in r.batches] or [0]) if q4 else 8
     h2d = sum(pin_batch(torch, b.c) for r in regions for b in r.batches)
     halo = 16384                                          # PB_REF_HALO: the reference window a pass uploads
@@ -546,24 +567,34 @@ def run_gpu_arm(args):
     # the same arm as round 1 ran it: every array of GenomeRegion.scala:247-253 + the call plane down (35 B per locus) and the
     # bases up as 2-bit codes -- what the minimal result set and the reference deltas bought
     e2e_classic = None
-    if args.planes == "fixmin" and args.base_deltas and world == 1:
+    if args.planes == "fixmin" and args.base_deltas and world == 1:      # (needs the reference deltas on: it re-pins bases2)
         for w in workers:
             for eng, _ in w:
                 eng.close()
         workers = make_workers("fix")
         saved_d = [(b, b.c.base_delta_idx, b.c.base_delta_code, b.c.n_base_delta) for r in regions for b in r.batches]
         h2d_c = h2d
+        saved_m = [(b, b.c.meta_codes) for b, _, _, _ in saved_d]
         for b, _, _, _ in saved_d:
             h2d_c += int(b.c.n_seq) // 4 - 5 * int(b.c.n_base_delta)
             b.c.base_delta_idx = None; b.c.base_delta_code = None; b.c.n_base_delta = 0
             _register(torch.cuda.cudart(), b.c.bases2, int(b.c.n_seq) // 4)
+            if b.c.meta_codes:
+                h2d_c -= int(b.c.n_reads) * 8 + int(b.c.n_meta_cigar) * 4 + int(b.c.n_meta_esc) * 12
+                for name, count, width in _BATCH_FIELDS:
+                    if name in _META_FIELDS and _field_bytes(b.c, count, width):
+                        _register(torch.cuda.cudart(), getattr(b.c, name), _field_bytes(b.c, count, width))
+                        h2d_c += _field_bytes(b.c, count, width)
+                b.c.meta_codes = None
         nc = max(1, min(args.steps, 3))
         tc = timed_variant(nc)
         e2e_classic = {"value": total_aligned / tc, "unit": UNIT, "ms_per_step": 1e3 * tc, "h2d_bytes_per_step": h2d_c,
                        "d2h_bytes_per_step": d2h_bytes("fix", 0), "steps": nc,
-                       "what": "round-1 transport: 2-bit bases up, the ten per-locus arrays of the fix + tracks path down"}
+                       "what": "round-1 transport: plain per-read arrays and 2-bit bases up, the ten per-locus arrays of the fix + tracks path down"}
         for b, di, dc, nd in saved_d:
             b.c.base_delta_idx = di; b.c.base_delta_code = dc; b.c.n_base_delta = nd
+        for b, mc in saved_m:
+            b.c.meta_codes = mc
         for w in workers:
             for eng, _ in w:
                 eng.close()
@@ -667,6 +698,8 @@ def run_gpu_arm(args):
                                          "fix": "the ten per-locus arrays of the fix + tracks path (35 B per locus)", "vcf": "every plane"}[args.planes],
                           "e2e_quals": ("%d-bit codes + table (the workload has <= %d distinct quality bytes), expanded on the device"
                                         % (qbits, 1 << qbits) if q4 else "1 byte per base"),
+                          "e2e_reads": ("8 bytes per read + listed CIGARs + escapes (pb_meta_encode), plain arrays rebuilt on the device" if meta_on
+                                        else "22 bytes per read + 4 per CIGAR op"),
                           "e2e_bases": ("deltas against the reference (5 B per differing base), bases2 rebuilt on the device"
                                         if args.base_deltas else "2 bits per base")},
                "wall_ms_per_step": wall_step_ms, "sequential_ms_per_step": seq_step_ms,
@@ -1010,6 +1043,8 @@ def main():
     ap.add_argument("--e2e-workers", type=int, default=3, help="host threads per GPU in the e2e arm")
     ap.add_argument("--e2e-depth", type=int, default=2, help="regions in flight per host thread in the e2e arm (one engine "
                     "and one result set each): the next region uploads while the previous one computes and downloads")
+    ap.add_argument("--no-compact-meta", dest="compact_meta", action="store_false", help="e2e arm: upload the eight plain per-read arrays "
+                    "instead of 8-byte records (pb_meta_encode)")
     ap.add_argument("--no-base-deltas", dest="base_deltas", action="store_false", help="e2e arm: upload the bases as 2-bit codes "
                     "instead of their deltas against the reference (pb_base_delta_encode; 5 B per differing base)")
     ap.add_argument("--quals8", action="store_true", help="e2e arm: upload one quality byte per base even when the batch "

@@ -120,6 +120,26 @@ typedef struct pb_batch {
     const uint32_t* base_delta_idx;   /* [n_base_delta] or NULL                               */
     const uint8_t*  base_delta_code;  /* [n_base_delta]                                       */
     int64_t n_base_delta;
+    /* Optional compact transport of the per-read arrays (pos, tlen, read_len, mapq, flags, cigar_off, cigar,
+     * seq_off: 22 bytes per read + 4 per CIGAR op) for PB_MEM_HOST batches of short reads: one 8-byte record per
+     * read, little endian,
+     *   bits  0..15  pos - pos of the previous read (of meta_pos0 for the first read); 0xFFFF: see meta_esc
+     *   bits 16..31  tlen as int16; -32768: see meta_esc
+     *   bits 32..39  read_len (0..255)      bits 40..47  mapq      bits 48..55  flags
+     *   bits 56..63  0: the CIGAR is one M over the whole read; n > 0: its n ops are the next n of meta_cigar
+     * meta_esc lists, sorted by read index, the values that do not fit: triples (read index, field, value) with
+     * field 0 = pos delta, 1 = tlen.  seq_off is implied: read r starts at r * meta_seq_stride when that is > 0,
+     * else at the sum of the earlier reads' lengths rounded up to multiples of 4.  When meta_codes is non-NULL
+     * the engine uploads these arrays instead of the eight plain ones (which may then be NULL for the engine) and
+     * rebuilds the plain ones on the device.  pb_meta_encode computes them, or says that the batch cannot be
+     * put this way (reads longer than 255 bases, more than 255 CIGAR ops, another seq_off layout, unsorted). */
+    const uint64_t* meta_codes;       /* [n_reads] or NULL                                    */
+    const uint32_t* meta_cigar;       /* [n_meta_cigar]                                       */
+    const int32_t*  meta_esc;         /* [3 * n_meta_esc]                                     */
+    int64_t n_meta_cigar;
+    int64_t n_meta_esc;
+    int32_t meta_pos0;
+    int32_t meta_seq_stride;
 } pb_batch;
 
 #define PB_REF_HALO 16384   /* loci of reference kept on the device on either side of a region */
@@ -292,6 +312,11 @@ int pb_region_compute(pb_engine* e);
 int pb_base_delta_encode(const pb_batch* b, const uint8_t* contig, int64_t contig_len, int32_t start, int32_t stop,
                          uint32_t** idx_out, uint8_t** code_out, int64_t* n_out);
 void pb_free(void* p);
+
+/* Compact per-read metadata of a host batch (see pb_batch.meta_codes).  Outputs are malloc'ed (release with pb_free).
+ * Returns PB_ERR_UNSUPPORTED, leaving the outputs untouched, when the batch cannot be put this way. */
+int pb_meta_encode(const pb_batch* b, uint64_t** codes_out, uint32_t** cigar_out, int64_t* n_cigar_out,
+                   int32_t** esc_out, int64_t* n_esc_out, int32_t* pos0_out, int32_t* seq_stride_out);
 
 /* Raw CUDA stream handle (cudaStream_t) so callers can order their own copies against the engine. */
 int pb_stream(pb_engine* e, void** stream_out);

@@ -37,7 +37,9 @@ class pb_batch(C.Structure):
                 ("bases2", C.c_void_p), ("exc_idx", C.c_void_p), ("exc_base", C.c_void_p),
                 ("exc_qual", C.c_void_p), ("mem", C.c_int32), ("qual_code_bits", C.c_int32),
                 ("qual_codes", C.c_void_p), ("qual_lut", C.c_uint8 * 16),
-                ("base_delta_idx", C.c_void_p), ("base_delta_code", C.c_void_p), ("n_base_delta", C.c_int64)]
+                ("base_delta_idx", C.c_void_p), ("base_delta_code", C.c_void_p), ("n_base_delta", C.c_int64),
+                ("meta_codes", C.c_void_p), ("meta_cigar", C.c_void_p), ("meta_esc", C.c_void_p),
+                ("n_meta_cigar", C.c_int64), ("n_meta_esc", C.c_int64), ("meta_pos0", C.c_int32), ("meta_seq_stride", C.c_int32)]
 
 
 class pb_indel(C.Structure):
@@ -114,12 +116,15 @@ def load_library() -> C.CDLL:
     lib.pb_packer_view.argtypes = [vp, C.POINTER(pb_batch)]
     lib.pb_base_delta_encode.argtypes = [C.POINTER(pb_batch), vp, i64, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
     lib.pb_base_delta_encode.restype = C.c_int
+    lib.pb_meta_encode.argtypes = [C.POINTER(pb_batch), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64),
+                                   C.POINTER(i32), C.POINTER(i32)]
+    lib.pb_meta_encode.restype = C.c_int
     lib.pb_free.argtypes = [vp]
     lib.pb_free.restype = None
     for name in ("pb_device_count", "pb_create", "pb_destroy", "pb_region_begin", "pb_region_add_batch",
                  "pb_region_finish", "pb_region_compute_timed", "pb_region_compute", "pb_stream", "pb_packer_create",
                  "pb_packer_destroy", "pb_packer_reset", "pb_packer_add", "pb_packer_add_many",
-                 "pb_packer_view", "pb_base_delta_encode"):
+                 "pb_packer_view", "pb_base_delta_encode", "pb_meta_encode"):
         getattr(lib, name).restype = C.c_int
     if lib.pb_abi_version() != ABI_VERSION:
         raise RuntimeError("libpilonb200.so ABI version mismatch")

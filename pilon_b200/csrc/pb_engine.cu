@@ -14,7 +14,9 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
+#include <thrust/iterator/transform_iterator.h>
 #include <thrust/iterator/counting_iterator.h>
 
 #include "pb_pileup7.cuh"
@@ -114,6 +116,7 @@ struct pb_engine {
     bool in_region = false;
     RegionDev R{};
     std::vector<HostBatch> batches;
+    DBuf meta_flag; bool meta_used = false;     // what k_meta_expand found wrong with a batch's compact metadata (checked by the pass)
     Arena arena;                     // device memory of the current region's batches
     DBuf d_batches, d_pile;          // DevBatch[] image; PileBatch[] image (only for > PB_MAXB batches)
     // per-locus buffers
@@ -200,7 +203,8 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
     CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1));
     CK(cudaEventCreate(&e->evp0)); CK(cudaEventCreate(&e->evp1));
     CK(cudaEventCreateWithFlags(&e->ev_sc, cudaEventDisableTiming));
-    CK(cudaMallocHost(&e->h_sc, SC_BYTES));
+    CK(cudaMallocHost(&e->h_sc, SC_BYTES + 16));          // + the compact-metadata flag word
+    CK(e->meta_flag.ensure(16, true, e->stream));
     cudaMemPool_t pool;
     CK(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;
@@ -228,7 +232,7 @@ extern "C" int pb_destroy(pb_engine* e) {
     cudaStreamSynchronize(e->stream);
     DBuf* all[] = {&e->d_batches, &e->d_pile, &e->extra, &e->head, &e->ref, &e->rare_bits, &e->pc_diff, &e->block_sums, &e->scalars,
                    &e->o_cnt, &e->o_qs, &e->o_wq, &e->o_wmq, &e->o_flags, &e->o_call, &e->ev_key, &e->ev, &e->perm,
-                   &e->groups, &e->cand, &e->work, &e->spill_scratch, &e->str_pool, &e->cub_tmp, &e->call_idx, &e->call_entries};
+                   &e->groups, &e->cand, &e->work, &e->spill_scratch, &e->str_pool, &e->cub_tmp, &e->call_idx, &e->call_entries, &e->meta_flag};
     for (DBuf* b : all) b->release();
     e->arena.release();
     e->rare.release(); for (auto& b : e->gplane) b.release();
@@ -293,6 +297,7 @@ extern "C" int pb_region_begin(pb_engine* e, const uint8_t* contig, int64_t cont
     R.ref = e->ref.as<uint8_t>();
     R.contig_len = contig_len; R.extra = nullptr; R.head = nullptr; R.head_len = 0;
     e->contig_host = contig;
+    if (e->meta_used) { CK(cudaMemsetAsync(e->meta_flag.p, 0, 4, s)); e->meta_used = false; }
     if (e->unverified && e->scalars.p) {              // asynchronous passes since the last read-back: did one of them raise a flag?
         CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -485,6 +490,156 @@ extern "C" int pb_base_delta_encode(const pb_batch* b, const uint8_t* contig, in
     return PB_OK;
 }
 
+// Compact per-read metadata (pb_batch.meta_codes): the plain arrays are 22 B per read + 4 B per CIGAR op, 29 % of what a
+// short-read batch uploads once qualities and bases travel packed; a position-sorted batch of reads with mostly "150M"
+// CIGARs needs 8 B per read.
+extern "C" int pb_meta_encode(const pb_batch* b, uint64_t** codes_out, uint32_t** cigar_out, int64_t* n_cigar_out,
+                              int32_t** esc_out, int64_t* n_esc_out, int32_t* pos0_out, int32_t* seq_stride_out) {
+    if (!b || !codes_out || !cigar_out || !n_cigar_out || !esc_out || !n_esc_out || !pos0_out || !seq_stride_out)
+        return fail(PB_ERR_INVALID, "null argument");
+    if (b->mem != PB_MEM_HOST) return fail(PB_ERR_INVALID, "pb_meta_encode needs a host batch");
+    const int64_t n = b->n_reads;
+    if (n && (!b->pos || !b->tlen || !b->read_len || !b->mapq || !b->flags || !b->cigar_off || !b->seq_off || (b->n_cigar && !b->cigar)))
+        return fail(PB_ERR_INVALID, "null per-read array in pb_batch");
+    // seq_off layout: cumulative padded lengths, or a constant stride
+    int32_t stride = 0;
+    {
+        bool canonical = true, strided = n > 1;
+        uint64_t acc = 0;
+        const int64_t st = n > 1 ? (int64_t)b->seq_off[1] - (int64_t)b->seq_off[0] : 0;
+        for (int64_t r = 0; r < n; r++) {
+            if ((uint64_t)b->seq_off[r] != acc) canonical = false;
+            if (strided && (int64_t)b->seq_off[r] != r * st) strided = false;
+            if (b->read_len[r] < 0 || b->read_len[r] > 255) return fail(PB_ERR_UNSUPPORTED, "a read is longer than 255 bases");
+            acc += (uint64_t)((b->read_len[r] + 3) & ~3);
+        }
+        if (!canonical) {
+            if (!strided || st <= 0 || st > 0x7FFFFFFF) return fail(PB_ERR_UNSUPPORTED, "seq_off is neither cumulative nor a constant stride");
+            stride = (int32_t)st;
+        }
+    }
+    std::vector<uint32_t> cig; std::vector<int32_t> esc;
+    uint64_t* codes = (uint64_t*)malloc((size_t)std::max<int64_t>(n, 1) * 8 + 64);
+    if (!codes) return fail(PB_ERR_OOM, "out of host memory");
+    int32_t prev = n ? b->pos[0] : 0;
+    for (int64_t r = 0; r < n; r++) {
+        const int64_t delta = (int64_t)b->pos[r] - prev;
+        const uint32_t c0 = b->cigar_off[r], c1 = b->cigar_off[r + 1];
+        if (delta < 0 || c1 < c0 || c1 - c0 > 255 || r > 0x7FFFFFFF) { free(codes); return fail(PB_ERR_UNSUPPORTED, delta < 0 ? "the batch is not sorted by pos" : "a read has more than 255 CIGAR ops"); }
+        prev = b->pos[r];
+        uint64_t code = 0;
+        if (delta >= 0xFFFF) { code |= 0xFFFFull; esc.push_back((int32_t)r); esc.push_back(0); esc.push_back((int32_t)delta); }
+        else code |= (uint64_t)delta;
+        const int32_t tl = b->tlen[r];
+        if (tl <= -32768 || tl > 32767) { code |= 0x8000ull << 16; esc.push_back((int32_t)r); esc.push_back(1); esc.push_back(tl); }
+        else code |= (uint64_t)(uint16_t)(int16_t)tl << 16;
+        code |= (uint64_t)(uint8_t)b->read_len[r] << 32 | (uint64_t)b->mapq[r] << 40 | (uint64_t)b->flags[r] << 48;
+        const bool simple = c1 - c0 == 1 && b->cigar[c0] == ((uint32_t)b->read_len[r] << 4);
+        if (!simple) {
+            if (c1 == c0) { free(codes); return fail(PB_ERR_UNSUPPORTED, "a read has no CIGAR op"); }
+            code |= (uint64_t)(c1 - c0) << 56;
+            cig.insert(cig.end(), b->cigar + c0, b->cigar + c1);
+        }
+        codes[r] = code;
+    }
+    uint32_t* oc = (uint32_t*)malloc(cig.size() * 4 + 64); int32_t* oe = (int32_t*)malloc(esc.size() * 4 + 64);
+    if (!oc || !oe) { free(codes); free(oc); free(oe); return fail(PB_ERR_OOM, "out of host memory"); }
+    if (!cig.empty()) memcpy(oc, cig.data(), cig.size() * 4);
+    if (!esc.empty()) memcpy(oe, esc.data(), esc.size() * 4);
+    *codes_out = codes; *cigar_out = oc; *n_cigar_out = (int64_t)cig.size(); *esc_out = oe; *n_esc_out = (int64_t)(esc.size() / 3);
+    *pos0_out = n ? b->pos[0] : 0; *seq_stride_out = stride;
+    return PB_OK;
+}
+
+// ---- device side of the compact metadata: one scan over (pos delta, padded length, ops, listed ops), then a thread per read ----
+namespace {
+struct MetaSums { uint32_t pos, seq, ops, listed; };
+struct MetaAdd { __host__ __device__ MetaSums operator()(const MetaSums& a, const MetaSums& b) const { return MetaSums{a.pos + b.pos, a.seq + b.seq, a.ops + b.ops, a.listed + b.listed}; } };
+__device__ __forceinline__ bool meta_escape(const int32_t* __restrict__ esc, int64_t n_esc, int32_t r, int32_t field, int32_t* v) {
+    int64_t lo = 0, hi = n_esc;
+    while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (esc[3 * m] < r) lo = m + 1; else hi = m; }
+    for (; lo < n_esc && esc[3 * lo] == r; lo++) if (esc[3 * lo + 1] == field) { *v = esc[3 * lo + 2]; return true; }
+    return false;
+}
+struct MetaTerm {
+    const uint64_t* codes; const int32_t* esc; int64_t n_esc;
+    __device__ MetaSums operator()(int32_t r) const {
+        const uint64_t c = codes[r];
+        int32_t d = (int32_t)(c & 0xFFFFu);
+        if (d == 0xFFFF && !meta_escape(esc, n_esc, r, 0, &d)) d = 0;
+        const uint32_t len = (uint32_t)(c >> 32) & 0xFFu, nl = (uint32_t)(c >> 56);
+        return MetaSums{(uint32_t)d, (len + 3u) & ~3u, nl ? nl : 1u, nl};
+    }
+};
+// flag bits: 1 = the records describe more CIGAR ops / base slots than n_cigar / n_seq say, 2 = an escape is missing
+__global__ void __launch_bounds__(256) k_meta_expand(const uint64_t* __restrict__ codes, const MetaSums* __restrict__ ex, const uint32_t* __restrict__ listed,
+                                                     const int32_t* __restrict__ esc, int64_t n_esc, int64_t n, int64_t n_cigar, int64_t n_seq, int64_t n_listed,
+                                                     int32_t pos0, int32_t stride, int32_t* pos, int32_t* tlen, int32_t* read_len, uint8_t* mapq, uint8_t* flags,
+                                                     uint32_t* cigar_off, uint32_t* cigar, uint32_t* seq_off, int* flag) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint64_t c = codes[r];
+    const MetaSums e = ex[r];
+    int32_t d = (int32_t)(c & 0xFFFFu);
+    if (d == 0xFFFF && !meta_escape(esc, n_esc, (int32_t)r, 0, &d)) { d = 0; atomicOr(flag, 2); }
+    int32_t tl = (int32_t)(int16_t)(uint16_t)(c >> 16);
+    if (tl == -32768 && !meta_escape(esc, n_esc, (int32_t)r, 1, &tl)) { tl = 0; atomicOr(flag, 2); }
+    const uint32_t len = (uint32_t)(c >> 32) & 0xFFu, nl = (uint32_t)(c >> 56), nops = nl ? nl : 1u;
+    pos[r] = pos0 + (int32_t)(e.pos + (uint32_t)d); tlen[r] = tl; read_len[r] = (int32_t)len;
+    mapq[r] = (uint8_t)(c >> 40); flags[r] = (uint8_t)(c >> 48);
+    const uint64_t so = stride > 0 ? (uint64_t)r * (uint64_t)stride : (uint64_t)e.seq;
+    seq_off[r] = (uint32_t)so;
+    cigar_off[r] = e.ops;
+    if (r == n - 1) cigar_off[n] = e.ops + nops;
+    if ((uint64_t)e.ops + nops > (uint64_t)n_cigar || so + ((len + 3u) & ~3u) > (uint64_t)n_seq || (uint64_t)e.listed + nl > (uint64_t)n_listed) {
+        atomicOr(flag, 1);                                   // the pass will be refused; until then this read is empty and harmless
+        read_len[r] = 0; seq_off[r] = 0;
+        for (uint32_t k = 0; k < nops; k++) if ((uint64_t)e.ops + k < (uint64_t)n_cigar) cigar[e.ops + k] = 0;
+        if ((uint64_t)e.ops > (uint64_t)n_cigar) cigar_off[r] = (uint32_t)n_cigar;
+        if (r == n - 1) cigar_off[n] = (uint32_t)min((uint64_t)e.ops + nops, (uint64_t)n_cigar);
+        return;
+    }
+    if (nl == 0) cigar[e.ops] = len << 4;
+    else for (uint32_t k = 0; k < nl; k++) cigar[e.ops + k] = listed[e.listed + k];
+}
+}  // namespace
+
+static int stage_meta(pb_engine* e, const pb_batch* b, DevBatch& d) {
+    cudaStream_t s = e->stream;
+    const int64_t n = b->n_reads;
+    void *pc = nullptr, *pl = nullptr, *pe = nullptr, *px = nullptr, *p = nullptr;
+    CK(e->arena.alloc((size_t)n * 8 + 64, &pc));
+    CK(e->arena.alloc((size_t)b->n_meta_cigar * 4 + 64, &pl));
+    CK(e->arena.alloc((size_t)b->n_meta_esc * 12 + 64, &pe));
+    CK(e->arena.alloc((size_t)n * sizeof(MetaSums) + 64, &px));
+    if (n) CK(cudaMemcpyAsync(pc, b->meta_codes, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    if (b->n_meta_cigar) CK(cudaMemcpyAsync(pl, b->meta_cigar, (size_t)b->n_meta_cigar * 4, cudaMemcpyHostToDevice, s));
+    if (b->n_meta_esc) CK(cudaMemcpyAsync(pe, b->meta_esc, (size_t)b->n_meta_esc * 12, cudaMemcpyHostToDevice, s));
+    CK(e->arena.alloc((size_t)n * 4 + 64, &p)); d.pos = (const int32_t*)p;
+    CK(e->arena.alloc((size_t)n * 4 + 64, &p)); d.tlen = (const int32_t*)p;
+    CK(e->arena.alloc((size_t)n * 4 + 64, &p)); d.read_len = (const int32_t*)p;
+    CK(e->arena.alloc((size_t)n + 64, &p)); d.mapq = (const uint8_t*)p;
+    CK(e->arena.alloc((size_t)n + 64, &p)); d.flags = (const uint8_t*)p;
+    CK(e->arena.alloc((size_t)(n + 1) * 4 + 64, &p)); d.cigar_off = (const uint32_t*)p;
+    CK(e->arena.alloc((size_t)b->n_cigar * 4 + 64, &p)); d.cigar = (const uint32_t*)p;
+    CK(e->arena.alloc((size_t)n * 4 + 64, &p)); d.seq_off = (const uint32_t*)p;
+    if (n == 0) { CK(cudaMemsetAsync((void*)d.cigar_off, 0, 4, s)); return PB_OK; }
+    MetaTerm term{(const uint64_t*)pc, (const int32_t*)pe, b->n_meta_esc};
+    auto in = thrust::make_transform_iterator(thrust::counting_iterator<int32_t>(0), term);
+    size_t tmp = 0;
+    CK(cub::DeviceScan::ExclusiveScan(nullptr, tmp, in, (MetaSums*)px, MetaAdd(), MetaSums{0, 0, 0, 0}, (int)n, s));
+    void* pt = nullptr;
+    CK(e->arena.alloc(tmp + 64, &pt));
+    CK(cub::DeviceScan::ExclusiveScan(pt, tmp, in, (MetaSums*)px, MetaAdd(), MetaSums{0, 0, 0, 0}, (int)n, s));
+    k_meta_expand<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const uint64_t*)pc, (const MetaSums*)px, (const uint32_t*)pl, (const int32_t*)pe, b->n_meta_esc, n,
+                                                              b->n_cigar, b->n_seq, b->n_meta_cigar, b->meta_pos0, b->meta_seq_stride,
+                                                              (int32_t*)d.pos, (int32_t*)d.tlen, (int32_t*)d.read_len, (uint8_t*)d.mapq, (uint8_t*)d.flags,
+                                                              (uint32_t*)d.cigar_off, (uint32_t*)d.cigar, (uint32_t*)d.seq_off, e->meta_flag.as<int>());
+    e->launches += 3;
+    e->meta_used = true;
+    return PB_OK;
+}
+
 // 4-bit quality codes -> quality bytes (pb_batch.qual_codes, qual_code_bits == 4).  A thread expands 16 bases: the low / high half of an input
 // word is directly a PRMT selector (one code per nibble); codes 0..7 and 8..15 come from two 8-byte pools, bit 3 picks.
 __global__ void __launch_bounds__(256) k_unpack_quals4(const uint2* __restrict__ in, uint4* __restrict__ out, size_t groups,
@@ -531,9 +686,12 @@ extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, in
     if (!deltas && !b->bases2 && b->n_seq) return fail(PB_ERR_INVALID, "batch has neither bases2 nor base deltas");
     if (qcodes && b->qual_code_bits != 3 && b->qual_code_bits != 4) return fail(PB_ERR_INVALID, "qual_code_bits must be 3 or 4 when qual_codes is given");
     if (!qcodes && !b->quals && b->n_seq) return fail(PB_ERR_INVALID, "batch has neither quals nor qual_codes");
-    if (b->n_reads && (!b->pos || !b->tlen || !b->read_len || !b->mapq || !b->flags || !b->cigar_off || !b->seq_off))
+    const bool meta = b->mem == PB_MEM_HOST && b->meta_codes;
+    if (meta && (b->n_meta_cigar < 0 || b->n_meta_esc < 0 || (b->n_meta_cigar && !b->meta_cigar) || (b->n_meta_esc && !b->meta_esc) || b->meta_seq_stride < 0))
+        return fail(PB_ERR_INVALID, "bad compact metadata arrays");
+    if (!meta && b->n_reads && (!b->pos || !b->tlen || !b->read_len || !b->mapq || !b->flags || !b->cigar_off || !b->seq_off))
         return fail(PB_ERR_INVALID, "null per-read array in pb_batch");
-    if ((b->n_cigar && !b->cigar) || (b->n_exc && (!b->exc_idx || !b->exc_base || !b->exc_qual))) return fail(PB_ERR_INVALID, "null array in pb_batch");
+    if ((!meta && b->n_cigar && !b->cigar) || (b->n_exc && (!b->exc_idx || !b->exc_base || !b->exc_qual))) return fail(PB_ERR_INVALID, "null array in pb_batch");
     CK(cudaSetDevice(e->device));
     const double t_ab = e->host_trace ? std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count() : 0.0;
     drop_graph(e);                                   // the captured pass belongs to the previous batch set
@@ -548,6 +706,7 @@ extern "C" int pb_region_add_batch(pb_engine* e, const pb_batch* b, int frag, in
     return rc_stage;
 }
 
+static int stage_meta(pb_engine* e, const pb_batch* b, DevBatch& d);
 static int stage_batch(pb_engine* e, const pb_batch* b, int frag, int long_read_type) {
     HostBatch& hb = e->batches.back();
     if (long_read_type != 0) {
@@ -571,8 +730,12 @@ static int stage_batch(pb_engine* e, const pb_batch* b, int frag, int long_read_
     const size_t n = (size_t)b->n_reads;
     int rc;
 #define ST(field, count) if ((rc = stage(e, hb, b->field, (size_t)(count), b->mem, &d.field)) != PB_OK) return rc
-    ST(pos, n); ST(tlen, n); ST(read_len, n); ST(mapq, n); ST(flags, n); ST(cigar_off, n + 1);
-    ST(cigar, b->n_cigar); ST(seq_off, n);
+    if (b->mem == PB_MEM_HOST && b->meta_codes) {       // compact transport of the eight per-read arrays, rebuilt on the device
+        if ((rc = stage_meta(e, b, d)) != PB_OK) return rc;
+    } else {
+        ST(pos, n); ST(tlen, n); ST(read_len, n); ST(mapq, n); ST(flags, n); ST(cigar_off, n + 1);
+        ST(cigar, b->n_cigar); ST(seq_off, n);
+    }
     if (b->mem == PB_MEM_HOST && b->base_delta_idx) {   // compact transport: upload the deltas, rebuild bases2 on the device
         void *pi = nullptr, *pc = nullptr, *pout = nullptr;
         const size_t nd = (size_t)b->n_base_delta;
@@ -950,8 +1113,16 @@ extern "C" int pb_region_finish(pb_engine* e, pb_region_result* res, int32_t* co
         if (rc != PB_OK) { cudaStreamSynchronize(s); return rc; }
         lap(0);
         CK(cudaMemcpyAsync(e->h_sc, e->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
+        int* h_meta = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(e->h_sc) + SC_BYTES);
+        *h_meta = 0;
+        if (e->meta_used) CK(cudaMemcpyAsync(h_meta, e->meta_flag.p, 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         lap(1);
+        if (*h_meta) {
+            e->dirty = true;
+            return fail(PB_ERR_INVALID, (*h_meta & 1) ? "compact metadata (pb_batch.meta_codes) describes more CIGAR ops or bases than n_cigar / n_seq / n_meta_cigar"
+                                                      : "compact metadata (pb_batch.meta_codes) refers to an escape that meta_esc does not hold");
+        }
         if (e->h_sc->error == 2 && attempt == 0) {       // the I/D bound did not hold (I/D-only CIGARs): once more, full capacity
             if ((rc = clean_sparse_planes(e)) != PB_OK) return rc;
             continue;

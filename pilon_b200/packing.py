@@ -37,6 +37,62 @@ def base_delta_encode(cb, contig, start: int, stop: int):
     return idx, code
 
 
+def meta_encode(cb):
+    """pb_meta_encode on a C batch: (codes uint64[n], cigar uint32[m + 16], esc int32[3 k + 16], pos0, seq_stride) as numpy
+    copies, or None when the batch cannot be put that way (long reads, another seq_off layout ...)."""
+    lib = capi.load_library()
+    pc, pg, pe = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    ng, ne, pos0, stride = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
+    rc = lib.pb_meta_encode(C.byref(cb), C.byref(pc), C.byref(pg), C.byref(ng), C.byref(pe), C.byref(ne), C.byref(pos0), C.byref(stride))
+    if rc == capi.PB_ERR_UNSUPPORTED:
+        return None
+    capi.check(rc)
+    n = int(cb.n_reads)
+    codes = np.zeros(n + 2, np.uint64)
+    cigar = np.zeros(ng.value + 16, np.uint32)
+    esc = np.zeros(3 * ne.value + 16, np.int32)
+    if n:
+        codes[:n] = np.ctypeslib.as_array(C.cast(pc, C.POINTER(C.c_uint64)), shape=(n,))
+    if ng.value:
+        cigar[:ng.value] = np.ctypeslib.as_array(C.cast(pg, C.POINTER(C.c_uint32)), shape=(ng.value,))
+    if ne.value:
+        esc[:3 * ne.value] = np.ctypeslib.as_array(C.cast(pe, C.POINTER(C.c_int32)), shape=(3 * ne.value,))
+    for p in (pc, pg, pe):
+        lib.pb_free(p)
+    return codes, cigar, esc, int(ng.value), int(ne.value), int(pos0.value), int(stride.value)
+
+
+def meta_decode(codes, cigar, esc, n_esc, pos0, stride, n):
+    """Reference decoder of the compact metadata (numpy, for tests): the eight plain arrays."""
+    c = codes[:n]
+    delta = (c & np.uint64(0xFFFF)).astype(np.int64)
+    tl = ((c >> np.uint64(16)) & np.uint64(0xFFFF)).astype(np.uint16).view(np.int16).astype(np.int32)
+    for k in range(n_esc):
+        r, f, v = (int(x) for x in esc[3 * k:3 * k + 3])
+        if f == 0:
+            delta[r] = v
+        else:
+            tl[r] = v
+    pos = (pos0 + np.cumsum(delta)).astype(np.int32)
+    read_len = ((c >> np.uint64(32)) & np.uint64(0xFF)).astype(np.int32)
+    mapq = ((c >> np.uint64(40)) & np.uint64(0xFF)).astype(np.uint8)
+    flags = ((c >> np.uint64(48)) & np.uint64(0xFF)).astype(np.uint8)
+    nl = (c >> np.uint64(56)).astype(np.int64)
+    nops = np.where(nl == 0, 1, nl)
+    cigar_off = np.zeros(n + 1, np.uint32)
+    cigar_off[1:] = np.cumsum(nops)
+    out = np.zeros(int(cigar_off[-1]), np.uint32)
+    lo = np.concatenate([[0], np.cumsum(nl)])
+    for r in range(n):
+        if nl[r] == 0:
+            out[cigar_off[r]] = np.uint32(read_len[r]) << np.uint32(4)
+        else:
+            out[cigar_off[r]:cigar_off[r + 1]] = cigar[lo[r]:lo[r + 1]]
+    pad = (read_len + 3) & ~3
+    seq_off = (np.arange(n, dtype=np.int64) * stride if stride > 0 else np.concatenate([[0], np.cumsum(pad)[:-1]]) if n else np.zeros(0)).astype(np.uint32)
+    return pos, tl, read_len, mapq, flags, cigar_off, out, seq_off
+
+
 _OPCODE = {op: i for i, op in enumerate(capi.CIGAR_OPS)}
 _BASE_CODE = np.full(256, 255, np.uint8)
 for _i, _c in enumerate(b"ACGT"):
@@ -64,6 +120,7 @@ class ReadBatch:
     qual_lut: Optional[np.ndarray] = None      # pb_batch.qual_lut: code -> quality byte
     base_delta_idx: Optional[np.ndarray] = None    # pb_batch.base_delta_idx / base_delta_code: bases that differ from
     base_delta_code: Optional[np.ndarray] = None   # the reference prediction (compact H2D transport of bases2)
+    meta: Optional[tuple] = None                   # compact per-read metadata (meta_encode): pb_batch.meta_codes & co.
 
     @property
     def n_reads(self) -> int:
@@ -94,9 +151,19 @@ class ReadBatch:
             b.base_delta_idx = self.base_delta_idx.ctypes.data
             b.base_delta_code = self.base_delta_code.ctypes.data
             b.n_base_delta = int(self.base_delta_idx.shape[0]) - 16      # (the arrays carry 16 spare entries)
+        if self.meta is not None:
+            codes, cigar, esc, ng, ne, pos0, stride = self.meta
+            b.meta_codes, b.meta_cigar, b.meta_esc = codes.ctypes.data, cigar.ctypes.data, esc.ctypes.data
+            b.n_meta_cigar, b.n_meta_esc, b.meta_pos0, b.meta_seq_stride = ng, ne, pos0, stride
         b.mem = capi.PB_MEM_HOST
         b._keepalive = self
         return b
+
+    def with_compact_meta(self) -> "ReadBatch":
+        """Adds the compact transport of the per-read arrays (pb_meta_encode); returns self unchanged when the batch cannot
+        be put that way."""
+        m = meta_encode(self.to_c())
+        return self if m is None else dataclasses.replace(self, meta=m)
 
     def with_base_deltas(self, contig: bytes, start: int, stop: int) -> "ReadBatch":
         """Adds the reference-delta transport of bases2 for the region [start, stop] (pb_base_delta_encode)."""

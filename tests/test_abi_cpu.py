@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     # sizes implied by the header's field lists (LP64)
     assert C.sizeof(capi.pb_config) == 40
-    assert C.sizeof(capi.pb_batch) == 4 * 8 + 13 * 8 + 8 + 8 + 16 + 24
+    assert C.sizeof(capi.pb_batch) == 4 * 8 + 13 * 8 + 8 + 8 + 16 + 24 + 3 * 8 + 2 * 8 + 2 * 4
     assert C.sizeof(capi.pb_indel) == 32
     assert C.sizeof(capi.pb_region_result) == 4 * 8 + 4 * 4 + 2 * 8 + 18 * 8 + 4 * 8 + 5 * 8 + 3 * 8
 
@@ -161,3 +161,43 @@ def test_base_delta_transport_round_trips():
         codes[rd.base_delta_idx[:n]] = rd.base_delta_code[:n]
         c4 = codes.reshape(-1, 4)
         assert np.array_equal((c4[:, 0] | (c4[:, 1] << 2) | (c4[:, 2] << 4) | (c4[:, 3] << 6)).astype(np.uint8), rb.bases2)
+
+
+def test_compact_metadata_round_trips_through_an_independent_decoder():
+    """pb_meta_encode (pb_batch.meta_codes): 8 bytes per read + listed CIGARs + escapes decode, by a numpy decoder written
+    from the header's description, to exactly the eight plain arrays -- including reads with indels and clips, a gap of more
+    than 65534 loci between neighbours and template lengths beyond int16."""
+    import random
+    from pilon_b200.packing import meta_decode, meta_encode, pack_records
+    from tests import helpers as H
+    contig, start, stop, reads = H.random_case(3, contig_len=2000, n_reads=500)
+    reads = sorted(reads, key=lambda r: r.pos)
+    rng = random.Random(3)
+    for r in reads[::7]:
+        r.tlen = rng.choice([-70000, 40000, 32767, -32768, -32767, 1 << 30])
+    far = [r for r in reads[-20:]]
+    for r in far:
+        r.pos += 200000                                      # > 65534 past the previous read
+    reads.sort(key=lambda r: r.pos)
+    rb = pack_records(reads)
+    m = meta_encode(rb.to_c())
+    assert m is not None
+    codes, cigar, esc, ng, ne, pos0, stride = m
+    assert ne >= len(reads[::7]) // 2 and stride == 0 and ng > 0
+    got = meta_decode(codes, cigar, esc, ne, pos0, stride, rb.n_reads)
+    for name, g in zip(("pos", "tlen", "read_len", "mapq", "flags", "cigar_off", "cigar", "seq_off"), got):
+        assert np.array_equal(g, getattr(rb, name)), name
+    # 8 B per read + the listed CIGARs instead of 22 B per read + every CIGAR
+    assert codes[:rb.n_reads].nbytes + 4 * ng + 12 * ne < 0.7 * sum(getattr(rb, f).nbytes for f in ("pos", "tlen", "read_len", "mapq", "flags", "cigar_off", "cigar", "seq_off"))
+
+
+def test_compact_metadata_refuses_what_it_cannot_hold():
+    from oracle import pilon_oracle as po
+    from pilon_b200.packing import meta_encode, pack_records
+    long_read = po.Read(pos=5, cigar=[("M", 300)], bases=b"A" * 300, quals=bytes([30]) * 300, mapq=60)
+    assert meta_encode(pack_records([long_read]).to_c()) is None
+    a = po.Read(pos=50, cigar=[("M", 20)], bases=b"C" * 20, quals=bytes([30]) * 20, mapq=60)
+    b = po.Read(pos=10, cigar=[("M", 20)], bases=b"C" * 20, quals=bytes([30]) * 20, mapq=60)
+    assert meta_encode(pack_records([a, b]).to_c()) is None     # not sorted by pos
+    assert meta_encode(pack_records([b, a]).to_c()) is not None
+    assert meta_encode(pack_records([]).to_c()) is not None

@@ -258,6 +258,57 @@ def test_packed_quality_transport_matches_byte_transport(engine, levels):
     assert np.array_equal(ins4[0], ins_ref[0])
 
 
+@pytest.mark.parametrize("seed", [3, 8])
+def test_compact_metadata_transport_matches_plain_arrays(engine, seed):
+    """pb_batch.meta_codes: the eight per-read arrays travel as 8 bytes per read + listed CIGARs + escapes and are rebuilt
+    on the device (one scan + one kernel); with the plain pointers NULL the results equal the oracle's, which reads the
+    plain arrays.  Reads with indels and clips, template lengths beyond int16, a gap of more than 65534 loci, two batches,
+    together with the packed quality and reference-delta transports."""
+    from pilon_b200.packing import ResultBuffers
+    contig, start, stop, reads = H.clean_case(seed, n=260000, start=1001, stop=250000, depth=3, n_sites=30)
+    reads = [r for r in reads if not (60000 < r.pos < 160000)]          # a hole in the coverage: pos delta > 65534
+    rng = random.Random(seed)
+    for r in reads[::11]:
+        r.tlen = rng.choice([-70000, 40000, -32768, 1 << 29])
+    groups = [([r for i, r in enumerate(reads) if i % 4], True), ([r for i, r in enumerate(reads) if i % 4 == 0], False)]
+    packed = [(pack_records(g), f) for g, f in groups]
+    ref, ins_ref = H.run_c_oracle(contig, start, stop, packed, indels_cap=1 << 18, bytes_cap=1 << 22)
+    engine.region_begin(contig, start, stop)
+    keep = []
+    for rb, f in packed:
+        m = rb.with_compact_meta().with_base_deltas(contig, start, stop)
+        assert m.meta is not None and m.meta[4] > 0 and m.meta[3] > 0            # escapes and listed CIGARs present
+        c = m.to_c()
+        for name in ("pos", "tlen", "read_len", "mapq", "flags", "cigar_off", "cigar", "seq_off", "bases2"):
+            setattr(c, name, None)                         # the engine must not need the plain arrays
+        keep.append((m, c))
+        engine.add_batch(c, f)
+    res = ResultBuffers(stop + 1 - start, None, 1 << 18, 1 << 22, calls_cap=1 << 16)
+    ins = [np.zeros(rb.n_reads, np.int32) for rb, _ in packed]
+    engine.finish(res, ins)
+    H.assert_results_equal(res, ref, "compact metadata vs C oracle")
+    for a, b in zip(ins, ins_ref):
+        assert np.array_equal(a, b)
+
+
+def test_compact_metadata_that_overruns_its_batch_is_refused(engine):
+    """Records that describe more CIGAR ops than n_cigar says must not write past the arrays: the pass is refused."""
+    from pilon_b200.packing import ResultBuffers
+    contig, start, stop, reads = H.clean_case(5, n=6000, start=501, stop=5500, depth=6, n_sites=6)
+    m = pack_records(reads).with_compact_meta()
+    c = m.to_c()
+    c.n_cigar = c.n_cigar - 3
+    engine.region_begin(contig, start, stop)
+    engine.add_batch(c, True)
+    res = ResultBuffers(stop + 1 - start, ["flags"], 1 << 16, 1 << 20)
+    with pytest.raises(capi.EngineError):
+        engine.finish(res, [np.zeros(m.n_reads, np.int32)])
+    # the engine is usable afterwards
+    ok, _ = engine.run_region(contig, start, stop, [(pack_records(reads), True)])
+    ref, _ = H.run_c_oracle(contig, start, stop, [(pack_records(reads), True)])
+    H.assert_results_equal(ok, ref, "after a refused pass")
+
+
 def test_more_batches_than_the_by_value_table_holds(engine):
     """More than 20 BAMs in one region (the kernels' by-value batch table holds 20): the engine falls back to the
     kernel generation that walks a device-side batch list; results stay bit-identical."""
