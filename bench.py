@@ -673,18 +673,23 @@ def run_gpu_arm(args):
             if mismatches:
                 parity["mismatches"] = mismatches[:10]
         from_bam = from_bam_leg(args, wl, regions, local) if (args.from_bam and world == 1) else None
-        # shared-memory reductions of the scatter kernel: one 32-bit RED lane-op per counted base (+ one per counted base of a
-        # batch outside fragCoverage); peak = 32 lanes x 1 wavefront per clock per SM.  Regions the engine gives to the gather
-        # kernel (deep and narrow: C5) accumulate in registers and issue no per-base atomics.
-        scatter = [r for r in regions if (r.size + 2047) // 2048 >= 256 and sum(int(b.c.n_seq) for b in r.batches) // r.size <= 1000]
+        # shared-memory reductions of the scatter kernels: one 32-bit RED lane-op per counted base (+ one per counted base of a
+        # batch outside fragCoverage); peak = 32 lanes x 1 wavefront per clock per SM.  The engine's choice (pb_engine.cu,
+        # compute()): mean depth > 1000 -> k_pileup7c, else >= 256 tiles of 2048 loci -> k_pileup7, else the gather kernel,
+        # which accumulates in registers and issues no per-base atomics.
+        def _depth(r):
+            return sum(int(b.c.n_seq) for b in r.batches) // r.size
+        deep = [r for r in regions if _depth(r) > 1000 and len(r.batches) <= 20]
+        scatter = deep + [r for r in regions if _depth(r) <= 1000 and (r.size + 2047) // 2048 >= 256 and len(r.batches) <= 20]
         sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
         lane_ops = sum(b.aligned_bases * (1 if b.frag else 2) for r in scatter for b in r.batches) * (130.0 / 150.0)
-        atomic = {"kernel": "k_pileup7 (scatter)" if scatter else "k_pileup5 (gather: no per-base atomics)",
+        atomic = {"kernel": ("k_pileup7c (cluster scatter)" if deep and len(deep) == len(scatter) else "k_pileup7 (scatter)" if scatter
+                             else "k_pileup5 (gather: no per-base atomics)"),
                   "regions": len(scatter),
                   "shared_red_lane_ops_per_s": (lane_ops / (pileup_ms * 1e-3)) if scatter else 0.0,
                   "peak_lane_ops_per_s": 148 * 32 * sm_hz,
                   "frac": (lane_ops / (pileup_ms * 1e-3)) / (148 * 32 * sm_hz) if scatter else 0.0,
-                  "note": "counted bases ~ aligned bases x 130/150 (trusted flank); ncu: profiles/r2_pileup7_raw.csv "
+                  "note": "counted bases ~ aligned bases x 130/150 (trusted flank); ncu: profiles/r2_pileup7_raw.csv, profiles/r2q/pileup7c_c5_raw.csv "
                           "(smsp__inst_executed_op_shared_atom, l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom)"}
         out = {"metric": METRIC, "value": job_aligned / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
@@ -708,7 +713,7 @@ def run_gpu_arm(args):
                        "host_threads_per_gpu": n_workers, "passes_in_flight_per_thread": e2e_depth,
                        "quals8": e2e8, "classic": e2e_classic},
                "gpu_launches": int(job_launches),
-               "roofline": {"bound": "hbm", "kernel": "k_pileup", "achieved": achieved, "peak": peak, "unit": "GB/s",
+               "roofline": {"bound": "hbm", "kernel": atomic["kernel"].split(" ")[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": sum(r.alg_bytes for r in regions) / len(regions),
                             "algorithmic_bytes_per_base": alg / total_aligned,

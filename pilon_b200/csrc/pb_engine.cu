@@ -205,10 +205,6 @@ extern "C" int pb_create(int device, const pb_config* c, pb_engine** out) {
     CK(cudaEventCreateWithFlags(&e->ev_sc, cudaEventDisableTiming));
     CK(cudaMallocHost(&e->h_sc, SC_BYTES + 16));          // + the compact-metadata flag word
     CK(e->meta_flag.ensure(16, true, e->stream));
-    cudaMemPool_t pool;
-    CK(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thr = UINT64_MAX;
-    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     *out = e;
     return PB_OK;
 }
