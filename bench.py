@@ -750,7 +750,7 @@ def from_bam_leg(args, wl, regions, local):
     bam_bytes = sum(os.path.getsize(p) for p, _ in paths)
     nthreads = max(1, min(len(sample), len(os.sched_getaffinity(0)), 6))
     max_size = max(r.size for r in sample)
-    slots = [(Engine(local), ResultBuffers(max_size, FIX_PLANES, indels_cap=1 << 20, indel_bytes_cap=1 << 23, pinned=True),
+    slots = [(Engine(local), ResultBuffers(max_size, FIXMIN_PLANES, indels_cap=1 << 20, indel_bytes_cap=1 << 23, pinned=True, calls_cap=CALLS_CAP),
               [bamio.BamFile(p, t) for p, t in paths]) for _ in range(nthreads)]
     order = list(range(len(sample)))
     lock = threading.Lock()

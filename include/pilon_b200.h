@@ -331,6 +331,11 @@ int pb_packer_reset(pb_packer* p);
 int pb_packer_add(pb_packer* p, int32_t pos, int32_t tlen, int32_t mapq, uint32_t flags,
                   const uint32_t* cigar, int32_t n_cigar,
                   const uint8_t* seq, const uint8_t* qual, int32_t read_len);
+/* The same for a record in BAM's own encoding: `seq4` = 4-bit bases, two per byte, high nibble first
+ * (=ACMGRSVTWYHKDBN), as they lie in a BAM record -- what pb_bam_query_pack feeds the packer with. */
+int pb_packer_add_bam(pb_packer* p, int32_t pos, int32_t tlen, int32_t mapq, uint32_t flags,
+                      const uint32_t* cigar, int32_t n_cigar,
+                      const uint8_t* seq4, const uint8_t* qual, int32_t read_len);
 /* Bulk form: reads already in struct-of-arrays with ASCII bases (one byte per base, unpadded). */
 int pb_packer_add_many(pb_packer* p, int64_t n_reads, const int32_t* pos, const int32_t* tlen,
                        const uint8_t* mapq, const uint8_t* flags, const int32_t* read_len,

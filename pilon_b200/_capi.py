@@ -124,7 +124,7 @@ def load_library() -> C.CDLL:
     for name in ("pb_device_count", "pb_create", "pb_destroy", "pb_region_begin", "pb_region_add_batch",
                  "pb_region_finish", "pb_region_compute_timed", "pb_region_compute", "pb_stream", "pb_packer_create",
                  "pb_packer_destroy", "pb_packer_reset", "pb_packer_add", "pb_packer_add_many",
-                 "pb_packer_view", "pb_base_delta_encode", "pb_meta_encode"):
+                 "pb_packer_view", "pb_packer_add_bam", "pb_base_delta_encode", "pb_meta_encode"):
         getattr(lib, name).restype = C.c_int
     if lib.pb_abi_version() != ABI_VERSION:
         raise RuntimeError("libpilonb200.so ABI version mismatch")

@@ -12,6 +12,9 @@
 //   * bases decode through "=ACMGRSVTWYHKDBN"; a quality array of 0xFF bytes means "no qualities".
 // The writer exists so that synthetic inputs can be given to the real Pilon JVM wherever one is available
 // (tools/run_real_pilon.sh) and so that the reader can be round-trip tested here.
+#include <chrono>
+#include <future>
+#include <thread>
 #include <zlib.h>
 
 #include <algorithm>
@@ -42,12 +45,25 @@ struct Bgzf {
     uint32_t block_csize = 0;          // its compressed size
     size_t at = 0;                     // read position inside `block`
     bool eof = false;
+    // Read-ahead window: the next blocks' compressed bytes are read in one sequential sweep and inflated by a few threads
+    // (BGZF blocks are independent deflate streams); load() then serves consecutive blocks out of the window.  Inflate was
+    // 60 % of a query's time on one thread.
+    struct Ahead { uint64_t addr = 0; uint32_t csize = 0; size_t data_len = 0; uint32_t isize = 0; bool ok = false, end = false, bad = false, live = false;
+                   std::vector<uint8_t> cdata, out; };
+    std::vector<Ahead> win; size_t win_n = 0;
+    std::vector<Ahead> nxt; size_t nxt_n = 0;          // the window after `win`, being read and inflated while `win` is consumed
+    std::future<bool> pending; bool has_pending = false; uint64_t nxt_addr = 0;
+    int threads = 4;
+    static constexpr size_t WINDOW = 48;
+    double t_load = 0;                 // PB_BAM_TRACE: seconds inside load()
 
-    bool load(uint64_t addr) {
+    // header + compressed payload of the block at `addr` into a; false = corrupt / short file.  a.end = clean end of file.
+    bool fetch(uint64_t addr, Ahead& a) {
+        a.addr = addr; a.ok = false; a.end = false; a.csize = 0; a.isize = 0; a.data_len = 0;
         if (fseeko(f, (off_t)addr, SEEK_SET) != 0) return false;
         uint8_t hdr[18];
         const size_t got = fread(hdr, 1, 18, f);
-        if (got == 0) { eof = true; block.clear(); at = 0; block_addr = addr; block_csize = 0; return true; }
+        if (got == 0) { a.end = true; return true; }
         if (got != 18 || hdr[0] != 31 || hdr[1] != 139 || hdr[2] != 8 || !(hdr[3] & 4)) return false;
         const unsigned xlen = rd16(hdr + 10);
         // the BC subfield is the first (and in practice only) extra subfield: SI1 = 66, SI2 = 67, SLEN = 2, BSIZE
@@ -63,25 +79,89 @@ struct Bgzf {
         if (bsize < 0) return false;
         const size_t csize = (size_t)bsize + 1;
         if (csize < 12 + (size_t)xlen + 8) return false;                 // corrupt block header
-        const size_t data_len = csize - 12 - xlen - 8;
-        std::vector<uint8_t> cdata(data_len + 8);
+        a.data_len = csize - 12 - xlen - 8;
+        a.cdata.resize(a.data_len + 8);
         if (xlen <= 6) {                                     // part of the payload may already sit in hdr (never: xlen == 6 exactly)
             if (fseeko(f, (off_t)(addr + 12 + xlen), SEEK_SET) != 0) return false;
         }
-        if (fread(cdata.data(), 1, data_len + 8, f) != data_len + 8) return false;
-        const uint32_t isize = rd32(cdata.data() + data_len + 4);
-        if (isize > 65536u) return false;                                // a BGZF block inflates to at most 64 KiB
-        block.resize(isize);
-        if (isize) {
-            z_stream zs; memset(&zs, 0, sizeof zs);
-            if (inflateInit2(&zs, -15) != Z_OK) return false;
-            zs.next_in = cdata.data(); zs.avail_in = (uInt)data_len; zs.next_out = block.data(); zs.avail_out = isize;
-            const int rc = inflate(&zs, Z_FINISH);
-            inflateEnd(&zs);
-            if (rc != Z_STREAM_END) return false;
-            if (crc32(crc32(0L, Z_NULL, 0), block.data(), isize) != rd32(cdata.data() + data_len)) return false;
+        if (fread(a.cdata.data(), 1, a.data_len + 8, f) != a.data_len + 8) return false;
+        a.isize = rd32(a.cdata.data() + a.data_len + 4);
+        if (a.isize > 65536u) return false;                              // a BGZF block inflates to at most 64 KiB
+        a.csize = (uint32_t)csize;
+        return true;
+    }
+    static void inflate_one(Ahead& a) {
+        a.out.resize(a.isize);
+        a.ok = true;
+        if (!a.isize) return;
+        z_stream zs; memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, -15) != Z_OK) { a.ok = false; return; }
+        zs.next_in = a.cdata.data(); zs.avail_in = (uInt)a.data_len; zs.next_out = a.out.data(); zs.avail_out = a.isize;
+        const int rc = inflate(&zs, Z_FINISH);
+        inflateEnd(&zs);
+        if (rc != Z_STREAM_END || crc32(crc32(0L, Z_NULL, 0), a.out.data(), a.isize) != rd32(a.cdata.data() + a.data_len)) a.ok = false;
+    }
+    // window = the blocks from `addr` on; the first one must be readable, later failures surface when they are reached
+    bool fill(std::vector<Ahead>& W, size_t& n, uint64_t addr) {
+        if (W.size() < WINDOW) W.resize(WINDOW);
+        n = 0;
+        uint64_t a = addr;
+        while (n < WINDOW) {
+            Ahead& w = W[n];
+            const bool got = fetch(a, w);
+            if (!got) { if (n == 0) return false; w.addr = a; w.ok = false; w.end = false; w.csize = 0; w.bad = true; n++; break; }
+            w.bad = false;
+            n++;
+            if (w.end) break;
+            a += w.csize;
         }
-        block_addr = addr; block_csize = (uint32_t)csize; at = 0; eof = false;
+        size_t n_inf = 0;
+        for (size_t k = 0; k < n; k++) if (!W[k].end && W[k].csize) n_inf++;
+        const int nt = (int)std::min<size_t>((size_t)std::max(1, threads), n_inf);
+        if (nt <= 1) { for (size_t k = 0; k < n; k++) if (!W[k].end && W[k].csize) inflate_one(W[k]); }
+        else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; t++) th.emplace_back([&W, n, nt, t]() { for (size_t k = (size_t)t; k < n; k += (size_t)nt) if (!W[k].end && W[k].csize) inflate_one(W[k]); });
+            for (auto& x : th) x.join();
+        }
+        return true;
+    }
+    void drain() { if (has_pending) { pending.get(); has_pending = false; } }       // nobody else may touch `f` while a prefetch runs
+    void prefetch_after_win() {
+        if (win_n == 0) return;
+        const Ahead& last = win[win_n - 1];
+        if (last.end || last.bad || !last.csize) return;
+        nxt_addr = last.addr + last.csize;
+        pending = std::async(std::launch::async, [this]() { return fill(nxt, nxt_n, nxt_addr); });
+        has_pending = true;
+    }
+    ~Bgzf() { drain(); }
+    bool load(uint64_t addr) {
+        const auto t0 = std::chrono::steady_clock::now();
+        const bool ok = load_(addr);
+        t_load += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return ok;
+    }
+    bool load_(uint64_t addr) {
+        size_t k = 0;
+        for (; k < win_n; k++) if (win[k].addr == addr && (win[k].end || win[k].bad || win[k].live)) break;
+        if (k == win_n) {
+            bool have = false;
+            if (has_pending) {                               // the sequential case: the next window is (being) prepared
+                const bool okp = pending.get(); has_pending = false;
+                if (okp && nxt_n && nxt_addr == addr) { win.swap(nxt); win_n = nxt_n; nxt_n = 0; have = true; }
+            }
+            if (!have && !fill(win, win_n, addr)) { win_n = 0; return false; }
+            for (size_t i = 0; i < win_n; i++) win[i].live = !win[i].end && !win[i].bad;
+            prefetch_after_win();
+            k = 0;
+        }
+        Ahead& a = win[k];
+        if (a.end) { eof = true; block.clear(); at = 0; block_addr = addr; block_csize = 0; return true; }
+        if (a.bad || !a.ok) return false;
+        block.swap(a.out);
+        block_addr = addr; block_csize = a.csize; at = 0; eof = false;
+        a.live = false;                                      // served: its bytes now live in `block`
         return true;
     }
     bool seek(uint64_t voff) {
@@ -168,6 +248,7 @@ struct pb_bam {
     std::vector<std::vector<uint64_t>> linear;      // BAI linear index per reference (16 kb windows)
     uint64_t first_record = 0;                       // virtual offset of the first alignment record
     std::vector<uint8_t> rec, seq, qual;
+    std::vector<uint32_t> cig;
 };
 
 extern "C" const char* pb_bam_last_error(void) { return g_err_bam.c_str(); }
@@ -179,7 +260,7 @@ extern "C" int pb_bam_open(const char* bam_path, const char* bai_path, pb_bam** 
     if (!b->z.f) { delete b; return fail_bam(PB_ERR_INVALID, std::string("cannot open ") + bam_path); }
     bool err = false;
     uint8_t w[8];
-    auto bad = [&](const char* m) { fclose(b->z.f); delete b; return fail_bam(PB_ERR_INVALID, std::string(bam_path) + ": " + m); };
+    auto bad = [&](const char* m) { b->z.drain(); fclose(b->z.f); delete b; return fail_bam(PB_ERR_INVALID, std::string(bam_path) + ": " + m); };
     if (!b->z.load(0) || !b->z.read(w, 8, &err) || memcmp(w, "BAM\1", 4) != 0) return bad("not a BAM file");
     const uint32_t l_text = rd32(w + 4);
     if (l_text > (1u << 30)) return bad("implausible header length");
@@ -224,7 +305,7 @@ extern "C" int pb_bam_open(const char* bam_path, const char* bai_path, pb_bam** 
     return PB_OK;
 }
 
-extern "C" int pb_bam_close(pb_bam* b) { if (b) { if (b->z.f) fclose(b->z.f); delete b; } return PB_OK; }
+extern "C" int pb_bam_close(pb_bam* b) { if (b) { b->z.drain(); if (b->z.f) fclose(b->z.f); delete b; } return PB_OK; }
 extern "C" int pb_bam_n_refs(const pb_bam* b, int32_t* n) { if (!b || !n) return fail_bam(PB_ERR_INVALID, "null argument"); *n = (int32_t)b->ref_names.size(); return PB_OK; }
 extern "C" int pb_bam_ref(const pb_bam* b, int32_t i, const char** name, int64_t* len) {
     if (!b || i < 0 || i >= (int32_t)b->ref_names.size()) return fail_bam(PB_ERR_INVALID, "bad reference index");
@@ -250,7 +331,6 @@ extern "C" int pb_bam_query_pack(pb_bam* b, int32_t ref_id, int32_t start, int32
         if (lin[w]) from = lin[w];
     }
     if (!b->z.seek(from)) return fail_bam(PB_ERR_INVALID, "corrupt BGZF block");
-    static const char DEC[] = "=ACMGRSVTWYHKDBN";
     int64_t n_ok = 0, n_rej = 0;
     bool err = false;
     uint8_t w4[4];
@@ -277,19 +357,18 @@ extern "C" int pb_bam_query_pack(pb_bam* b, int32_t ref_id, int32_t start, int32
         if ((!non_pf && (flag & 0x200)) || (!duplicates && (flag & 0x400)) || (flag & 0x100)) { n_rej++; continue; }   // validateRead
         const uint8_t* sq = cig + 4 * (size_t)n_cigar;
         const uint8_t* ql = sq + ((size_t)l_seq + 1) / 2;
-        b->seq.resize(l_seq);
-        for (uint32_t i = 0; i < l_seq; i++) b->seq[i] = (uint8_t)DEC[(sq[i >> 1] >> ((~i & 1) << 2)) & 15];
-        std::vector<uint32_t> cigar(n_cigar);
-        for (uint32_t k = 0; k < n_cigar; k++) cigar[k] = rd32(cig + 4 * k);
+        b->cig.resize(n_cigar);
+        if (n_cigar) memcpy(b->cig.data(), cig, 4 * (size_t)n_cigar);       // (BAM is little endian, and so are we; the record is unaligned)
         const uint32_t f = ((flag & 0x1) ? PB_F_PAIRED : 0) | ((flag & 0x2) ? PB_F_PROPER : 0) | ((refID == next_ref) ? PB_F_MATE_SAME_REF : 0) |
                            (unmapped ? PB_F_UNMAPPED : 0) | ((flag & 0x10) ? PB_F_REVERSE : 0);
-        const int rc = pb_packer_add(packer, aStart, tlen, (int32_t)mapq, f, cigar.data(), (int32_t)n_cigar, b->seq.data(), l_seq ? ql : nullptr, (int32_t)l_seq);
+        const int rc = pb_packer_add_bam(packer, aStart, tlen, (int32_t)mapq, f, b->cig.data(), (int32_t)n_cigar, sq, l_seq ? ql : nullptr, (int32_t)l_seq);
         if (rc != PB_OK) return fail_bam(rc, pb_last_error());
         n_ok++;
     }
     if (err) return fail_bam(PB_ERR_INVALID, "corrupt or truncated BGZF stream");
     if (n_records) *n_records = n_ok;
     if (n_rejected) *n_rejected = n_rej;
+    if (getenv("PB_BAM_TRACE")) { fprintf(stderr, "pb_bam_query_pack: %lld records, %.3f s in BGZF block loads so far\n", (long long)n_ok, b->z.t_load); }
     return PB_OK;
 }
 

@@ -1244,8 +1244,24 @@ extern "C" int pb_packer_reset(pb_packer* p) {
     return PB_OK;
 }
 
-extern "C" int pb_packer_add(pb_packer* p, int32_t pos, int32_t tlen, int32_t mapq, uint32_t flags,
-                             const uint32_t* cigar, int32_t n_cigar, const uint8_t* seq, const uint8_t* qual, int32_t read_len) {
+// One record into the packer.  BASES gives, for base j, its 2-bit code (or 0x80 for anything that is not exactly A/C/G/T)
+// and, for the exception table, its ASCII letter.
+namespace {
+struct AsciiBases {
+    const uint8_t* seq;
+    static const uint8_t* lut() { static const struct L { uint8_t v[256]; L() { memset(v, 0x80, 256); v['A'] = 0; v['C'] = 1; v['G'] = 2; v['T'] = 3; } } T; return T.v; }
+    uint8_t code(int32_t j) const { return lut()[seq[j]]; }
+    uint8_t ascii(int32_t j) const { return seq[j]; }
+};
+struct BamBases {                       // BAM's own encoding: two bases per byte, high nibble first, =ACMGRSVTWYHKDBN
+    const uint8_t* seq4;
+    uint8_t nib(int32_t j) const { return (uint8_t)((seq4[j >> 1] >> ((~j & 1) << 2)) & 15); }
+    uint8_t code(int32_t j) const { static const uint8_t C4[16] = {0x80, 0, 1, 0x80, 2, 0x80, 0x80, 0x80, 3, 0x80, 0x80, 0x80, 0x80, 0x80, 0x80, 0x80}; return C4[nib(j)]; }
+    uint8_t ascii(int32_t j) const { return (uint8_t)"=ACMGRSVTWYHKDBN"[nib(j)]; }
+};
+template <class BASES>
+int packer_add(pb_packer* p, int32_t pos, int32_t tlen, int32_t mapq, uint32_t flags, const uint32_t* cigar, int32_t n_cigar,
+               const BASES& B, const uint8_t* qual, int32_t read_len) {
     if (!p || read_len < 0 || n_cigar < 0) return fail(PB_ERR_INVALID, "bad argument");
     const size_t off = p->quals.size();
     const size_t padded = ((size_t)read_len + 3) & ~(size_t)3;
@@ -1260,19 +1276,44 @@ extern "C" int pb_packer_add(pb_packer* p, int32_t pos, int32_t tlen, int32_t ma
     p->seq_off.push_back((uint32_t)off);
     p->quals.resize(off + padded, 0);
     p->bases2.resize((off + padded) / 4, 0);
-    for (int32_t j = 0; j < read_len; j++) {
-        const uint8_t c = seq[j];
-        const int code = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
-        const uint8_t q = hasq ? qual[j] : 0;
-        const size_t i = off + (size_t)j;
-        if (code < 0 || q >= 128) {
-            p->quals[i] = 0x80;
-            p->exc_idx.push_back((uint32_t)i); p->exc_base.push_back(c); p->exc_qual.push_back(q);
-        } else p->quals[i] = q;
-        p->note(p->quals[i]);
-        if (code > 0) p->bases2[i >> 2] |= (uint8_t)(code << (2 * (i & 3)));
+    // four bases per step: one bases2 byte, four quality bytes; anything irregular (a letter that is not exactly A/C/G/T, a
+    // quality byte >= 128) takes the base-by-base path for that group of four
+    uint8_t* const qo = p->quals.data() + off;
+    uint8_t* const bo = p->bases2.data() + off / 4;               // `off` is a multiple of 4
+    auto slow = [&](int32_t j) {
+        const uint8_t code = B.code(j), q = hasq ? qual[j] : 0;
+        if ((code | q) & 0x80) {
+            qo[j] = 0x80;
+            p->exc_idx.push_back((uint32_t)(off + (size_t)j)); p->exc_base.push_back(B.ascii(j)); p->exc_qual.push_back(q);
+        } else qo[j] = q;
+        if (!(code & 0x80)) bo[j >> 2] |= (uint8_t)(code << (2 * (j & 3)));      // (a plain letter keeps its code even when its quality is an exception)
+        if (p->code_of[qo[j]] == 0xFF) p->note(qo[j]);
+    };
+    int32_t j = 0;
+    for (; j + 4 <= read_len; j += 4) {
+        const uint8_t c0 = B.code(j), c1 = B.code(j + 1), c2 = B.code(j + 2), c3 = B.code(j + 3);
+        uint8_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+        if (hasq) { q0 = qual[j]; q1 = qual[j + 1]; q2 = qual[j + 2]; q3 = qual[j + 3]; }
+        if ((c0 | c1 | c2 | c3 | q0 | q1 | q2 | q3) & 0x80) { slow(j); slow(j + 1); slow(j + 2); slow(j + 3); continue; }
+        bo[j >> 2] = (uint8_t)(c0 | (c1 << 2) | (c2 << 4) | (c3 << 6));
+        qo[j] = q0; qo[j + 1] = q1; qo[j + 2] = q2; qo[j + 3] = q3;
+        if ((p->code_of[q0] | p->code_of[q1] | p->code_of[q2] | p->code_of[q3]) == 0xFF) { p->note(q0); p->note(q1); p->note(q2); p->note(q3); }
     }
+    for (; j < read_len; j++) slow(j);
     return PB_OK;
+}
+}  // namespace
+
+extern "C" int pb_packer_add(pb_packer* p, int32_t pos, int32_t tlen, int32_t mapq, uint32_t flags,
+                             const uint32_t* cigar, int32_t n_cigar, const uint8_t* seq, const uint8_t* qual, int32_t read_len) {
+    if (read_len > 0 && !seq) return fail(PB_ERR_INVALID, "bad argument");
+    return packer_add(p, pos, tlen, mapq, flags, cigar, n_cigar, AsciiBases{seq}, qual, read_len);
+}
+
+extern "C" int pb_packer_add_bam(pb_packer* p, int32_t pos, int32_t tlen, int32_t mapq, uint32_t flags,
+                                 const uint32_t* cigar, int32_t n_cigar, const uint8_t* seq4, const uint8_t* qual, int32_t read_len) {
+    if (read_len > 0 && !seq4) return fail(PB_ERR_INVALID, "bad argument");
+    return packer_add(p, pos, tlen, mapq, flags, cigar, n_cigar, BamBases{seq4}, qual, read_len);
 }
 
 extern "C" int pb_packer_add_many(pb_packer* p, int64_t n, const int32_t* pos, const int32_t* tlen, const uint8_t* mapq,
@@ -1302,11 +1343,24 @@ extern "C" int pb_packer_view(pb_packer* p, pb_batch* b) {
         const size_t ns = p->quals.size();
         const int bits = p->n_codes <= 8 ? 3 : 4;
         p->qual_codes.assign((ns * bits + 7) / 8 + 32, 0);
-        for (size_t i = 0; i < ns; i++) {
+        const uint8_t* q = p->quals.data();
+        uint8_t* o = p->qual_codes.data();
+        size_t i = 0;
+        if (bits == 3) {
+            for (; i + 8 <= ns; i += 8) {                // eight codes -> three bytes
+                uint32_t v = 0;
+                for (int t = 0; t < 8; t++) v |= (uint32_t)p->code_of[q[i + t]] << (3 * t);
+                uint8_t* d = o + 3 * (i >> 3);
+                d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16);
+            }
+        } else {
+            for (; i + 2 <= ns; i += 2) o[i >> 1] = (uint8_t)(p->code_of[q[i]] | (p->code_of[q[i + 1]] << 4));
+        }
+        for (; i < ns; i++) {
             const uint32_t c = p->code_of[p->quals[i]];
             const size_t bit = i * bits;
-            p->qual_codes[bit >> 3] |= (uint8_t)(c << (bit & 7));
-            if ((bit & 7) + bits > 8) p->qual_codes[(bit >> 3) + 1] |= (uint8_t)(c >> (8 - (bit & 7)));
+            o[bit >> 3] |= (uint8_t)(c << (bit & 7));
+            if ((bit & 7) + bits > 8) o[(bit >> 3) + 1] |= (uint8_t)(c >> (8 - (bit & 7)));
         }
         b->qual_codes = p->qual_codes.data(); b->qual_code_bits = bits; memcpy(b->qual_lut, p->lut, 16);
     }
