@@ -774,10 +774,21 @@ def from_bam_leg(args, wl, regions, local):
             eng.finish(res)
             with lock:
                 got[0] += int(res.c.aligned_bases)
+    def one_pass():
+        order[:] = list(range(len(sample)))
+        ts = [threading.Thread(target=work, args=(s,)) for s in range(nthreads)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+    big = max(range(len(sample)), key=lambda k: sample[k].aligned)
+    for slot in range(nthreads):                 # warm-up: every engine, packer and BAM handle takes the largest region once
+        order[:] = [big]
+        work(slot)
+    rounds = 3
+    t_ingest[:] = [0.0] * nthreads
+    got[0] = 0
     t0 = time.perf_counter()
-    ts = [threading.Thread(target=work, args=(s,)) for s in range(nthreads)]
-    [t.start() for t in ts]
-    [t.join() for t in ts]
+    for _ in range(rounds):
+        one_pass()
     dt = time.perf_counter() - t0
     for eng, _, bams in slots:
         eng.close()
@@ -785,9 +796,11 @@ def from_bam_leg(args, wl, regions, local):
     for p, _ in paths:
         os.remove(p); os.remove(p + ".bai")
     os.rmdir(tmp)
-    return {"value": got[0] / dt, "unit": UNIT, "regions": len(sample), "aligned_bases": got[0], "bam_bytes": bam_bytes,
-            "host_threads": nthreads, "seconds": dt, "ingest_seconds_per_thread": sum(t_ingest) / nthreads,
-            "note": "BGZF inflate + BAM decode + packing are inside the timed region (zlib, one stream per host thread)"}
+    return {"value": got[0] / dt, "unit": UNIT, "regions": len(sample), "passes": rounds, "aligned_bases": got[0] // rounds, "bam_bytes": bam_bytes,
+            "host_threads": nthreads, "inflate_threads_per_query": 4, "seconds_per_pass": dt / rounds,
+            "ingest_seconds_per_thread_per_pass": sum(t_ingest) / nthreads / rounds,
+            "note": "BGZF inflate + BAM decode + packing are inside the timed region (zlib; a read-ahead window of blocks inflated by 4 threads per "
+                    "query); the packed batches are uploaded from pageable memory; engines warmed with one untimed region each"}
 
 
 
